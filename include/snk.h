@@ -1,0 +1,183 @@
+/* snk.h -- C ABI of the B200-native batched Snake-v1 step path (libsnk.so).
+ *
+ * The reference (tranthai189765/MARL-Snake, a fork of kc-ml2/marlenv) is pure
+ * Python and has no FFI for this path: its boundary is the gym.Env protocol of
+ * `SnakeEnv` reached through `make_snake` / `gym.make('Snake-v1')`.  Every entry
+ * point below states the reference interface it stands in for (paths relative to
+ * /root/reference/marlenv/marlenv/).  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only, no torch types.  Every call
+ * returns 0 on success or a negative SNK_E_* code; snk_last_error() gives the
+ * message for the calling thread.  Pointers named *_dev are CUDA device pointers
+ * on the handle's device, *_host are host pointers.  `stream` is a cudaStream_t
+ * passed as void* (NULL = legacy default stream); device-pointer calls only
+ * enqueue work on it and never synchronise.  A handle is not thread-safe.
+ *
+ * Batched layouts (N = num_envs, ns = num_snakes, oh x ow = observation window):
+ *   actions  uint8  [N, ns]             0 keep, 1 turn left, 2 turn right
+ *   obs      uint8  [N, ns, oh, ow, 8*frame_stack]   NHWC, values 0/1, frames oldest->newest
+ *   rewards  double [N, ns]
+ *   dones    uint8  [N, ns]
+ */
+#ifndef SNK_H_
+#define SNK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNK_ABI_VERSION 1
+
+enum {
+  SNK_OK = 0,
+  SNK_E_INVALID = -1,   /* bad argument / unsupported configuration            */
+  SNK_E_CUDA = -2,      /* a CUDA runtime call failed                          */
+  SNK_E_NOMEM = -3,
+  SNK_E_STATE = -4      /* call not valid in the handle's current mode         */
+};
+
+/* sticky per-handle device error bits, read with snk_device_errors() */
+enum {
+  SNK_DEV_BAD_ACTION = 1,        /* action outside {0,1,2} (reference: KeyError, snake_env.py:606)   */
+  SNK_DEV_REPLAY_UNDERRUN = 2,   /* replay stream exhausted                                         */
+  SNK_DEV_REPLAY_RANGE = 4,      /* replayed draw out of range / replayed spawn overlaps            */
+  SNK_DEV_SPAWN_GIVEUP = 8       /* no overlap-free spawn found within the attempt cap               */
+};
+
+enum { SNK_RNG_PHILOX = 0, SNK_RNG_REPLAY = 1 };
+
+/* Constructor arguments of SnakeEnv.__init__ (envs/snake_env.py:58-88) plus batching. */
+typedef struct snk_config {
+  int32_t abi_version;        /* must be SNK_ABI_VERSION                                   */
+  int32_t device;             /* CUDA device ordinal                                        */
+  int32_t num_envs;           /* N: environments resident on this device                   */
+  int32_t height, width;      /* grid_shape, walls included (snake_env.py:60-61)           */
+  int32_t num_snakes;         /* 1..25 (cell code 10*idx+type must fit uint8)               */
+  int32_t snake_length;       /* initial length, 2..25 (snake_env.py:63)                    */
+  int32_t vision_range;       /* 0 = full-grid observation (None / 0 in the reference)     */
+  int32_t frame_stack;        /* >= 1 (snake_env.py:65)                                     */
+  int32_t num_fruits;         /* <0: int(round(0.8*num_snakes)) (snake_env.py:87-88); <=32 */
+  int32_t auto_reset;         /* 1: reset an env inside the step that ends it and return
+                                 the reset observation (wrappers.py:138-146)                */
+  int32_t done_mode;          /* 0: all(dones) ends the episode (snake_env.py:416);
+                                 1: any(dones) (coop_snake_env.py:14-22)                    */
+  int32_t rng_mode;           /* SNK_RNG_PHILOX or SNK_RNG_REPLAY                           */
+  int32_t reserved0;
+  uint64_t seed;              /* Philox key                                                 */
+  uint64_t env_id_offset;     /* global id of env 0: streams are keyed by global env id so a
+                                 sharded run equals the single-device run                   */
+  double max_episode_steps;   /* episode_length >= this forces all dones (snake_env.py:393)*/
+  double reward_fruit, reward_kill, reward_lose, reward_win, reward_time;   /* :46-52      */
+} snk_config;
+
+typedef struct snk_env snk_env;   /* opaque handle: one shard of environments on one GPU */
+
+/* Optional per-step outputs; any pointer may be NULL.  Device pointers. */
+typedef struct snk_step_extra {
+  uint8_t* finished;          /* [N]     1 where the episode ended this step (info emitted, :396) */
+  int32_t* rank;              /* [N, ns] info['rank'] of envs with finished=1 (:397-404)          */
+  double*  episode_scores;    /* [N, ns] info['episode_scores'] (:407)                            */
+  int32_t* episode_steps;     /* [N, ns] info['episode_steps']  (integral in the reference)       */
+  int32_t* episode_fruits;    /* [N, ns] info['episode_fruits']                                   */
+  int32_t* episode_kills;     /* [N, ns] info['episode_kills']                                    */
+} snk_step_extra;
+
+/* Full environment state, the parity interface (reference: SnakeEnv.grid, .snakes[i].coords /
+ * .direction / .alive, .alive_snakes, .episode_length).  Device pointers, any may be NULL.  */
+typedef struct snk_state_view {
+  uint8_t* grid;              /* [N, H*W]  cell codes type + 10*owner (core/snake.py:5-11)   */
+  int32_t* head;              /* [N, ns]   flat cell index r*W+c, -1 for dead snakes          */
+  int32_t* tail;              /* [N, ns]                                                      */
+  int32_t* length;            /* [N, ns]   0 for dead snakes                                  */
+  uint8_t* dir;               /* [N, ns]   0 UP 1 RIGHT 2 DOWN 3 LEFT (core/snake.py:33-37)   */
+  uint8_t* alive;             /* [N, ns]                                                      */
+  int32_t* alive_counter;     /* [N]       SnakeEnv.alive_snakes (signed, drifts: :334-345)   */
+  int32_t* episode_length;    /* [N]                                                          */
+  int32_t* cells;             /* [N, ns, max_cells] head-first body cells, -1 padded          */
+  int32_t  max_cells;
+} snk_state_view;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+
+/* SnakeEnv.__init__ for N environments (snake_env.py:58-129) + make_snake batching (wrappers.py:203-223).
+ * Builds the spawn-candidate table (core/grid_util.py:73-115) and allocates all device state. */
+int snk_create(const snk_config* cfg, snk_env** out);
+/* SnakeEnv.close (snake_env.py:298) */
+int snk_destroy(snk_env* env);
+const char* snk_last_error(void);
+int snk_abi_version(void);
+
+/* observation_space.shape (snake_env.py:115-129): out[4] = {ns, oh, ow, 8*frame_stack} */
+int snk_obs_shape(const snk_env* env, int32_t out[4]);
+size_t snk_obs_bytes(const snk_env* env);       /* N * prod(shape) */
+int snk_num_envs(const snk_env* env);
+/* bytes the step kernel must move per env-step (state read+write, history, obs, I/O): the
+ * algorithmic-traffic figure bench.py uses for the roofline. */
+size_t snk_algorithmic_bytes_per_env_step(const snk_env* env);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+
+/* SnakeEnv.reset (snake_env.py:131-159) for every env, or for envs with mask_dev[e] != 0.
+ * Writes the initial stacked observation of the reset envs into obs_dev (NULL = skip). */
+int snk_reset(snk_env* env, const uint8_t* mask_dev, uint8_t* obs_dev, void* stream);
+
+/* SnakeEnv.step (snake_env.py:301-414) for all N envs, with the vector worker's auto-reset
+ * (wrappers.py:138-146) when cfg.auto_reset.  One kernel launch on `stream`. */
+int snk_step(snk_env* env, const uint8_t* actions_dev, uint8_t* obs_dev, double* rewards_dev,
+             uint8_t* dones_dev, const snk_step_extra* extra, void* stream);
+
+/* Same call with HOST buffers (the reference's step() takes and returns host objects): copies
+ * actions in, steps, copies obs / rewards / dones out and synchronises.  Pinned buffers make the
+ * copies asynchronous to the host until the final synchronise.  obs_host may be NULL. */
+int snk_step_host(snk_env* env, const uint8_t* actions_host, uint8_t* obs_host,
+                  double* rewards_host, uint8_t* dones_host);
+int snk_reset_host(snk_env* env, uint8_t* obs_host);
+
+/* ---- parity / checkpoint interface ---------------------------------------------------------- */
+
+int snk_get_state(snk_env* env, const snk_state_view* out, void* stream);
+/* Needs grid, alive, dir, cells(+max_cells), length, alive_counter, episode_length. Rebuilds the
+ * body-direction plane, zeroes episode statistics, fills every frame-stack slot with the encoding
+ * of the given grid.  obs_dev (may be NULL) receives that stacked observation. */
+int snk_set_state(snk_env* env, const snk_state_view* in, uint8_t* obs_dev, void* stream);
+
+/* Replay mode: per-env streams of recorded draw OUTPUTS in consumption order -- per reset the ns
+ * accepted spawn-candidate indices (np.random.permutation, snake_env.py:581) then the fruit ranks
+ * (np.random.randint, grid_util.py:130); per step its fruit ranks.  draws_host holds all streams
+ * back to back, offsets_host[e]..offsets_host[e+1] delimits env e (N+1 entries).  Resets cursors. */
+int snk_set_replay(snk_env* env, const int32_t* draws_host, const int64_t* offsets_host);
+int snk_replay_cursors(snk_env* env, int32_t* cursors_host /* [N] */);
+
+/* Sticky device error bits (SNK_DEV_*); synchronises the device. `clear` != 0 resets them. */
+int snk_device_errors(snk_env* env, uint32_t* bits, int clear);
+
+/* ---- rollout statistics (end-of-rollout allreduce payload) ----------------------------------- */
+enum {
+  SNK_STAT_EPISODES = 0,   /* episodes ended                                  */
+  SNK_STAT_RETURN,         /* sum over ended episodes and snakes of episode_scores */
+  SNK_STAT_EP_STEPS,       /* sum of episode lengths (env steps)              */
+  SNK_STAT_FRUITS,         /* sum of episode_fruits                           */
+  SNK_STAT_KILLS,          /* sum of episode_kills                            */
+  SNK_STAT_DEATHS,         /* snakes that died                                */
+  SNK_STAT_ENV_STEPS,      /* env steps executed                              */
+  SNK_STAT_COUNT = 8
+};
+/* Device pointer to SNK_STAT_COUNT doubles accumulated on device (for an in-place NCCL allreduce). */
+int snk_stats_dev(snk_env* env, double** stats_dev);
+int snk_stats(snk_env* env, double* out_host /* [SNK_STAT_COUNT] */, int clear);
+
+/* ---- spawn table (host only, no GPU needed) -------------------------------------------------- */
+
+/* Number of spawn poses dfs_sweep_empty enumerates on the empty walled grid (grid_util.py:73-99). */
+int64_t snk_spawn_count(int32_t height, int32_t width, int32_t snake_length);
+/* Writes them, in the reference's order, as flat cell indices [count, snake_length], head first. */
+int snk_spawn_cells(int32_t height, int32_t width, int32_t snake_length, int32_t* out, int64_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNK_H_ */

@@ -1,0 +1,345 @@
+// snk_api.cu -- the C ABI declared in include/snk.h.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "../../include/snk.h"
+#include "snk_kernels.h"
+
+using namespace snk;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return fail(SNK_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+struct snk_env {
+  Dims d;
+  int device = 0;
+  int tile_envs = 0, threads = 0;
+  size_t smem_bytes = 0;
+  uint8_t* recs = nullptr;
+  uint8_t* hist = nullptr;
+  uint64_t* spawn = nullptr;
+  int32_t* replay = nullptr;
+  int64_t* replay_off = nullptr;
+  uint32_t* err = nullptr;
+  double* stats = nullptr;
+  // device mirrors used by the *_host entry points
+  uint8_t* h_actions = nullptr; uint8_t* h_obs = nullptr; double* h_rew = nullptr; uint8_t* h_done = nullptr;
+  cudaStream_t own_stream = nullptr;
+  double env_steps = 0.0;
+  bool was_reset = false;
+};
+
+extern "C" const char* snk_last_error(void) { return g_err; }
+extern "C" int snk_abi_version(void) { return SNK_ABI_VERSION; }
+
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+static KParams base_params(const snk_env* h) {
+  KParams p;
+  memset(&p, 0, sizeof p);
+  p.d = h->d;
+  p.recs = h->recs; p.hist = h->hist; p.spawn = h->spawn;
+  p.replay = h->replay; p.replay_off = h->replay_off;
+  p.err = h->err; p.stats = h->stats;
+  p.E = h->tile_envs;
+  return p;
+}
+
+extern "C" int snk_create(const snk_config* c, snk_env** out) {
+  if (!c || !out) return fail(SNK_E_INVALID, "null argument");
+  if (c->abi_version != SNK_ABI_VERSION) return fail(SNK_E_INVALID, "abi_version %d != %d", c->abi_version, SNK_ABI_VERSION);
+  if (c->num_envs < 1) return fail(SNK_E_INVALID, "num_envs must be >= 1");
+  if (c->num_snakes < 1 || c->num_snakes > MAX_SNAKES) return fail(SNK_E_INVALID, "num_snakes must be in 1..%d", MAX_SNAKES);
+  if (c->snake_length < 2 || c->snake_length > MAX_SNAKE_LENGTH) return fail(SNK_E_INVALID, "snake_length must be in 2..%d", MAX_SNAKE_LENGTH);
+  if (c->height < 4 || c->width < 4 || (int64_t)c->height * c->width > 65535) return fail(SNK_E_INVALID, "grid must be at least 4x4 and at most 65535 cells");
+  if (c->vision_range < 0 || c->frame_stack < 1 || c->frame_stack > 64) return fail(SNK_E_INVALID, "bad vision_range / frame_stack");
+  if (c->rng_mode != SNK_RNG_PHILOX && c->rng_mode != SNK_RNG_REPLAY) return fail(SNK_E_INVALID, "bad rng_mode");
+  int nfruits = c->num_fruits < 0 ? (int)nearbyint(c->num_snakes * 0.8) : c->num_fruits;   // snake_env.py:87-88
+  if (nfruits > MAX_FRUIT_DRAWS) return fail(SNK_E_INVALID, "num_fruits must be <= %d", MAX_FRUIT_DRAWS);
+
+  snk_env* h = new (std::nothrow) snk_env();
+  if (!h) return fail(SNK_E_NOMEM, "out of host memory");
+  Dims& d = h->d;
+  memset(&d, 0, sizeof d);
+  d.N = c->num_envs; d.H = c->height; d.W = c->width; d.ns = c->num_snakes; d.K = c->snake_length;
+  d.V = c->vision_range; d.fs = c->frame_stack; d.nfruits = nfruits;
+  d.auto_reset = c->auto_reset ? 1 : 0; d.done_mode = c->done_mode ? 1 : 0; d.rng_mode = c->rng_mode;
+  d.seed_lo = (uint32_t)c->seed; d.seed_hi = (uint32_t)(c->seed >> 32);
+  d.env_off_lo = (uint32_t)c->env_id_offset; d.env_off_hi = (uint32_t)(c->env_id_offset >> 32);
+  d.r_fruit = c->reward_fruit; d.r_kill = c->reward_kill; d.r_lose = c->reward_lose;
+  d.r_win = c->reward_win; d.r_time = c->reward_time; d.max_steps = c->max_episode_steps;
+  finalize_layout(d);
+  h->device = c->device;
+
+  // spawn table (host) -- core/grid_util.py:73-115
+  const int64_t n_cand = spawn_enumerate(d.H, d.W, d.K, nullptr, nullptr, 0);
+  if (n_cand < d.ns) { delete h; return fail(SNK_E_INVALID, "only %lld spawn poses for %d snakes", (long long)n_cand, c->num_snakes); }
+  if (n_cand > 0x7fffffff) { delete h; return fail(SNK_E_INVALID, "spawn table too large"); }
+  std::vector<uint64_t> table((size_t)n_cand);
+  spawn_enumerate(d.H, d.W, d.K, table.data(), nullptr, n_cand);
+  d.n_cand = (uint32_t)n_cand;
+
+  // tile shape: environments per CTA sized for ~40 KB of shared memory, threads per CTA
+  const size_t per_env = (size_t)d.rec_bytes + d.stage_env_bytes + d.scr_bytes + 2;
+  int E = (int)((size_t)env_int("SNK_TILE_SMEM", 40 * 1024) / per_env);
+  if (E > 64) E = 64;
+  if (E > 2) E &= ~1;
+  if (E < 1) E = 1;
+  E = env_int("SNK_TILE_ENVS", E);
+  int threads = env_int("SNK_THREADS", 256);
+  if (threads < 32 || threads > SNK_MAX_THREADS || (threads & 31)) { delete h; return fail(SNK_E_INVALID, "SNK_THREADS must be a multiple of 32 in 32..%d", SNK_MAX_THREADS); }
+  if (E < 1 || E > threads) { delete h; return fail(SNK_E_INVALID, "SNK_TILE_ENVS must be in 1..threads"); }
+  h->tile_envs = E; h->threads = threads;
+  h->smem_bytes = (size_t)E * d.rec_bytes + (size_t)round_up(E * d.stage_env_bytes, 16) + (size_t)E * d.scr_bytes + 2 * (size_t)E + 16;
+  if (h->smem_bytes > 227 * 1024) {
+    const size_t need = h->smem_bytes;
+    delete h;
+    return fail(SNK_E_INVALID, "configuration needs %zu bytes of shared memory per tile", need);
+  }
+
+  cudaError_t e = cudaSetDevice(c->device);
+  if (e != cudaSuccess) { delete h; return fail(SNK_E_CUDA, "cudaSetDevice(%d): %s", c->device, cudaGetErrorString(e)); }
+#define CUH(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { int rc = fail(SNK_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); snk_destroy(h); return rc; } } while (0)
+  CUH(cudaMalloc(&h->recs, (size_t)d.N * d.rec_bytes));
+  if (d.hist_env_bytes) CUH(cudaMalloc(&h->hist, (size_t)d.N * d.hist_env_bytes));
+  CUH(cudaMalloc(&h->spawn, table.size() * sizeof(uint64_t)));
+  CUH(cudaMalloc(&h->err, sizeof(uint32_t)));
+  CUH(cudaMalloc(&h->stats, STAT_COUNT * sizeof(double)));
+  CUH(cudaMalloc(&h->replay_off, ((size_t)d.N + 1) * sizeof(int64_t)));
+  CUH(cudaMemcpy(h->spawn, table.data(), table.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  CUH(cudaMemset(h->err, 0, sizeof(uint32_t)));
+  CUH(cudaMemset(h->stats, 0, STAT_COUNT * sizeof(double)));
+  CUH(cudaMemset(h->replay_off, 0, ((size_t)d.N + 1) * sizeof(int64_t)));
+  if (d.hist_env_bytes) CUH(cudaMemset(h->hist, 0, (size_t)d.N * d.hist_env_bytes));
+  CUH(launch_init_records(d, h->recs, nullptr));
+  CUH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  CUH(cudaDeviceSynchronize());
+#undef CUH
+  *out = h;
+  return SNK_OK;
+}
+
+extern "C" int snk_destroy(snk_env* h) {
+  if (!h) return SNK_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->recs); cudaFree(h->hist); cudaFree(h->spawn); cudaFree(h->replay); cudaFree(h->replay_off);
+  cudaFree(h->err); cudaFree(h->stats);
+  cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_rew); cudaFree(h->h_done);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return SNK_OK;
+}
+
+extern "C" int snk_obs_shape(const snk_env* h, int32_t out[4]) {
+  if (!h || !out) return fail(SNK_E_INVALID, "null argument");
+  out[0] = h->d.ns; out[1] = h->d.oh; out[2] = h->d.ow; out[3] = 8 * h->d.fs;
+  return SNK_OK;
+}
+extern "C" size_t snk_obs_bytes(const snk_env* h) { return h ? (size_t)h->d.N * h->d.obs_env_bytes : 0; }
+extern "C" int snk_num_envs(const snk_env* h) { return h ? h->d.N : 0; }
+
+extern "C" size_t snk_algorithmic_bytes_per_env_step(const snk_env* h) {
+  if (!h) return 0;
+  const Dims& d = h->d;
+  // state record read + write, frame history (read fs-1 rows, write 1), observation write,
+  // actions in, rewards (f64) and dones out.
+  size_t b = 2 * (size_t)d.rec_bytes + (size_t)d.obs_env_bytes + (size_t)d.ns * (1 + 8 + 1);
+  if (d.fs > 1) b += (size_t)d.ns * d.fs * d.ohw;
+  return b;
+}
+
+static int check_vec16(const snk_env* h, const uint8_t* obs) {
+  if (!obs) return 0;
+  return (((uintptr_t)obs & 15) == 0 && ((size_t)h->tile_envs * h->d.obs_env_bytes) % 16 == 0) ? 1 : 0;
+}
+
+extern "C" int snk_reset(snk_env* h, const uint8_t* mask_dev, uint8_t* obs_dev, void* stream) {
+  if (!h) return fail(SNK_E_INVALID, "null handle");
+  if (obs_dev && ((uintptr_t)obs_dev & 7)) return fail(SNK_E_INVALID, "obs must be 8-byte aligned");
+  CU(cudaSetDevice(h->device));
+  KParams p = base_params(h);
+  p.mode = MODE_RESET; p.mask = mask_dev; p.obs = obs_dev;
+  CU(launch_tile_kernel(p, h->threads, h->smem_bytes, (cudaStream_t)stream));
+  h->was_reset = true;
+  return SNK_OK;
+}
+
+extern "C" int snk_step(snk_env* h, const uint8_t* actions_dev, uint8_t* obs_dev, double* rewards_dev,
+                        uint8_t* dones_dev, const snk_step_extra* x, void* stream) {
+  if (!h) return fail(SNK_E_INVALID, "null handle");
+  if (!actions_dev || !rewards_dev || !dones_dev) return fail(SNK_E_INVALID, "actions, rewards and dones are required");
+  if (!h->was_reset) return fail(SNK_E_STATE, "step before reset");
+  if (obs_dev && ((uintptr_t)obs_dev & 7)) return fail(SNK_E_INVALID, "obs must be 8-byte aligned");
+  if ((uintptr_t)rewards_dev & 7) return fail(SNK_E_INVALID, "rewards must be 8-byte aligned");
+  KParams p = base_params(h);
+  p.mode = MODE_STEP;
+  p.actions = actions_dev; p.obs = obs_dev; p.rew = rewards_dev; p.done = dones_dev;
+  if (x) {
+    p.fin = x->finished; p.rank = x->rank; p.ep_scores = x->episode_scores;
+    p.ep_steps = x->episode_steps; p.ep_fruits = x->episode_fruits; p.ep_kills = x->episode_kills;
+  }
+  p.vec16 = check_vec16(h, obs_dev);
+  CU(launch_tile_kernel(p, h->threads, h->smem_bytes, (cudaStream_t)stream));
+  h->env_steps += (double)h->d.N;
+  return SNK_OK;
+}
+
+static int ensure_mirrors(snk_env* h) {
+  const Dims& d = h->d;
+  if (!h->h_actions) CU(cudaMalloc(&h->h_actions, (size_t)d.N * d.ns));
+  if (!h->h_obs) CU(cudaMalloc(&h->h_obs, (size_t)d.N * d.obs_env_bytes));
+  if (!h->h_rew) CU(cudaMalloc(&h->h_rew, (size_t)d.N * d.ns * sizeof(double)));
+  if (!h->h_done) CU(cudaMalloc(&h->h_done, (size_t)d.N * d.ns));
+  return SNK_OK;
+}
+
+extern "C" int snk_step_host(snk_env* h, const uint8_t* actions_host, uint8_t* obs_host,
+                             double* rewards_host, uint8_t* dones_host) {
+  if (!h) return fail(SNK_E_INVALID, "null handle");
+  if (!actions_host || !rewards_host || !dones_host) return fail(SNK_E_INVALID, "actions, rewards and dones are required");
+  CU(cudaSetDevice(h->device));
+  int rc = ensure_mirrors(h);
+  if (rc) return rc;
+  const Dims& d = h->d;
+  cudaStream_t s = h->own_stream;
+  CU(cudaMemcpyAsync(h->h_actions, actions_host, (size_t)d.N * d.ns, cudaMemcpyHostToDevice, s));
+  rc = snk_step(h, h->h_actions, obs_host ? h->h_obs : nullptr, h->h_rew, h->h_done, nullptr, s);
+  if (rc) return rc;
+  if (obs_host) CU(cudaMemcpyAsync(obs_host, h->h_obs, (size_t)d.N * d.obs_env_bytes, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(rewards_host, h->h_rew, (size_t)d.N * d.ns * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(dones_host, h->h_done, (size_t)d.N * d.ns, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return SNK_OK;
+}
+
+extern "C" int snk_reset_host(snk_env* h, uint8_t* obs_host) {
+  if (!h) return fail(SNK_E_INVALID, "null handle");
+  CU(cudaSetDevice(h->device));
+  int rc = ensure_mirrors(h);
+  if (rc) return rc;
+  cudaStream_t s = h->own_stream;
+  rc = snk_reset(h, nullptr, obs_host ? h->h_obs : nullptr, s);
+  if (rc) return rc;
+  if (obs_host) CU(cudaMemcpyAsync(obs_host, h->h_obs, (size_t)h->d.N * h->d.obs_env_bytes, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return SNK_OK;
+}
+
+static StateView to_view(const snk_state_view* v) {
+  StateView s;
+  s.grid = v->grid; s.head = v->head; s.tail = v->tail; s.length = v->length; s.dir = v->dir; s.alive = v->alive;
+  s.alive_counter = v->alive_counter; s.episode_length = v->episode_length; s.cells = v->cells; s.max_cells = v->max_cells;
+  return s;
+}
+
+extern "C" int snk_get_state(snk_env* h, const snk_state_view* out, void* stream) {
+  if (!h || !out) return fail(SNK_E_INVALID, "null argument");
+  if (out->cells && out->max_cells < 1) return fail(SNK_E_INVALID, "max_cells must be >= 1 when cells is given");
+  CU(cudaSetDevice(h->device));
+  CU(launch_get_state(h->d, h->recs, to_view(out), (cudaStream_t)stream));
+  return SNK_OK;
+}
+
+extern "C" int snk_set_state(snk_env* h, const snk_state_view* in, uint8_t* obs_dev, void* stream) {
+  if (!h || !in) return fail(SNK_E_INVALID, "null argument");
+  if (!in->grid || !in->alive || !in->dir || !in->cells || !in->length || !in->alive_counter || !in->episode_length || in->max_cells < 2)
+    return fail(SNK_E_INVALID, "set_state needs grid, alive, dir, cells, length, alive_counter, episode_length");
+  if (obs_dev && ((uintptr_t)obs_dev & 7)) return fail(SNK_E_INVALID, "obs must be 8-byte aligned");
+  CU(cudaSetDevice(h->device));
+  CU(launch_set_state(h->d, h->recs, to_view(in), (cudaStream_t)stream));
+  KParams p = base_params(h);
+  p.mode = MODE_ENCODE; p.obs = obs_dev;
+  CU(launch_tile_kernel(p, h->threads, h->smem_bytes, (cudaStream_t)stream));
+  h->was_reset = true;
+  return SNK_OK;
+}
+
+extern "C" int snk_set_replay(snk_env* h, const int32_t* draws_host, const int64_t* offsets_host) {
+  if (!h || !offsets_host) return fail(SNK_E_INVALID, "null argument");
+  if (h->d.rng_mode != RNG_REPLAY) return fail(SNK_E_STATE, "handle was not created with SNK_RNG_REPLAY");
+  CU(cudaSetDevice(h->device));
+  const int N = h->d.N;
+  const int64_t total = offsets_host[N];
+  if (offsets_host[0] != 0 || total < 0) return fail(SNK_E_INVALID, "offsets must start at 0 and be non-decreasing");
+  for (int e = 0; e < N; ++e) if (offsets_host[e + 1] < offsets_host[e]) return fail(SNK_E_INVALID, "offsets must be non-decreasing");
+  CU(cudaDeviceSynchronize());
+  cudaFree(h->replay); h->replay = nullptr;
+  CU(cudaMalloc(&h->replay, (size_t)(total > 0 ? total : 1) * sizeof(int32_t)));
+  if (total > 0) {
+    if (!draws_host) return fail(SNK_E_INVALID, "null draws");
+    CU(cudaMemcpy(h->replay, draws_host, (size_t)total * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  CU(cudaMemcpy(h->replay_off, offsets_host, ((size_t)N + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+  // cursors live in the records: zero them
+  CU(cudaMemset2D(h->recs + h->d.off_hdr + offsetof(EnvHdr, cursor), (size_t)h->d.rec_bytes, 0, sizeof(uint32_t), (size_t)N));
+  return SNK_OK;
+}
+
+extern "C" int snk_replay_cursors(snk_env* h, int32_t* cursors_host) {
+  if (!h || !cursors_host) return fail(SNK_E_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy2D(cursors_host, sizeof(int32_t), h->recs + h->d.off_hdr + offsetof(EnvHdr, cursor), (size_t)h->d.rec_bytes,
+                  sizeof(int32_t), (size_t)h->d.N, cudaMemcpyDeviceToHost));
+  return SNK_OK;
+}
+
+extern "C" int snk_device_errors(snk_env* h, uint32_t* bits, int clear) {
+  if (!h || !bits) return fail(SNK_E_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(bits, h->err, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (clear) CU(cudaMemset(h->err, 0, sizeof(uint32_t)));
+  return SNK_OK;
+}
+
+extern "C" int snk_stats_dev(snk_env* h, double** stats_dev) {
+  if (!h || !stats_dev) return fail(SNK_E_INVALID, "null argument");
+  *stats_dev = h->stats;
+  return SNK_OK;
+}
+
+extern "C" int snk_stats(snk_env* h, double* out_host, int clear) {
+  if (!h || !out_host) return fail(SNK_E_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(out_host, h->stats, STAT_COUNT * sizeof(double), cudaMemcpyDeviceToHost));
+  out_host[STAT_ENV_STEPS] = h->env_steps;
+  if (clear) { CU(cudaMemset(h->stats, 0, STAT_COUNT * sizeof(double))); h->env_steps = 0.0; }
+  return SNK_OK;
+}
+
+extern "C" int64_t snk_spawn_count(int32_t H, int32_t W, int32_t K) {
+  if (H < 3 || W < 3 || K < 1 || K > MAX_SNAKE_LENGTH) { fail(SNK_E_INVALID, "bad spawn table shape"); return -1; }
+  return spawn_enumerate(H, W, K, nullptr, nullptr, 0);
+}
+
+extern "C" int snk_spawn_cells(int32_t H, int32_t W, int32_t K, int32_t* out, int64_t count) {
+  if (!out || H < 3 || W < 3 || K < 1 || K > MAX_SNAKE_LENGTH) return fail(SNK_E_INVALID, "bad argument");
+  spawn_enumerate(H, W, K, nullptr, out, count);
+  return SNK_OK;
+}

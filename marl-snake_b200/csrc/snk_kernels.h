@@ -1,0 +1,54 @@
+// snk_kernels.h -- internal interface between the C-ABI layer (snk_api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "snk_core.cuh"
+
+#define SNK_MAX_THREADS 512
+
+namespace snk {
+
+enum : int { MODE_STEP = 0, MODE_RESET = 1, MODE_ENCODE = 2 };
+
+struct KParams {
+  Dims d;
+  // resident state
+  uint8_t* recs;               // [N] records, rec_bytes each
+  uint8_t* hist;               // [N, ns, fs, ohw_p] channel-bit frames (fs > 1 only)
+  const uint64_t* spawn;       // [n_cand] packed spawn poses
+  const int32_t* replay;       // replay draws, all envs back to back
+  const int64_t* replay_off;   // [N+1]
+  uint32_t* err;               // sticky error bits
+  double* stats;               // [STAT_COUNT]
+  // per-call I/O
+  const uint8_t* actions;
+  uint8_t* obs;
+  double* rew;
+  uint8_t* done;
+  uint8_t* fin;
+  int32_t* rank;
+  double* ep_scores;
+  int32_t* ep_steps;
+  int32_t* ep_fruits;
+  int32_t* ep_kills;
+  const uint8_t* mask;
+  int32_t mode;
+  int32_t E;                   // environments per CTA
+  int32_t vec16;               // 128-bit observation stores are legal for every tile
+};
+
+struct StateView {
+  uint8_t* grid; int32_t* head; int32_t* tail; int32_t* length; uint8_t* dir; uint8_t* alive;
+  int32_t* alive_counter; int32_t* episode_length; int32_t* cells; int32_t max_cells;
+};
+
+cudaError_t launch_tile_kernel(const KParams& p, int threads, size_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_get_state(const Dims& d, const uint8_t* recs, const StateView& sv, cudaStream_t s);
+cudaError_t launch_set_state(const Dims& d, uint8_t* recs, const StateView& sv, cudaStream_t s);
+cudaError_t launch_init_records(const Dims& d, uint8_t* recs, cudaStream_t s);
+
+// host-side spawn table (snk_spawn.cpp)
+int64_t spawn_enumerate(int H, int W, int K, uint64_t* packed_out, int32_t* cells_out, int64_t cap);
+
+}  // namespace snk

@@ -1,0 +1,332 @@
+"""Host-side mirror of the reference's SnakeEnv interface over libsnk.so.
+
+`SnakeBatch`  N environments resident on one GPU; step()/reset() take and return CUDA tensors
+              (the fast path; one kernel launch per step on the current torch stream).
+`SnakeEnv`    drop-in for `gym.make('Snake-v1', **kw)` (marlenv/envs/snake_env.py:31): one
+              environment, NumPy observation without batch dimension, list rewards / dones, dict info,
+              same constructor kwargs, same exceptions.
+
+PyTorch is used for device memory and streams only; every rule of the game runs in the CUDA library.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import SnkConfig, SnkStateView, SnkStepExtra, check, lib
+from .spaces import Box, Discrete
+
+DEFAULT_REWARD_DICT = {'fruit': 10.0, 'kill': 0.0, 'lose': -0.5, 'win': 0.0, 'time': -0.001}   # snake_env.py:46-52
+ACTION_ANGLE_DICT = {0: 0.0, 1: np.pi / 2.0, 2: -np.pi / 2.0}                                   # snake_env.py:40-44
+DEFAULT_MAX_EPISODE_STEPS = 1e4                                                                 # snake_env.py:56
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class SnakeBatch:
+    """A shard of `num_envs` Snake-v1 environments on one GPU."""
+
+    def __init__(self, num_envs, height=20, width=20, num_snakes=4, snake_length=3, vision_range=None,
+                 frame_stack=1, observer='snake', reward_dict=None, num_fruits=None,
+                 max_episode_steps=DEFAULT_MAX_EPISODE_STEPS, device=0, seed=0, rng='philox',
+                 auto_reset=True, env_id_offset=0, done_mode='all', **ignored):
+        reward_dict = DEFAULT_REWARD_DICT if reward_dict is None else reward_dict
+        if reward_dict.keys() != DEFAULT_REWARD_DICT.keys():                      # snake_env.py:77-80
+            raise KeyError(f'reward dict keys must correspond to {DEFAULT_REWARD_DICT.keys()}')
+        if observer != 'snake':
+            raise NotImplementedError("only observer='snake' (three relative actions) is implemented")
+        if rng not in ('philox', 'replay'):
+            raise ValueError("rng must be 'philox' or 'replay'")
+        if not torch.cuda.is_available():
+            raise RuntimeError('SnakeBatch needs a CUDA device: the step path has no CPU fallback')
+        self.device = torch.device('cuda', device if isinstance(device, int) else torch.device(device).index or 0)
+        self.num_envs, self.num_snakes = int(num_envs), int(num_snakes)
+        self.grid_shape = (int(height), int(width))
+        self.snake_length = int(snake_length)
+        self.vision_range = vision_range
+        self.frame_stack = int(frame_stack)
+        self.reward_dict = dict(reward_dict)
+        self.num_fruits = int(round(num_snakes * 0.8)) if num_fruits is None else int(num_fruits)
+        self.max_episode_steps = max_episode_steps
+        self.auto_reset = bool(auto_reset)
+        self.rng = rng
+
+        cfg = SnkConfig(abi_version=_lib.SNK_ABI_VERSION, device=self.device.index, num_envs=self.num_envs,
+                        height=height, width=width, num_snakes=num_snakes, snake_length=snake_length,
+                        vision_range=int(vision_range or 0), frame_stack=frame_stack,
+                        num_fruits=self.num_fruits, auto_reset=int(self.auto_reset),
+                        done_mode={'all': 0, 'any': 1}[done_mode],
+                        rng_mode=_lib.SNK_RNG_REPLAY if rng == 'replay' else _lib.SNK_RNG_PHILOX,
+                        seed=int(seed), env_id_offset=int(env_id_offset),
+                        max_episode_steps=float(max_episode_steps),
+                        reward_fruit=float(reward_dict['fruit']), reward_kill=float(reward_dict['kill']),
+                        reward_lose=float(reward_dict['lose']), reward_win=float(reward_dict['win']),
+                        reward_time=float(reward_dict['time']))
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.snk_create(C.byref(cfg), C.byref(self._h)))
+        shape = (C.c_int32 * 4)()
+        check(lib.snk_obs_shape(self._h, C.byref(shape)))
+        self.obs_shape = tuple(shape)                                  # (ns, oh, ow, 8*fs)
+        self.obs_ch = self.obs_shape[-1]
+        N, ns, dev = self.num_envs, self.num_snakes, self.device
+        self._obs = torch.empty((N,) + self.obs_shape, dtype=torch.uint8, device=dev)
+        self._rew = torch.empty((N, ns), dtype=torch.float64, device=dev)
+        self._done = torch.empty((N, ns), dtype=torch.uint8, device=dev)
+        self._fin = torch.zeros((N,), dtype=torch.uint8, device=dev)
+        self._rank = torch.zeros((N, ns), dtype=torch.int32, device=dev)
+        self._ep_scores = torch.zeros((N, ns), dtype=torch.float64, device=dev)
+        self._ep_steps = torch.zeros((N, ns), dtype=torch.int32, device=dev)
+        self._ep_fruits = torch.zeros((N, ns), dtype=torch.int32, device=dev)
+        self._ep_kills = torch.zeros((N, ns), dtype=torch.int32, device=dev)
+        self._extra = SnkStepExtra(self._fin.data_ptr(), self._rank.data_ptr(), self._ep_scores.data_ptr(),
+                                   self._ep_steps.data_ptr(), self._ep_fruits.data_ptr(),
+                                   self._ep_kills.data_ptr())
+        self.observation_space = Box(0, 1, (N,) + self.obs_shape, np.uint8)
+        self.action_space = Discrete(3)
+
+    # ---- lifecycle ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            lib.snk_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- hot path ----------------------------------------------------------------------------------
+    def reset(self, mask=None, copy=False):
+        """SnakeEnv.reset for all envs (or those with mask != 0). Returns uint8 [N, ns, oh, ow, 8*fs]."""
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        check(lib.snk_reset(self._h, _ptr(mask), _ptr(self._obs), self._stream()))
+        return self._obs.clone() if copy else self._obs
+
+    def step(self, actions, copy=False, want_obs=True, want_info=True):
+        """actions: uint8 CUDA tensor [N, ns] in {0,1,2}.  Returns (obs, rewards f64, dones bool, info)
+        where info holds per-env `finished` and, for finished envs, the terminal `rank` / `episode_*`
+        arrays the reference puts in its info dict (snake_env.py:396-410).  The returned tensors are
+        the batch's own buffers, overwritten by the next call unless copy=True."""
+        if actions.dtype != torch.uint8 or actions.device != self.device or not actions.is_contiguous() \
+                or actions.numel() != self.num_envs * self.num_snakes:
+            raise ValueError('actions must be a contiguous uint8 CUDA tensor of shape [num_envs, num_snakes]')
+        check(lib.snk_step(self._h, _ptr(actions), _ptr(self._obs if want_obs else None), _ptr(self._rew),
+                           _ptr(self._done), C.byref(self._extra) if want_info else None, self._stream()))
+        info = {}
+        if want_info:
+            info = dict(finished=self._fin.view(torch.bool), rank=self._rank, episode_scores=self._ep_scores,
+                        episode_steps=self._ep_steps, episode_fruits=self._ep_fruits,
+                        episode_kills=self._ep_kills)
+        out = (self._obs if want_obs else None, self._rew, self._done.view(torch.bool), info)
+        if copy:
+            out = (None if out[0] is None else out[0].clone(), out[1].clone(), out[2].clone(),
+                   {k: v.clone() for k, v in info.items()})
+        return out
+
+    def step_host(self, actions, obs, rewards, dones):
+        """Reference-shaped call on HOST buffers (pinned NumPy/torch CPU arrays): copies actions in,
+        steps, copies obs/rewards/dones out, synchronises.  `obs` may be None."""
+        check(lib.snk_step_host(self._h, C.c_void_p(actions.data_ptr()),
+                                C.c_void_p(obs.data_ptr()) if obs is not None else C.c_void_p(0),
+                                C.c_void_p(rewards.data_ptr()), C.c_void_p(dones.data_ptr())))
+
+    def reset_host(self, obs):
+        check(lib.snk_reset_host(self._h, C.c_void_p(obs.data_ptr()) if obs is not None else C.c_void_p(0)))
+        self._host_reset_done = True
+
+    # ---- parity / checkpoint interface ---------------------------------------------------------------
+    def get_state(self, max_cells=None):
+        N, ns, dev = self.num_envs, self.num_snakes, self.device
+        H, W = self.grid_shape
+        i32 = dict(dtype=torch.int32, device=dev)
+        u8 = dict(dtype=torch.uint8, device=dev)
+        st = dict(grid=torch.empty((N, H * W), **u8), head=torch.empty((N, ns), **i32),
+                  tail=torch.empty((N, ns), **i32), length=torch.empty((N, ns), **i32),
+                  dir=torch.empty((N, ns), **u8), alive=torch.empty((N, ns), **u8),
+                  alive_counter=torch.empty((N,), **i32), episode_length=torch.empty((N,), **i32))
+        if max_cells:
+            st['cells'] = torch.empty((N, ns, max_cells), **i32)
+        view = SnkStateView(**{k: v.data_ptr() for k, v in st.items()}, max_cells=int(max_cells or 0))
+        check(lib.snk_get_state(self._h, C.byref(view), self._stream()))
+        st['grid'] = st['grid'].view(N, H, W)
+        return st
+
+    def set_state(self, grid, alive, dir, length, cells, alive_counter, episode_length=None):
+        """Force a state (scenario tests / restore). cells: int32 [N, ns, L] head-first flat cell indices."""
+        N, ns, dev = self.num_envs, self.num_snakes, self.device
+
+        def t(x, dtype, shape):
+            return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).reshape(shape).to(dev).contiguous()
+        cells = t(cells, torch.int32, (N, ns, -1))
+        if episode_length is None:
+            episode_length = np.zeros(N, dtype=np.int32)
+        keep = dict(grid=t(grid, torch.uint8, (N, -1)), alive=t(alive, torch.uint8, (N, ns)),
+                    dir=t(dir, torch.uint8, (N, ns)), length=t(length, torch.int32, (N, ns)), cells=cells,
+                    alive_counter=t(alive_counter, torch.int32, (N,)),
+                    episode_length=t(episode_length, torch.int32, (N,)))
+        view = SnkStateView(**{k: v.data_ptr() for k, v in keep.items()}, max_cells=cells.shape[-1])
+        check(lib.snk_set_state(self._h, C.byref(view), _ptr(self._obs), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()      # `keep` must outlive the kernels
+        return self._obs
+
+    def set_replay(self, draws_per_env):
+        """draws_per_env: sequence of N int arrays -- recorded draw outputs in consumption order."""
+        assert len(draws_per_env) == self.num_envs
+        off = np.zeros(self.num_envs + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(d) for d in draws_per_env])
+        flat = np.concatenate([np.asarray(d, dtype=np.int32).reshape(-1) for d in draws_per_env]) \
+            if off[-1] else np.zeros(1, dtype=np.int32)
+        flat = np.ascontiguousarray(flat, dtype=np.int32)
+        check(lib.snk_set_replay(self._h, flat.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p)))
+
+    def replay_cursors(self):
+        out = np.zeros(self.num_envs, dtype=np.int32)
+        check(lib.snk_replay_cursors(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def device_errors(self, clear=False):
+        bits = C.c_uint32(0)
+        check(lib.snk_device_errors(self._h, C.byref(bits), int(clear)))
+        return bits.value
+
+    def raise_on_device_errors(self):
+        bits = self.device_errors(clear=True)
+        if bits & 1:
+            raise KeyError('action outside {0, 1, 2}')                 # the reference's KeyError (:606)
+        if bits:
+            raise _lib.SnkError('; '.join(m for b, m in _lib.DEV_ERRORS.items() if bits & b))
+
+    # ---- rollout statistics --------------------------------------------------------------------------
+    def stats(self, clear=False):
+        out = np.zeros(8, dtype=np.float64)
+        check(lib.snk_stats(self._h, out.ctypes.data_as(C.c_void_p), int(clear)))
+        return dict(zip(_lib.STAT_NAMES[:7], out[:7]))
+
+    def stats_tensor(self):
+        """The device-resident statistics vector (8 doubles) as a torch tensor sharing memory, ready
+        for an in-place torch.distributed.all_reduce at the end of a rollout."""
+        p = C.c_void_p()
+        check(lib.snk_stats_dev(self._h, C.byref(p)))
+        return _tensor_from_ptr(p.value, 8, torch.float64, self.device)
+
+    def algorithmic_bytes_per_env_step(self):
+        return int(lib.snk_algorithmic_bytes_per_env_step(self._h))
+
+
+def _tensor_from_ptr(ptr, n, dtype, device):
+    class _Holder:
+        pass
+    h = _Holder()
+    itemsize = torch.empty((), dtype=dtype).element_size()
+    h.__cuda_array_interface__ = dict(shape=(n,), typestr={8: '<f8', 4: '<f4'}[itemsize], data=(ptr, False),
+                                      version=2)
+    return torch.as_tensor(h, device=device)
+
+
+class SnakeEnv:
+    """Drop-in for the reference's SnakeEnv (one environment, host-side return types).
+
+    reset() -> np.uint8 [ns, oh, ow, 8*fs]; step(actions) -> (obs, list[float], list[bool], dict).
+    Unknown kwargs are ignored as the reference does (snake_env.py:68-69); `reward_func` is accepted as
+    an alias of `reward_dict` (README spelling)."""
+
+    default_reward_dict = DEFAULT_REWARD_DICT
+    action_angle_dict = ACTION_ANGLE_DICT
+    reward_keys = DEFAULT_REWARD_DICT.keys()
+    metadata = {}
+    _done_mode = 'all'
+
+    def __init__(self, height=20, width=20, num_snakes=4, snake_length=3, vision_range=None, frame_stack=1,
+                 observer='snake', *args, **kwargs):
+        if 'reward_dict' not in kwargs and isinstance(kwargs.get('reward_func'), dict):
+            kwargs['reward_dict'] = kwargs.pop('reward_func')
+        reward_dict = kwargs.pop('reward_dict', DEFAULT_REWARD_DICT)
+        self._batch = SnakeBatch(1, height=height, width=width, num_snakes=num_snakes,
+                                 snake_length=snake_length, vision_range=vision_range, frame_stack=frame_stack,
+                                 observer=observer, reward_dict=reward_dict,
+                                 num_fruits=kwargs.pop('num_fruits', None),
+                                 max_episode_steps=kwargs.pop('max_episode_steps', DEFAULT_MAX_EPISODE_STEPS),
+                                 device=kwargs.pop('device', 0), seed=kwargs.pop('seed', 0),
+                                 rng=kwargs.pop('rng', 'philox'), auto_reset=False, done_mode=self._done_mode)
+        b = self._batch
+        self.reward_dict = b.reward_dict
+        self.max_episode_steps = b.max_episode_steps
+        self.num_snakes, self.num_fruits = b.num_snakes, b.num_fruits
+        self.grid_shape, self.snake_length = b.grid_shape, b.snake_length
+        self.vision_range, self.frame_stack, self.observer = vision_range, b.frame_stack, observer
+        self.low, self.high, self.image_obs = 0, 1, False
+        self.action_dict = ACTION_ANGLE_DICT
+        self.obs_ch = b.obs_ch
+        self.action_space = Discrete(len(self.action_dict) * self.num_snakes)             # snake_env.py:107-109
+        self.observation_space = Box(self.low, self.high, b.obs_shape, np.uint8)          # snake_env.py:115-129
+        self._actions = torch.zeros((1, self.num_snakes), dtype=torch.uint8, device=b.device)
+        self._alive = np.zeros(self.num_snakes, dtype=bool)
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def seed(self, seed=42):
+        return [seed]
+
+    def close(self):
+        self._batch.close()
+
+    def reset(self):
+        obs = self._batch.reset()[0].cpu().numpy()
+        self._alive[:] = True
+        return obs
+
+    def step(self, actions):
+        if isinstance(actions, int):
+            actions = [actions]
+        assert len(actions) == self.num_snakes                                            # snake_env.py:313
+        acts = []
+        for i, ac in enumerate(actions):
+            if isinstance(ac, np.ndarray):
+                ac = ac.item()
+            if self._alive[i] and ac not in self.action_dict:
+                raise KeyError(ac)                                                        # snake_env.py:606
+            acts.append(int(ac) if ac in self.action_dict else 0)
+        self._actions.copy_(torch.tensor([acts], dtype=torch.uint8))
+        obs, rew, done, info = self._batch.step(self._actions)
+        st = self._batch.get_state()
+        self._alive[:] = st['alive'][0].cpu().numpy().astype(bool)
+        out_info = {}
+        if bool(info['finished'][0]):
+            out_info['rank'] = [int(r) for r in info['rank'][0].cpu().numpy()]
+            out_info['episode_scores'] = info['episode_scores'][0].cpu().numpy().copy()
+            for k in ('episode_steps', 'episode_fruits', 'episode_kills'):
+                out_info[k] = info[k][0].cpu().numpy().astype(np.float64)
+        return (obs[0].cpu().numpy(), [float(r) for r in rew[0].cpu().numpy()],
+                [bool(d) for d in done[0].cpu().numpy()], out_info)
+
+    @property
+    def grid(self):
+        """The H x W cell-code grid as the reference keeps it (np.int64)."""
+        return self._batch.get_state()['grid'][0].cpu().numpy().astype(np.int64)
+
+    @property
+    def alive_snakes(self):
+        return int(self._batch.get_state()['alive_counter'][0])
+
+    def render(self, mode='ascii'):
+        if mode == 'ascii':
+            sym = {0: '.', 1: '#', 2: 'o', 3: 'H', 4: 'b', 5: 't'}
+            print('\n'.join(''.join(sym[int(v) % 10] for v in row) for row in self.grid))
+        elif mode == 'rgb_array':
+            raise NotImplementedError('rendering is host-side visualisation, outside the step path')
+
+
+class CoopSnakeEnv(SnakeEnv):
+    """SnakeCoop-v1: the episode ends as soon as any snake is done (coop_snake_env.py:14-22)."""
+    _done_mode = 'any'

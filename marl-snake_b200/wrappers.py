@@ -1,0 +1,147 @@
+"""make_snake and the agent wrappers, same names and return contract as the reference's
+marlenv/wrappers.py (make_snake :203-223, SingleAgent :84-105, SingleMultiAgent :107-124).
+
+The reference vectorises with one OS process per environment (gym AsyncVectorEnv, :211-212); here
+`num_envs > 1` is one `SnakeBatch` on the GPU with the reference worker's auto-reset rule (:138-146).
+"""
+import numpy as np
+import torch
+
+from .env import ACTION_ANGLE_DICT, SnakeBatch
+from .registration import make
+from .spaces import Box, Discrete
+
+
+class _Wrapper:
+    def __init__(self, env):
+        self.env = env
+        self.action_space = env.action_space
+        self.observation_space = env.observation_space
+
+    def __getattr__(self, name):
+        if name.startswith('_'):
+            raise AttributeError(name)
+        return getattr(self.env, name)
+
+    @property
+    def unwrapped(self):
+        return self.env.unwrapped
+
+    def reset(self, **kwargs):
+        return self.env.reset(**kwargs)
+
+    def step(self, action, **kwargs):
+        return self.env.step(action, **kwargs)
+
+    def close(self):
+        return self.env.close()
+
+
+def _obs_hw(env):
+    vr = getattr(env, 'vision_range', None)
+    return (vr * 2 + 1, vr * 2 + 1) if vr else tuple(env.grid_shape)
+
+
+class SingleAgent(_Wrapper):
+    """num_snakes == 1: squeeze the snake axis (wrappers.py:84-105)."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        assert env.num_snakes == 1, "Number of player must be one"
+        self.action_space = Discrete(len(env.action_dict))
+        self.observation_space = Box(0, 255, (*_obs_hw(env), env.obs_ch), np.uint8)
+
+    def reset(self, **kwargs):
+        return self.env.reset(**kwargs)[0]
+
+    def step(self, action, **kwargs):
+        obs, rews, dones, infos = self.env.step([action], **kwargs)
+        return obs[0], rews[0], dones[0], {}
+
+
+class SingleMultiAgent(_Wrapper):
+    """num_snakes > 1: per-snake Discrete(3) action space, obs [ns, h, w, c] (wrappers.py:107-124)."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.action_space = Discrete(len(env.action_dict))
+        self.observation_space = Box(0, 255, (env.num_snakes, *_obs_hw(env), getattr(env, 'obs_ch', 3)), np.uint8)
+
+
+class RenderGUI(_Wrapper):
+    """Placeholder for the reference's cv2 window wrapper (wrappers.py:20-82): visualisation is
+    outside the accelerated path.  step/reset pass through; render() returns None."""
+
+    def __init__(self, env, window_name="Snake AI", save_video=False, video_path="output.mp4", fps=20):
+        super().__init__(env)
+
+    def render(self):
+        return None
+
+
+class VectorSnakeEnv:
+    """`num_envs` environments stepped by one kernel launch.  By default returns host arrays shaped like
+    gym's vector API (obs [N, ns, h, w, c], rewards [N, ns], dones [N, ns], tuple of info dicts);
+    `output='torch'` returns the batch's CUDA tensors and a dict of info tensors instead."""
+
+    def __init__(self, num_envs, num_snakes, output='numpy', **kwargs):
+        self.batch = SnakeBatch(num_envs, num_snakes=num_snakes, auto_reset=True, **kwargs)
+        self.num_envs, self.num_snakes, self.output = num_envs, num_snakes, output
+        b = self.batch
+        self.action_dict = ACTION_ANGLE_DICT
+        self.vision_range, self.obs_ch, self.grid_shape = b.vision_range, b.obs_ch, b.grid_shape
+        single = b.obs_shape if num_snakes > 1 else b.obs_shape[1:]
+        self.single_observation_space = Box(0, 255, single, np.uint8)
+        self.observation_space = Box(0, 255, (num_envs, *single), np.uint8)
+        self.single_action_space = self.action_space = Discrete(3)
+        self._act = torch.zeros((num_envs, num_snakes), dtype=torch.uint8, device=b.device)
+
+    def _squeeze(self, x):
+        return x[:, 0] if self.num_snakes == 1 else x
+
+    def reset(self):
+        obs = self._squeeze(self.batch.reset())
+        return obs if self.output == 'torch' else obs.cpu().numpy()
+
+    def step(self, actions):
+        if isinstance(actions, torch.Tensor) and actions.is_cuda:
+            self._act.copy_(actions.reshape(self.num_envs, self.num_snakes))
+        else:
+            self._act.copy_(torch.as_tensor(np.asarray(actions, dtype=np.uint8).reshape(self.num_envs, self.num_snakes)))
+        obs, rew, done, info = self.batch.step(self._act)
+        obs, rew, done = self._squeeze(obs), self._squeeze(rew), self._squeeze(done)
+        if self.output == 'torch':
+            return obs, rew, done, info
+        self.batch.raise_on_device_errors()
+        fin = info['finished'].cpu().numpy()
+        infos = [{} for _ in range(self.num_envs)]
+        if fin.any() and self.num_snakes > 1:
+            host = {k: info[k].cpu().numpy() for k in ('rank', 'episode_scores', 'episode_steps',
+                                                       'episode_fruits', 'episode_kills')}
+            for e in np.nonzero(fin)[0]:
+                infos[e] = dict(rank=[int(r) for r in host['rank'][e]],
+                                episode_scores=host['episode_scores'][e].copy(),
+                                episode_steps=host['episode_steps'][e].astype(np.float64),
+                                episode_fruits=host['episode_fruits'][e].astype(np.float64),
+                                episode_kills=host['episode_kills'][e].astype(np.float64))
+        return obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy(), tuple(infos)
+
+    def close(self):
+        self.batch.close()
+
+
+def make_snake(num_envs=1, num_snakes=4, env_id="Snake-v1", **kwargs):
+    """Same signature and 4-tuple return as the reference (wrappers.py:203-223):
+    (env, None, None, {'action_info': {'action_n': 3}, 'num_envs', 'num_snakes'})."""
+    if num_envs > 1:
+        coop = env_id.lower() == 'snakecoop-v1'
+        env = VectorSnakeEnv(num_envs, num_snakes, done_mode='any' if coop else 'all', **kwargs)
+        action_n = env.action_space.n
+    else:
+        wrapper = SingleMultiAgent if num_snakes > 1 else SingleAgent
+        for k in ('output',):
+            kwargs.pop(k, None)
+        env = wrapper(make(env_id, num_snakes=num_snakes, **kwargs))
+        action_n = env.action_space.n
+    properties = {'action_info': {'action_n': action_n}, 'num_envs': num_envs, 'num_snakes': num_snakes}
+    return env, None, None, properties

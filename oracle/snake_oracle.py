@@ -456,3 +456,52 @@ class VectorOracle:
             dones.append(d)
             infos.append(info)
         return np.stack(obs), np.asarray(rews, dtype=np.float64), np.asarray(dones, dtype=bool), infos
+
+
+# --------------------------------------------------------------------------- Philox draw source
+def philox4x32_10(counter, key):
+    """Philox4x32-10 (Salmon et al., SC'11): counter 4x u32, key 2x u32 -> 4x u32."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c0, c1, c2, c3 = counter
+    k0, k1 = key
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, \
+                         ((p0 >> 32) ^ c3 ^ k1) & 0xFFFFFFFF, p0 & 0xFFFFFFFF
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+class PhiloxDraws:
+    """The device's counter-based stream (DESIGN.md 'RNG'): word(seed; env, event, purpose, idx) with
+    counter = {env_lo, env_hi ^ 'SNK1', event, purpose << 24 | idx // 4}, bounded draw = mulhi(word, n).
+    `event` is bumped by the driver once per step and per explicit reset (tick())."""
+    STEP_FRUIT, SPAWN, RESET_FRUIT = 0, 1, 2
+
+    def __init__(self, seed, env_id):
+        self.key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+        self.env_id = env_id
+        self.event = 0
+        self.in_reset = False
+
+    def tick(self):
+        self.event = (self.event + 1) & 0xFFFFFFFF
+
+    def _below(self, purpose, idx, n):
+        ctr = (self.env_id & 0xFFFFFFFF, ((self.env_id >> 32) & 0xFFFFFFFF) ^ 0x534E4B31, self.event,
+               (purpose << 24) | (idx >> 2))
+        return (philox4x32_10(ctr, self.key)[idx & 3] * n) >> 32
+
+    def spawn(self, n_cand, ns, no_overlap):
+        self.in_reset = True
+        attempt = 0
+        while True:
+            pick = [self._below(self.SPAWN, attempt * ns + i, n_cand) for i in range(ns)]
+            if no_overlap(pick):
+                return pick
+            attempt += 1
+
+    def fruit(self, n_empty, k):
+        purpose = self.RESET_FRUIT if self.in_reset else self.STEP_FRUIT
+        self.in_reset = False
+        return [self._below(purpose, j, n_empty) for j in range(k)]

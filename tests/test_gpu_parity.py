@@ -1,0 +1,153 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (libsnk.so), against the golden
+vectors recorded from the reference and against the oracle.  Integer / byte data and the float64
+rewards must match exactly (rewards are fixed-order sums of the configured constants)."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import ROLLOUTS, Rollout, load_scenarios
+from gpu_backend import GpuBackend
+from parity_util import check_against_oracle_philox, check_rollout_replay, check_scenario
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('name', ROLLOUTS)
+def test_gpu_rollout_replay(name):
+    g = Rollout(name)
+    be = GpuBackend(g.num_envs, g.kwargs, rng_mode=1, auto_reset=1)
+    check_rollout_replay(be, g)
+    assert be.errors() == 0
+    be.close()
+
+
+@pytest.mark.parametrize('sc', load_scenarios(), ids=lambda s: s.name)
+def test_gpu_scenarios(sc):
+    kw = dict(height=sc.H, width=sc.W, num_snakes=sc.num_snakes, snake_length=2, **sc.kwargs)
+    be = GpuBackend(1, kw, rng_mode=1, auto_reset=0)
+    check_scenario(be, sc)
+    assert be.errors() == 0
+    be.close()
+
+
+@pytest.mark.parametrize('kw,num_envs,steps', [
+    (dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5), 67, 150),
+    (dict(height=20, width=20, num_snakes=4, snake_length=3), 33, 80),
+    (dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5, frame_stack=4), 40, 120),
+    (dict(height=9, width=12, num_snakes=3, snake_length=4, vision_range=2, frame_stack=3,
+          max_episode_steps=30), 35, 100),
+    (dict(height=16, width=16, num_snakes=7, snake_length=4, vision_range=7,
+          reward_dict={'fruit': 10.0, 'kill': 1.0, 'lose': -1.0, 'win': 0.1, 'time': -0.001}), 9, 80),
+    (dict(height=10, width=10, num_snakes=1, snake_length=3, num_fruits=4), 21, 100),
+])
+def test_gpu_philox_matches_oracle(kw, num_envs, steps):
+    be = check_against_oracle_philox(GpuBackend, kw, num_envs=num_envs, steps=steps, seed=0xC0FFEE1234,
+                                     env_id_offset=3)
+    assert be.errors() == 0
+    be.close()
+
+
+def test_gpu_matches_hostsim_large():
+    """Same rule source on both sides; checks the kernel's tiling / warp-cooperative paths at a size the
+    Python oracle cannot reach quickly: 4099 envs (ragged last tile) x 300 steps, Philox mode."""
+    from hostsim_util import HostSim
+    kw = dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5)
+    N = 4099
+    hs = HostSim(N, kw, rng_mode=0, auto_reset=1, seed=77)
+    be = GpuBackend(N, kw, rng_mode=0, auto_reset=1, seed=77)
+    assert np.array_equal(hs.reset(), be.reset())
+    rng = np.random.RandomState(1)
+    for t in range(300):
+        a = rng.randint(0, 3, size=(N, 4)).astype(np.uint8)
+        o1, r1, d1, i1 = hs.step(a)
+        o2, r2, d2, i2 = be.step(a)
+        assert np.array_equal(r1, r2) and np.array_equal(d1, d2.astype(np.uint8)), t
+        assert np.array_equal(o1, o2), t
+        assert np.array_equal(i1['finished'], i2['finished'].astype(np.uint8)), t
+    assert np.array_equal(hs.grid()[0], be.grid()[0])
+    assert be.errors() == 0
+
+
+def test_gpu_shard_invariance():
+    """Streams are keyed by global env id: two shards reproduce the single-batch run (multi-GPU rule)."""
+    kw = dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5)
+    whole = GpuBackend(64, kw, rng_mode=0, seed=9)
+    lo = GpuBackend(24, kw, rng_mode=0, seed=9, env_id_offset=0)
+    hi = GpuBackend(40, kw, rng_mode=0, seed=9, env_id_offset=24)
+    assert np.array_equal(whole.reset(), np.concatenate([lo.reset(), hi.reset()]))
+    rng = np.random.RandomState(4)
+    for t in range(120):
+        a = rng.randint(0, 3, size=(64, 4)).astype(np.uint8)
+        o, r, d, _ = whole.step(a)
+        o1, r1, d1, _ = lo.step(a[:24])
+        o2, r2, d2, _ = hi.step(a[24:])
+        assert np.array_equal(o, np.concatenate([o1, o2])) and np.array_equal(r, np.concatenate([r1, r2]))
+
+
+def test_gpu_invariants_full_size():
+    """BASELINE cfg5 shard (131072 envs): size-independent properties after 64 steps."""
+    from marl_snake_b200 import SnakeBatch
+    N, ns = 131072, 4
+    b = SnakeBatch(N, num_snakes=ns, vision_range=5, seed=1)
+    b.reset()
+    g = torch.Generator(device='cuda').manual_seed(0)
+    for _ in range(64):
+        a = torch.randint(0, 3, (N, ns), dtype=torch.uint8, device='cuda', generator=g)
+        obs, rew, done, info = b.step(a)
+    st = b.get_state(max_cells=16)
+    grid = st['grid'].reshape(N, -1).long()
+    kind, owner = grid % 10, grid // 10
+    alive = st['alive'].bool()
+    # exactly one HEAD and one TAIL cell per live snake, none for dead ones
+    for i in range(ns):
+        heads = ((kind == 3) & (owner == i)).sum(1)
+        tails = ((kind == 5) & (owner == i)).sum(1)
+        assert torch.equal(heads, alive[:, i].long()) and torch.equal(tails, alive[:, i].long())
+        cells = ((kind >= 3) & (owner == i)).sum(1)
+        assert torch.equal(cells, st['length'][:, i].long())
+    # head cell of every live snake holds its HEAD code; the observation centre shows it on channel 5
+    idx = st['head'].clamp(min=0).long()
+    code = torch.gather(grid, 1, idx)
+    want = 3 + 10 * torch.arange(ns, device='cuda')[None, :]
+    assert torch.equal(code[alive], want.expand(N, ns)[alive])
+    centre = obs[:, :, 5, 5, 5].bool()
+    assert torch.equal(centre, alive)
+    # walls intact, observation is 0/1, dones mirror alive
+    border = torch.zeros(20, 20, dtype=torch.bool, device='cuda')
+    border[0] = border[-1] = True
+    border[:, 0] = border[:, -1] = True
+    assert bool((grid.view(N, 20, 20)[:, border] == 1).all())
+    assert int(obs.max()) == 1
+    assert torch.equal(done, ~alive)
+    assert b.device_errors() == 0
+
+
+def test_dropin_api():
+    """make_snake / SnakeEnv return contract of the reference (wrappers.py:203-223, snake_env.py:159,414)."""
+    from marl_snake_b200 import make, make_snake
+    env, o_s, a_s, props = make_snake(num_envs=1, num_snakes=4, height=20, width=20, snake_length=3,
+                                      vision_range=5)
+    assert o_s is None and a_s is None
+    assert props == {'action_info': {'action_n': 3}, 'num_envs': 1, 'num_snakes': 4}
+    obs = env.reset()
+    assert isinstance(obs, np.ndarray) and obs.shape == (4, 11, 11, 8) and obs.dtype == np.uint8
+    assert env.observation_space.shape == (4, 11, 11, 8) and env.action_space.n == 3
+    obs, rews, dones, info = env.step([env.action_space.sample() for _ in range(4)])
+    assert isinstance(rews, list) and isinstance(rews[0], float) and isinstance(dones[0], bool)
+    assert isinstance(info, dict)
+    with pytest.raises(AssertionError):
+        env.step([0])
+    with pytest.raises(KeyError):
+        env.step([0, 1, 2, 5])
+    with pytest.raises(KeyError):
+        make('Snake-v1', reward_dict={'fruit': 1.0})
+    single, _, _, _ = make_snake(num_envs=1, num_snakes=1, num_fruits=4)
+    o = single.reset()
+    assert o.shape == (20, 20, 8)
+    o, r, d, i = single.step(1)
+    assert isinstance(r, float) and isinstance(d, bool) and i == {}
+    venv, _, _, props = make_snake(num_envs=16, num_snakes=4, vision_range=5)
+    o = venv.reset()
+    assert o.shape == (16, 4, 11, 11, 8)
+    o, r, d, infos = venv.step(np.zeros((16, 4), dtype=np.int64))
+    assert r.shape == (16, 4) and d.shape == (16, 4) and len(infos) == 16

@@ -1,0 +1,45 @@
+"""CPU check of the DEVICE rule source: marl-snake_b200/csrc/snk_core.cuh compiled for the host
+(tests/hostsim) must reproduce the reference's golden trajectories bit for bit, and its Philox stream
+must match the oracle's Python restatement of the same spec."""
+import numpy as np
+import pytest
+
+from golden_util import ROLLOUTS, Rollout, load_scenarios
+from hostsim_util import HostSim
+from parity_util import check_against_oracle_philox, check_rollout_replay, check_scenario
+
+
+@pytest.mark.parametrize('name', ROLLOUTS)
+def test_hostsim_rollout_replay(name):
+    g = Rollout(name)
+    hs = HostSim(g.num_envs, g.kwargs, rng_mode=1, auto_reset=1)
+    check_rollout_replay(hs, g)
+    assert hs.errors() == 0
+    hs.close()
+
+
+@pytest.mark.parametrize('sc', load_scenarios(), ids=lambda s: s.name)
+def test_hostsim_scenarios(sc):
+    kw = dict(height=sc.H, width=sc.W, num_snakes=sc.num_snakes, snake_length=2, **sc.kwargs)
+    hs = HostSim(1, kw, rng_mode=1, auto_reset=0)
+    check_scenario(hs, sc)
+    assert hs.errors() == 0
+    hs.close()
+
+
+@pytest.mark.parametrize('kw', [
+    dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5),
+    dict(height=9, width=12, num_snakes=3, snake_length=4, vision_range=2, frame_stack=3, max_episode_steps=30),
+])
+def test_hostsim_philox_matches_oracle(kw):
+    hs = check_against_oracle_philox(HostSim, kw, num_envs=6, steps=120, seed=0xC0FFEE1234, env_id_offset=5)
+    assert hs.errors() == 0
+    hs.close()
+
+
+def test_bad_action_flag():
+    hs = HostSim(1, dict(num_snakes=2), rng_mode=0, auto_reset=1)
+    hs.reset()
+    hs.step(np.array([[0, 7]], dtype=np.uint8))
+    assert hs.errors() & 1
+    hs.close()
