@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/s of the Snake-v1 step path on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path over the whole batch: ONE launch of snk_tile_kernel stepping every
+environment of the shard (rules + auto-reset + observation render).  Workload (config.workload): BASELINE
+cfg5 shape -- 20x20 grid, 4 snakes, length 3, vision_range 5, frame_stack 1, auto-reset, Philox seed 0,
+uniform random actions -- with 1,048,576 environments per GPU (weak scaling; no collective on the step
+path, one NCCL all-reduce of the 8-double statistics vector after the timed region).
+
+Prints ONE JSON line (rank 0): value = device-timed whole-job throughput with state and actions
+resident in HBM; e2e = the same metric through the C ABI's host-buffer call (snk_step_host: pinned
+actions H2D, step, obs + rewards + dones D2H, synchronise); roofline = the kernel against measured HBM
+peak; cpu_baseline = the oracle's Python port on this box's host cores, run as the reference
+vectorises (one process per env).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENV_KW = dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5, frame_stack=1)
+WORKLOAD = 'cfg5: 20x20, 4 snakes, len 3, vision_range 5, frame_stack 1, auto-reset, random actions'
+BURN_IN = 256          # steps before warm-up so the alive / reset mix is stationary (mean episode ~68)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=2000)
+    ap.add_argument('--warmup', type=int, default=100)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--envs-per-gpu', type=int, default=1 << 20)
+    ap.add_argument('--e2e-steps', type=int, default=8)
+    ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------ CPU legs
+def cpu_leg(seconds, chunk=250):
+    """Oracle port on all host cores for about `seconds`; returns (agent-steps/s, cores, sample text)."""
+    from oracle.cpu_runner import CpuPool
+    pool = CpuPool(ENV_KW)
+    pool.run(chunk)
+    total, wall = 0, 0.0
+    while wall < seconds:
+        wall += pool.run(chunk)
+        total += chunk
+    pool.close()
+    ns = ENV_KW['num_snakes']
+    val = total * pool.procs * ns / wall
+    return val, pool.procs, (f'{pool.procs} processes x 1 env (reference vectorisation), {total} env-steps each '
+                             f'incl. resets, {wall:.1f} s wall, Python {sys.version.split()[0]}')
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU path (oracle port; the Python reference cannot travel to the
+    GPU box) on all host cores.  One 'step' = every worker process advances its env by 250 env-steps."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle.cpu_runner import CpuPool
+    chunk = 250
+    pool = CpuPool(ENV_KW)
+    for _ in range(max(args.warmup, 1)):
+        pool.run(chunk)
+    t = 0.0
+    for _ in range(args.steps):
+        t += pool.run(chunk)
+    pool.close()
+    ns = ENV_KW['num_snakes']
+    val = args.steps * chunk * pool.procs * ns / t
+    sample = f'{pool.procs} processes x 1 env, {chunk} env-steps per bench step incl. resets'
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'agent_steps_per_sec', 'value': val, 'unit': 'agent-steps/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'envs_per_step': pool.procs, 'env_steps_per_bench_step': chunk},
+        'cpu_baseline': {'value': val, 'unit': 'agent-steps/s', 'cores': pool.procs, 'kind': 'port',
+                         'sample': sample},
+        'e2e': {'value': val, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0}))
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+    BAD = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20,
+           'hw_power_brake_slowdown': 0x80}
+    NOTE = {'sw_power_cap': 0x4}
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], 0
+        self.stop_flag = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.max_mhz = None
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self.reasons |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': ['unsampled']}
+        s = sorted(self.samples)
+        names = [n for n, b in {**self.BAD, **self.NOTE}.items() if self.reasons & b]
+        return {'sm_mhz': s[len(s) // 2], 'sm_max_mhz': self.max_mhz, 'reasons': names, 'samples': len(s)}
+
+
+# ------------------------------------------------------------------------------ our arm
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    from marl_snake_b200 import SnakeBatch, allreduce_stats
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+
+    # CPU baseline first (rank 0, N=1 only), before the GPU is busy
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, sample = cpu_leg(args.cpu_seconds)
+        cpu = {'value': v, 'unit': 'agent-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+
+    N, ns = args.envs_per_gpu, ENV_KW['num_snakes']
+    batch = SnakeBatch(N, device=local, seed=0, rng='philox', auto_reset=True, env_id_offset=rank * N, **ENV_KW)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    pool = [torch.randint(0, 3, (N, ns), dtype=torch.uint8, device=dev, generator=gen) for _ in range(16)]
+    batch.reset()
+    for t in range(BURN_IN):
+        batch.step(pool[t % 16], want_info=False)
+    for t in range(args.warmup):
+        batch.step(pool[t % 16], want_info=False)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    ev0.record()
+    for t in range(args.steps):
+        batch.step(pool[t % 16], want_info=False)       # one kernel launch per step, on the current stream
+    ev1.record()
+    torch.cuda.synchronize()
+    sampler.stop_flag.set()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        dist.barrier()
+        tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    errs = batch.device_errors()
+
+    # end-of-rollout statistics all-reduce (the only collective; outside the step path)
+    stats = allreduce_stats(batch.stats_tensor().clone())
+    stats_host = stats.cpu().tolist()
+
+    # e2e: the reference-shaped call with HOST buffers (pinned), copies inside the timed region
+    K2 = max(1, args.e2e_steps)
+    h_act = [p.cpu().pin_memory() for p in pool[:4]]
+    h_obs = torch.empty((N,) + batch.obs_shape, dtype=torch.uint8).pin_memory()
+    h_rew = torch.empty((N, ns), dtype=torch.float64).pin_memory()
+    h_done = torch.empty((N, ns), dtype=torch.uint8).pin_memory()
+    for t in range(2):
+        batch.step_host(h_act[t % 4], h_obs, h_rew, h_done)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for t in range(K2):
+        batch.step_host(h_act[t % 4], h_obs, h_rew, h_done)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        ts = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        e2e_s = float(ts.item())
+    assert int(h_obs.max()) == 1 and bool((h_done <= 1).all())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak = float(peaks.get('hbm_gbs', 6650.0))
+        bytes_per_env = batch.algorithmic_bytes_per_env_step()
+        obs_bytes = 1
+        for x in batch.obs_shape:
+            obs_bytes *= x
+        rec_bytes = (bytes_per_env - obs_bytes - 10 * ns) // 2
+        per_launch = bytes_per_env * N
+        achieved = per_launch / (ms / args.steps * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get('dram_bytes_per_launch')
+        except Exception:
+            pass
+        value = N * world * ns * args.steps / (ms * 1e-3)
+        out = {
+            'metric': 'agent_steps_per_sec', 'value': value, 'unit': 'agent-steps/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'envs_per_gpu': N, 'global_envs': N * world, 'burn_in_steps': BURN_IN,
+                       'l2': 'no flush: per-step working set (records %.0f MB read + written, obs %.0f MB written) '
+                             'exceeds the 126 MB L2' % (N * rec_bytes / 1e6, N * obs_bytes / 1e6),
+                       'parallelism': f'env-shard x{world}', 'rng': 'philox seed 0',
+                       'device_errors': errs},
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                         'frac': achieved / peak, 'traffic': traffic,
+                         'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured)' if peaks else 'fallback 6650',
+                         'algorithmic_bytes_per_env_step': bytes_per_env, 'kernel': 'snk_tile_kernel',
+                         'launch_ms': ms / args.steps},
+            'e2e': {'value': N * world * ns * K2 / e2e_s, 'unit': 'agent-steps/s',
+                    'h2d_bytes_per_step': N * ns, 'd2h_bytes_per_step': N * (batch.obs_shape[0] * batch.obs_shape[1] *
+                                                                             batch.obs_shape[2] * batch.obs_shape[3]) + N * ns * 9,
+                    'steps': K2, 'ms_per_step': 1e3 * e2e_s / K2, 'api': 'snk_step_host (C ABI, pinned host buffers)'},
+            'gpu_launches': args.steps,
+            'clocks': sampler.summary(),
+            'rollout_stats': dict(zip(('episodes', 'return_sum', 'episode_steps_sum', 'fruits_sum', 'kills_sum',
+                                       'deaths'), stats_host[:6])),
+        }
+        if cpu:
+            out['cpu_baseline'] = cpu
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        reference_arm(a)
+    else:
+        ours(a)
