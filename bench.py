@@ -154,12 +154,16 @@ def ours(args):
     N, ns = args.envs_per_gpu, ENV_KW['num_snakes']
     batch = SnakeBatch(N, device=local, seed=0, rng='philox', auto_reset=True, env_id_offset=rank * N, **ENV_KW)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    pool = [torch.randint(0, 3, (N, ns), dtype=torch.uint8, device=dev, generator=gen) for _ in range(16)]
+    # A short action cycle would trap snakes in closed orbits (net turn of the cycle != 0 closes the
+    # path after 4 cycles) and empty the workload of deaths and resets; 509 distinct tensors make the
+    # cycle far longer than any snake lives (mean episode ~70 steps).
+    NPOOL = 509
+    pool = [torch.randint(0, 3, (N, ns), dtype=torch.uint8, device=dev, generator=gen) for _ in range(NPOOL)]
     batch.reset()
-    for t in range(BURN_IN):
-        batch.step(pool[t % 16], want_info=False)
-    for t in range(args.warmup):
-        batch.step(pool[t % 16], want_info=False)
+    step_no = 0
+    for t in range(BURN_IN + args.warmup):
+        batch.step(pool[step_no % NPOOL], want_info=False)
+        step_no += 1
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
@@ -170,7 +174,7 @@ def ours(args):
     sampler.start()
     ev0.record()
     for t in range(args.steps):
-        batch.step(pool[t % 16], want_info=False)       # one kernel launch per step, on the current stream
+        batch.step(pool[(step_no + t) % NPOOL], want_info=False)   # one kernel launch per step, current stream
     ev1.record()
     torch.cuda.synchronize()
     sampler.stop_flag.set()
@@ -181,6 +185,7 @@ def ours(args):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
     errs = batch.device_errors()
+    st_after = batch.stats()
 
     # end-of-rollout statistics all-reduce (the only collective; outside the step path)
     stats = allreduce_stats(batch.stats_tensor().clone())
@@ -236,6 +241,8 @@ def ours(args):
                        'l2': 'no flush: per-step working set (records %.0f MB read + written, obs %.0f MB written) '
                              'exceeds the 126 MB L2' % (N * rec_bytes / 1e6, N * obs_bytes / 1e6),
                        'parallelism': f'env-shard x{world}', 'rng': 'philox seed 0',
+                       'tile_envs': os.environ.get('SNK_TILE_ENVS', 'auto'), 'threads': os.environ.get('SNK_THREADS', '256'),
+                       'mean_episode_steps_rank0': st_after['episode_steps_sum'] / max(st_after['episodes'], 1.0),
                        'device_errors': errs},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': traffic,

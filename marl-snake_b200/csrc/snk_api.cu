@@ -47,6 +47,7 @@ struct snk_env {
   uint8_t* h_actions = nullptr; uint8_t* h_obs = nullptr; double* h_rew = nullptr; uint8_t* h_done = nullptr;
   cudaStream_t own_stream = nullptr;
   double env_steps = 0.0;
+  int force_generic = 0;
   bool was_reset = false;
 };
 
@@ -66,6 +67,7 @@ static KParams base_params(const snk_env* h) {
   p.replay = h->replay; p.replay_off = h->replay_off;
   p.err = h->err; p.stats = h->stats;
   p.E = h->tile_envs;
+  p.force_generic = h->force_generic;
   return p;
 }
 
@@ -103,18 +105,21 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
   spawn_enumerate(d.H, d.W, d.K, table.data(), nullptr, n_cand);
   d.n_cand = (uint32_t)n_cand;
 
-  // tile shape: environments per CTA sized for ~40 KB of shared memory, threads per CTA
-  const size_t per_env = (size_t)d.rec_bytes + d.stage_env_bytes + d.scr_bytes + 2;
+  // tile shape: environments per CTA sized for ~40 KB of shared memory (a multiple of 32 when
+  // possible: phase L runs one thread per environment), threads per CTA
+  size_t per_env = (size_t)d.rec_bytes + d.scr_bytes + 2;
+  if (d.fs > 1) per_env += d.stage_env_bytes;
   int E = (int)((size_t)env_int("SNK_TILE_SMEM", 40 * 1024) / per_env);
   if (E > 64) E = 64;
-  if (E > 2) E &= ~1;
+  if (E >= 32) E &= ~31; else if (E > 2) E &= ~1;
   if (E < 1) E = 1;
   E = env_int("SNK_TILE_ENVS", E);
   int threads = env_int("SNK_THREADS", 256);
   if (threads < 32 || threads > SNK_MAX_THREADS || (threads & 31)) { delete h; return fail(SNK_E_INVALID, "SNK_THREADS must be a multiple of 32 in 32..%d", SNK_MAX_THREADS); }
   if (E < 1 || E > threads) { delete h; return fail(SNK_E_INVALID, "SNK_TILE_ENVS must be in 1..threads"); }
   h->tile_envs = E; h->threads = threads;
-  h->smem_bytes = (size_t)E * d.rec_bytes + (size_t)round_up(E * d.stage_env_bytes, 16) + (size_t)E * d.scr_bytes + 2 * (size_t)E + 16;
+  h->force_generic = env_int("SNK_FORCE_GENERIC", 0);
+  h->smem_bytes = tile_smem_bytes(d, E);
   if (h->smem_bytes > 227 * 1024) {
     const size_t need = h->smem_bytes;
     delete h;

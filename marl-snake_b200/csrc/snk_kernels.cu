@@ -151,21 +151,46 @@ __device__ void reset_env_warp(const KParams& p, Rec& r, uint32_t env_local) {
 }
 
 // ---- the fused step / reset / encode kernel -------------------------------------------------------
+//
+// Template parameters are compile-time copies of configuration values (0 = read the runtime value):
+// the BASELINE shapes get specialised instances so index arithmetic folds to shifts and multiplies.
+template <int kNS, int kW, int kOH, int kOW, int kFS>
+struct Shape {
+  const Dims& d;
+  __device__ __forceinline__ explicit Shape(const Dims& dd) : d(dd) {}
+  __device__ __forceinline__ int ns() const { return kNS ? kNS : d.ns; }
+  __device__ __forceinline__ int W() const { return kW ? kW : d.W; }
+  __device__ __forceinline__ int oh() const { return kOH ? kOH : d.oh; }
+  __device__ __forceinline__ int ow() const { return kOW ? kOW : d.ow; }
+  __device__ __forceinline__ int ohw() const { return oh() * ow(); }
+  __device__ __forceinline__ int fs() const { return kFS ? kFS : d.fs; }
+  __device__ __forceinline__ int lut_stride() const { return 10 * ns() + 6; }   // cell codes 0 .. 10*(ns-1)+5
+};
+
+__device__ __forceinline__ void st_cs_128(void* p, uint2 a, uint2 b) { __stcs(reinterpret_cast<uint4*>(p), make_uint4(a.x, a.y, b.x, b.y)); }
+__device__ __forceinline__ void st_cs_64(void* p, uint2 a) { __stcs(reinterpret_cast<uint2*>(p), a); }
+
+template <int kNS, int kW, int kOH, int kOW, int kFS>
 __global__ void __launch_bounds__(SNK_MAX_THREADS)
 snk_tile_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const Dims& d = p.d;
+  const Shape<kNS, kW, kOH, kOW, kFS> sh(d);
   const int E = p.E;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, nwarps = nt >> 5;
   const uint32_t lane = lane_id();
   const int e0 = blockIdx.x * E;
   const int ne = min(E, d.N - e0);
-  const int ns = d.ns;
+  const int ns = sh.ns();
+  const int fs = sh.fs(), ohw = sh.ohw(), ow = sh.ow(), W = sh.W();
+  const int LS = sh.lut_stride();
 
+  // shared memory carve-up (offsets computed on the host side the same way, see tile_smem_bytes)
   uint8_t* s_rec = smem;
-  uint8_t* s_stage = s_rec + (size_t)E * d.rec_bytes;
-  uint8_t* s_scr = s_stage + round_up(E * d.stage_env_bytes, 16);
+  uint8_t* s_lut = s_rec + (size_t)E * d.rec_bytes;                    // fs==1: uint2[ns*LS]; else uint8[ns*LS]
+  uint8_t* s_stage = s_lut + round_up(ns * LS * (fs == 1 ? 8 : 1), 16);   // fs>1 only
+  uint8_t* s_scr = s_stage + (fs == 1 ? 0 : round_up(E * d.stage_env_bytes, 16));
   uint8_t* s_fruit = s_scr + (size_t)E * d.scr_bytes;
   uint8_t* s_flag = s_fruit + E;
 
@@ -174,7 +199,14 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
     const uint4* src = reinterpret_cast<const uint4*>(p.recs + (size_t)e0 * d.rec_bytes);
     uint4* dst = reinterpret_cast<uint4*>(s_rec);
     const int n16 = ne * (d.rec_bytes >> 4);
-    for (int i = tid; i < n16; i += nt) dst[i] = src[i];
+    for (int i = tid; i < n16; i += nt) dst[i] = __ldcs(src + i);
+  }
+  // ---- per-viewer lookup table: cell code -> channel bits (expanded to 8 bytes when fs == 1)
+  for (int idx = tid; idx < ns * LS; idx += nt) {
+    const int v = idx / LS, code = idx - v * LS;
+    const uint32_t bits = cell_bits((uint32_t)code, (uint32_t)v);
+    if (fs == 1) reinterpret_cast<uint2*>(s_lut)[idx] = make_uint2(spread4(bits & 15u), spread4(bits >> 4));
+    else s_lut[idx] = (uint8_t)bits;
   }
   __syncthreads();
 
@@ -250,80 +282,133 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   __syncthreads();
 
   const bool want_obs = p.obs != nullptr;
-  const int fs = d.fs, ohw = d.ohw, ow = d.ow;
-  if (want_obs || fs > 1) {
-    // ---- older frames of the stack: history rows -> staging, already in output (oldest-first) order
-    if (fs > 1 && want_obs) {
-      const int rows = ne * ns * fs;
-      for (int row = warp; row < rows; row += nwarps) {
-        const int el = row / (ns * fs);
-        const int rem = row - el * ns * fs;
-        const int v = rem / fs, slot = rem - v * fs;
-        if (s_flag[el] & (F_RESET | F_INIT | F_SKIP)) continue;
-        const int hpos = (int)((const EnvHdr*)(s_rec + (size_t)el * d.rec_bytes + d.off_hdr))->hpos;
-        if (slot == hpos) continue;                  // about to be overwritten by the new frame
-        int f = slot - hpos - 1; if (f < 0) f += fs;
-        const uint8_t* src = p.hist + (size_t)(e0 + el) * d.hist_env_bytes + (size_t)(v * fs + slot) * d.ohw_p;
-        uint8_t* dst = s_stage + (size_t)el * d.stage_env_bytes + (size_t)v * ohw * fs + f;
-        for (int c4 = (int)lane * 4; c4 < ohw; c4 += 128) {
-          const uint32_t w = *reinterpret_cast<const uint32_t*>(src + c4);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (c4 + k < ohw) dst[(size_t)(c4 + k) * fs] = (uint8_t)(w >> (8 * k));
-        }
-      }
+
+  if (fs == 1) {
+    // ---- write the records back: shared -> HBM (nothing below modifies them)
+    {
+      uint4* dst = reinterpret_cast<uint4*>(p.recs + (size_t)e0 * d.rec_bytes);
+      const uint4* src = reinterpret_cast<const uint4*>(s_rec);
+      const int n16 = ne * (d.rec_bytes >> 4);
+      for (int i = tid; i < n16; i += nt) dst[i] = src[i];
     }
-    // ---- phase A: encode the new frame, one warp per (environment, viewer)     snake_env.py:474-519
-    const int i_step = 32 / ow, j_step = 32 - i_step * ow;
-    const int i_first = (int)lane / ow, j_first = (int)lane - i_first * ow;
-    const int pairs = ne * ns;
-    const int el_step = nwarps / ns, v_step = nwarps - el_step * ns;
-    int el = warp / ns, v = warp - el * ns;
-    for (int pv = warp; pv < pairs; pv += nwarps) {
-      const uint8_t flag = s_flag[el];
-      if (!(flag & F_SKIP)) {
+    // ---- fused encode: one warp per (environment, viewer); each lane produces 16 output bytes
+    //      (two cells x 8 channels) per iteration straight from the staged grid through the LUT.
+    //      snake_env.py:474-519.  A viewer's block of ohw*8 bytes is only 8-byte aligned when ohw is
+    //      odd, so its 16-byte units are laid out from the address parity and the two end units may
+    //      be half units.
+    if (want_obs) {
+      const uint2* lut_all = reinterpret_cast<const uint2*>(s_lut);
+      const int H = d.H, V = d.V;
+      const int pairs = ne * ns;
+      for (int pv = warp; pv < pairs; pv += nwarps) {
+        const int el = pv / ns, v = pv - el * ns;
+        if (s_flag[el] & F_SKIP) continue;
         const uint8_t* base = s_rec + (size_t)el * d.rec_bytes;
         const uint8_t* grid = base;
         const uint8_t alive = base[d.off_snk + 7 * ns + v];
         // crop centre: own head, or cell (0,0) when the viewer has no head in the grid   :500-502
         const int hc = alive ? (int)((const uint16_t*)(base + d.off_snk))[v] : 0;
         int r0 = 0, c0 = 0;
-        if (d.V > 0) { const int hr = hc / d.W; r0 = hr - d.V; c0 = hc - hr * d.W - d.V; }
-        const bool init = (flag & (F_RESET | F_INIT)) != 0;
-        const int hpos = (int)((const EnvHdr*)(base + d.off_hdr))->hpos;
-        uint8_t* stg = s_stage + (size_t)el * d.stage_env_bytes + (size_t)v * ohw * fs;
-        uint8_t* hrow = fs > 1 ? p.hist + (size_t)(e0 + el) * d.hist_env_bytes + (size_t)(v * fs) * d.ohw_p : nullptr;
-        int i = i_first, j = j_first;
-        for (int cell = (int)lane; cell < ohw; cell += 32) {
-          const int rr = r0 + i, cc = c0 + j;
-          uint32_t bits = 0;
-          if ((unsigned)rr < (unsigned)d.H && (unsigned)cc < (unsigned)d.W)
-            bits = cell_bits(grid[rr * d.W + cc], (uint32_t)v);
-          if (fs == 1) {
-            stg[cell] = (uint8_t)bits;
-          } else if (!init) {
-            stg[(size_t)cell * fs + (fs - 1)] = (uint8_t)bits;
-            hrow[(size_t)hpos * d.ohw_p + cell] = (uint8_t)bits;
-          } else {                                   // reset: every slot holds the first frame (:452-457)
-            for (int f = 0; f < fs; ++f) {
-              stg[(size_t)cell * fs + f] = (uint8_t)bits;
-              hrow[(size_t)f * d.ohw_p + cell] = (uint8_t)bits;
-            }
+        if (V > 0) { const int hr = hc / W; r0 = hr - V; c0 = hc - hr * W - V; }
+        uint8_t* outv = p.obs + ((size_t)(e0 + el) * ns + v) * (size_t)ohw * 8;
+        const int shift = (int)((reinterpret_cast<uintptr_t>(outv) >> 3) & 1);
+        const uint2* lut = lut_all + v * LS;
+        const int units = (ohw + shift + 1) >> 1;
+        for (int u = (int)lane; u < units; u += 32) {
+          const int ca = 2 * u - shift, cb = ca + 1;
+          const bool va = ca >= 0, vb = cb < ohw;
+          uint2 qa = make_uint2(0, 0), qb = make_uint2(0, 0);
+          {
+            const int c = va ? ca : 0;
+            const int i = c / ow, j = c - i * ow;
+            const int rr = r0 + i, cc = c0 + j;
+            uint32_t code = 0;
+            if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
+            qa = lut[code];
           }
-          i += i_step; j += j_step;
-          if (j >= ow) { j -= ow; ++i; }
+          {
+            const int c = vb ? cb : 0;
+            const int i = c / ow, j = c - i * ow;
+            const int rr = r0 + i, cc = c0 + j;
+            uint32_t code = 0;
+            if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
+            qb = lut[code];
+          }
+          uint8_t* dst = outv + (ptrdiff_t)ca * 8;
+          if (va && vb) st_cs_128(dst, qa, qb);
+          else if (va) st_cs_64(dst, qa);
+          else st_cs_64(dst + 8, qb);
         }
       }
-      el += el_step; v += v_step;
-      if (v >= ns) { v -= ns; ++el; }
     }
-    __syncthreads();
-    if (fs > 1 && tid < ne && !(s_flag[tid] & F_SKIP)) {
-      EnvHdr* h = (EnvHdr*)(s_rec + (size_t)tid * d.rec_bytes + d.off_hdr);
-      h->hpos = (s_flag[tid] & (F_RESET | F_INIT)) ? 0u : (h->hpos + 1u) % (uint32_t)fs;
-    }
-    if (fs > 1) __syncthreads();
+    return;
   }
+
+  // ================= frame_stack > 1: channel-bit frames staged in output order ======================
+  // ---- older frames of the stack: history rows -> staging (oldest-first)
+  if (want_obs) {
+    const int rows = ne * ns * fs;
+    for (int row = warp; row < rows; row += nwarps) {
+      const int el = row / (ns * fs);
+      const int rem = row - el * ns * fs;
+      const int v = rem / fs, slot = rem - v * fs;
+      if (s_flag[el] & (F_RESET | F_INIT | F_SKIP)) continue;
+      const int hpos = (int)((const EnvHdr*)(s_rec + (size_t)el * d.rec_bytes + d.off_hdr))->hpos;
+      if (slot == hpos) continue;                  // about to be overwritten by the new frame
+      int f = slot - hpos - 1; if (f < 0) f += fs;
+      const uint8_t* src = p.hist + (size_t)(e0 + el) * d.hist_env_bytes + (size_t)(v * fs + slot) * d.ohw_p;
+      uint8_t* dst = s_stage + (size_t)el * d.stage_env_bytes + (size_t)v * ohw * fs + f;
+      for (int c4 = (int)lane * 4; c4 < ohw; c4 += 128) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(src + c4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (c4 + k < ohw) dst[(size_t)(c4 + k) * fs] = (uint8_t)(w >> (8 * k));
+      }
+    }
+  }
+  // ---- phase A: encode the new frame, one warp per (environment, viewer)     snake_env.py:474-519
+  {
+    const int H = d.H, V = d.V;
+    const int pairs = ne * ns;
+    for (int pv = warp; pv < pairs; pv += nwarps) {
+      const int el = pv / ns, v = pv - el * ns;
+      const uint8_t flag = s_flag[el];
+      if (flag & F_SKIP) continue;
+      const uint8_t* base = s_rec + (size_t)el * d.rec_bytes;
+      const uint8_t* grid = base;
+      const uint8_t alive = base[d.off_snk + 7 * ns + v];
+      const int hc = alive ? (int)((const uint16_t*)(base + d.off_snk))[v] : 0;
+      int r0 = 0, c0 = 0;
+      if (V > 0) { const int hr = hc / W; r0 = hr - V; c0 = hc - hr * W - V; }
+      const bool init = (flag & (F_RESET | F_INIT)) != 0;
+      const int hpos = (int)((const EnvHdr*)(base + d.off_hdr))->hpos;
+      const uint8_t* lut = s_lut + v * LS;
+      uint8_t* stg = s_stage + (size_t)el * d.stage_env_bytes + (size_t)v * ohw * fs;
+      uint8_t* hrow = p.hist + (size_t)(e0 + el) * d.hist_env_bytes + (size_t)(v * fs) * d.ohw_p;
+      for (int cell = (int)lane; cell < ohw; cell += 32) {
+        const int i = cell / ow, j = cell - i * ow;
+        const int rr = r0 + i, cc = c0 + j;
+        uint32_t code = 0;
+        if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
+        const uint8_t bits = lut[code];
+        if (!init) {
+          stg[(size_t)cell * fs + (fs - 1)] = bits;
+          hrow[(size_t)hpos * d.ohw_p + cell] = bits;
+        } else {                                   // reset: every slot holds the first frame (:452-457)
+          for (int f = 0; f < fs; ++f) {
+            stg[(size_t)cell * fs + f] = bits;
+            hrow[(size_t)f * d.ohw_p + cell] = bits;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < ne && !(s_flag[tid] & F_SKIP)) {
+    EnvHdr* h = (EnvHdr*)(s_rec + (size_t)tid * d.rec_bytes + d.off_hdr);
+    h->hpos = (s_flag[tid] & (F_RESET | F_INIT)) ? 0u : (h->hpos + 1u) % (uint32_t)fs;
+  }
+  __syncthreads();
 
   // ---- write the records back: shared -> HBM
   {
@@ -432,17 +517,41 @@ __global__ void snk_init_records_kernel(const Dims d, uint8_t* __restrict__ recs
 }
 
 // ---- launch wrappers -----------------------------------------------------------------------------
-cudaError_t launch_tile_kernel(const KParams& p, int threads, size_t smem_bytes, cudaStream_t stream) {
+size_t tile_smem_bytes(const Dims& d, int E) {
+  const int LS = 10 * d.ns + 6;
+  size_t b = (size_t)E * d.rec_bytes + (size_t)round_up(d.ns * LS * (d.fs == 1 ? 8 : 1), 16);
+  if (d.fs > 1) b += (size_t)round_up(E * d.stage_env_bytes, 16);
+  b += (size_t)E * d.scr_bytes + 2 * (size_t)E + 16;
+  return b;
+}
+
+template <int kNS, int kW, int kOH, int kOW, int kFS>
+static cudaError_t launch_instance(const KParams& p, int threads, size_t smem_bytes, cudaStream_t stream) {
   static size_t configured = 0;
+  auto kern = snk_tile_kernel<kNS, kW, kOH, kOW, kFS>;
   if (smem_bytes > configured) {
-    cudaError_t e = cudaFuncSetAttribute(snk_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     configured = smem_bytes;
   }
   const int grid = (p.d.N + p.E - 1) / p.E;
-  snk_tile_kernel<<<grid, threads, smem_bytes, stream>>>(p);
+  kern<<<grid, threads, smem_bytes, stream>>>(p);
   return cudaGetLastError();
+}
+
+// Specialised instances for the BASELINE shapes; everything else runs the generic instance.
+cudaError_t launch_tile_kernel(const KParams& p, int threads, size_t smem_bytes, cudaStream_t stream) {
+  const Dims& d = p.d;
+  const bool generic = p.force_generic != 0;
+#define SNK_TRY(NS, W_, OH, OW, FS)                                                              \
+  if (!generic && d.ns == NS && d.W == W_ && d.oh == OH && d.ow == OW && d.fs == FS)             \
+    return launch_instance<NS, W_, OH, OW, FS>(p, threads, smem_bytes, stream);
+  SNK_TRY(4, 20, 11, 11, 1)      // cfg1 / cfg5: 20x20, 4 snakes, vision 5
+  SNK_TRY(4, 20, 20, 20, 1)      // cfg2: full-grid observation
+  SNK_TRY(4, 20, 11, 11, 4)      // cfg3: frame_stack 4
+  SNK_TRY(16, 64, 15, 15, 1)     // cfg4: 64x64, 16 snakes, vision 7
+#undef SNK_TRY
+  return launch_instance<0, 0, 0, 0, 0>(p, threads, smem_bytes, stream);
 }
 
 cudaError_t launch_get_state(const Dims& d, const uint8_t* recs, const StateView& sv, cudaStream_t s) {

@@ -152,3 +152,80 @@ def test_dropin_api():
     assert o.shape == (16, 4, 11, 11, 8)
     o, r, d, infos = venv.step(np.zeros((16, 4), dtype=np.int64))
     assert r.shape == (16, 4) and d.shape == (16, 4) and len(infos) == 16
+
+
+def test_gpu_generic_kernel_instance(monkeypatch):
+    """The BASELINE shapes run specialised template instances; the unspecialised instance must agree."""
+    from hostsim_util import HostSim
+    monkeypatch.setenv('SNK_FORCE_GENERIC', '1')
+    for kw in (dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5),
+               dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5, frame_stack=4),
+               dict(height=20, width=20, num_snakes=4, snake_length=3)):
+        N = 301
+        hs = HostSim(N, kw, rng_mode=0, auto_reset=1, seed=5)
+        be = GpuBackend(N, kw, rng_mode=0, auto_reset=1, seed=5)
+        assert np.array_equal(hs.reset(), be.reset())
+        rng = np.random.RandomState(2)
+        for t in range(150):
+            a = rng.randint(0, 3, size=(N, 4)).astype(np.uint8)
+            o1, r1, d1, _ = hs.step(a)
+            o2, r2, d2, _ = be.step(a)
+            assert np.array_equal(o1, o2) and np.array_equal(r1, r2) and np.array_equal(d1, d2.astype(np.uint8)), t
+        be.close()
+
+
+@pytest.mark.parametrize('kw,N', [
+    (dict(height=20, width=20, num_snakes=4, snake_length=3), 1000),                                  # cfg2 shape
+    (dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5, frame_stack=4), 1000),   # cfg3 shape
+    (dict(height=64, width=64, num_snakes=16, snake_length=5, vision_range=7,
+          reward_dict={'fruit': 10.0, 'kill': 1.0, 'lose': -1.0, 'win': 0.1, 'time': -0.001}), 70),   # cfg4 shape
+    (dict(height=12, width=17, num_snakes=5, snake_length=3, vision_range=3), 257),                   # generic, odd window
+    (dict(height=8, width=8, num_snakes=1, snake_length=2, vision_range=1, frame_stack=3), 129),
+])
+def test_gpu_matches_hostsim_shapes(kw, N):
+    """BASELINE config shapes (specialised instances) and odd generic shapes against the host build of
+    the same rule source, Philox mode, with info outputs."""
+    from hostsim_util import HostSim
+    ns = kw['num_snakes']
+    hs = HostSim(N, kw, rng_mode=0, auto_reset=1, seed=11)
+    be = GpuBackend(N, kw, rng_mode=0, auto_reset=1, seed=11)
+    assert np.array_equal(hs.reset(), be.reset())
+    rng = np.random.RandomState(3)
+    for t in range(120):
+        a = rng.randint(0, 3, size=(N, ns)).astype(np.uint8)
+        o1, r1, d1, i1 = hs.step(a)
+        o2, r2, d2, i2 = be.step(a)
+        assert np.array_equal(r1, r2) and np.array_equal(d1, d2.astype(np.uint8)), t
+        assert np.array_equal(o1, o2), t
+        fin = i1['finished'].astype(bool)
+        assert np.array_equal(fin, i2['finished'])
+        for k in ('rank', 'episode_scores', 'episode_steps', 'episode_fruits', 'episode_kills'):
+            assert np.array_equal(i1[k][fin], i2[k][fin]), (k, t)
+    assert np.array_equal(hs.grid()[0], be.grid()[0])
+    assert be.errors() == 0
+    be.close()
+
+
+def test_gpu_rollout_stats():
+    """Device-side rollout statistics equal the sums of the per-step terminal info."""
+    from marl_snake_b200 import SnakeBatch
+    N, ns = 3000, 4
+    b = SnakeBatch(N, num_snakes=ns, vision_range=5, seed=3)
+    b.reset()
+    g = torch.Generator(device='cuda').manual_seed(1)
+    eps = ret = fruits = kills = 0.0
+    for _ in range(200):
+        a = torch.randint(0, 3, (N, ns), dtype=torch.uint8, device='cuda', generator=g)
+        _, _, _, info = b.step(a)
+        fin = info['finished']
+        eps += float(fin.sum())
+        ret += float(info['episode_scores'][fin].sum())
+        fruits += float(info['episode_fruits'][fin].sum())
+        kills += float(info['episode_kills'][fin].sum())
+    st = b.stats()
+    assert st['episodes'] == eps and eps > 1000
+    assert st['fruits_sum'] == fruits and st['kills_sum'] == kills
+    assert abs(st['return_sum'] - ret) < 1e-6 * max(1.0, abs(ret))
+    assert st['env_steps'] == 200 * N
+    t = b.stats_tensor()
+    assert float(t[0]) == eps
