@@ -105,21 +105,14 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
   spawn_enumerate(d.H, d.W, d.K, table.data(), nullptr, n_cand);
   d.n_cand = (uint32_t)n_cand;
 
-  // tile shape: environments per CTA sized for ~40 KB of shared memory (a multiple of 32 when
-  // possible: phase L runs one thread per environment), threads per CTA
-  size_t per_env = (size_t)d.rec_bytes + d.scr_bytes + 2;
-  if (d.fs > 1) per_env += d.stage_env_bytes;
-  int E = (int)((size_t)env_int("SNK_TILE_SMEM", 40 * 1024) / per_env);
-  if (E > 64) E = 64;
-  if (E >= 32) E &= ~31; else if (E > 2) E &= ~1;
-  if (E < 1) E = 1;
-  E = env_int("SNK_TILE_ENVS", E);
-  int threads = env_int("SNK_THREADS", 256);
+  // tile shape: a warp owns 32/G environments (G = num_snakes rounded up to a power of two); the CTA
+  // is `threads`/32 independent warps sharing only the lookup table.
+  int threads = env_int("SNK_THREADS", 128);
   if (threads < 32 || threads > SNK_MAX_THREADS || (threads & 31)) { delete h; return fail(SNK_E_INVALID, "SNK_THREADS must be a multiple of 32 in 32..%d", SNK_MAX_THREADS); }
-  if (E < 1 || E > threads) { delete h; return fail(SNK_E_INVALID, "SNK_TILE_ENVS must be in 1..threads"); }
-  h->tile_envs = E; h->threads = threads;
+  while (threads > 32 && tile_smem_bytes(d, threads / 32) > 200 * 1024) threads -= 32;
+  h->tile_envs = 32 / tile_group(d.ns); h->threads = threads;
   h->force_generic = env_int("SNK_FORCE_GENERIC", 0);
-  h->smem_bytes = tile_smem_bytes(d, E);
+  h->smem_bytes = tile_smem_bytes(d, threads / 32);
   if (h->smem_bytes > 227 * 1024) {
     const size_t need = h->smem_bytes;
     delete h;

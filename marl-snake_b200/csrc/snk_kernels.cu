@@ -1,15 +1,20 @@
 // snk_kernels.cu -- sm_100a kernels of the batched Snake-v1 step path.
 //
-// One CTA owns a tile of E consecutive environments.  Their records (grid, body-direction plane,
-// snake table, counters, episode statistics) are contiguous in HBM, so the tile is staged into
-// shared memory with 128-bit coalesced loads, stepped there, and written back the same way.
+// A WARP owns a tile of 32/G consecutive environments, G = num_snakes rounded up to a power of two:
+// lane = (environment in tile, snake).  The tile's records (grid, body-direction plane, snake table,
+// counters, episode statistics) are contiguous in HBM; the warp stages them into its private slice of
+// shared memory with 128-bit coalesced loads, steps them there and writes them back the same way.
+// After the CTA-wide lookup-table build there is no block barrier: warps are independent, so one
+// warp's rule phase overlaps the other warps' observation stores.
 //
-//   phase L  one thread per environment runs the step rules (env_step_logic, snk_core.cuh)
-//   phase R  rare events, one WARP per environment: fruit respawn = k-th empty cell by
-//            ballot/popc rank-select over the grid; auto-reset = spawn sampling + overlap vote
-//   phase A  one warp per (environment, viewer): egocentric crop -> 1 byte of channel bits per
-//            cell, written to a staging area in output order (and to the frame-stack history)
-//   phase B  whole CTA: staging bytes -> NHWC uint8 observation, 128-bit coalesced stores
+//   rules    lanes = snakes: turn, head advance, __match_any_sync on target cells (head-on and arrival
+//            order), ballots for deaths / fruit cells / alive set, shuffles for kill attribution and the
+//            tail-growth rule, float64 reward, clear-then-write grid update      (step_group)
+//   rare     whole warp per environment: fruit respawn = k-th empty cell by ballot/popc rank-select;
+//            auto-reset = spawn picks + paint-and-vote overlap test + fruit seeding
+//   encode   whole warp per (environment, viewer): two crop cells per lane -> LUT -> one 128-bit
+//            streaming store (frame_stack 1); channel-bit frames staged in output order and expanded
+//            with flat 128-bit stores (frame_stack > 1)
 //
 // Reference: SnakeEnv.step / reset / _encode (envs/snake_env.py:301-414, 131-159, 474-519) and the
 // vector worker's auto-reset (wrappers.py:138-146).
@@ -29,7 +34,7 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
 // Place k fruits on the k drawn ranks of the row-major empty-cell list (all ranks refer to the
 // grid as it is before any of them is placed; duplicates collapse)    core/grid_util.py:126-133
-__device__ void place_fruits_warp(const KParams& p, Rec& r, uint32_t env_local, int k, int purpose) {
+__device__ __noinline__ void place_fruits_warp(const KParams& p, Rec& r, uint32_t env_local, int k, int purpose) {
   const Dims& d = p.d;
   const uint32_t lane = lane_id();
   const int HW = d.HW;
@@ -71,7 +76,7 @@ __device__ void place_fruits_warp(const KParams& p, Rec& r, uint32_t env_local, 
 }
 
 // SnakeEnv.reset for one environment record in shared memory      envs/snake_env.py:131-159, 576-596
-__device__ void reset_env_warp(const KParams& p, Rec& r, uint32_t env_local) {
+__device__ __noinline__ void reset_env_warp(const KParams& p, Rec& r, uint32_t env_local) {
   const Dims& d = p.d;
   const uint32_t lane = lane_id();
   const int ns = d.ns, K = d.K, W = d.W;
@@ -165,10 +170,155 @@ struct Shape {
   __device__ __forceinline__ int ohw() const { return oh() * ow(); }
   __device__ __forceinline__ int fs() const { return kFS ? kFS : d.fs; }
   __device__ __forceinline__ int lut_stride() const { return 10 * ns() + 6; }   // cell codes 0 .. 10*(ns-1)+5
+  __device__ __forceinline__ int group() const {                                // lanes per environment
+    const int n = ns();
+    return n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : 32;
+  }
 };
 
 __device__ __forceinline__ void st_cs_128(void* p, uint2 a, uint2 b) { __stcs(reinterpret_cast<uint4*>(p), make_uint4(a.x, a.y, b.x, b.y)); }
 __device__ __forceinline__ void st_cs_64(void* p, uint2 a) { __stcs(reinterpret_cast<uint2*>(p), a); }
+
+// Several lanes of one environment may update plane bytes that share a word: atomic read-modify-write.
+__device__ __forceinline__ void dirp_set_atomic(uint8_t* dirp, int c, int v) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(dirp) + (c >> 4);
+  const int sh = (c & 15) * 2;
+  atomicAnd(w, ~(3u << sh));
+  atomicOr(w, (uint32_t)v << sh);
+}
+
+struct GroupOut {
+  int fruit_taken;     // fruit draws owed by this lane's environment (same on all its lanes)
+  bool finished;       // episode ended this step (same on all lanes of the environment)
+  bool newly_dead;     // this lane's snake died this step
+};
+
+// The step rules with lanes = snakes.  Restates env_step_logic (snk_core.cuh, the sequential form the
+// host simulation runs) for a group of G lanes per environment; tests compare the two on the GPU.
+// `active`: this lane holds a real snake of a real environment.  All 32 lanes must call.
+template <class SH>
+__device__ __forceinline__ GroupOut step_group(const KParams& p, const SH& sh, Rec& r, bool active, int i,
+                                               uint32_t gmask, int gbase, size_t io) {
+  const Dims& d = p.d;
+  const uint32_t FULL = 0xffffffffu;
+  const uint32_t lane = lane_id();
+  const int ns = sh.ns(), W = sh.W(), G = sh.group();
+
+  // 1. relative turn + head advance for live snakes                     snake_env.py:320-330, 598-608
+  const bool was_alive = active && r.alive[i] != 0;
+  int dirv = 0;
+  uint32_t tgt = 0x10000u + lane;                       // unique dummy: never matches a real cell
+  if (was_alive) {
+    uint32_t a = p.actions[io];
+    if (a > 2u) { atomicOr(p.err, ERR_BAD_ACTION); a = 0; }
+    dirv = (r.dir[i] + (a == 1u ? 3 : a == 2u ? 1 : 0)) & 3;
+    tgt = (uint32_t)(r.head[i] + dir_delta(dirv, W));
+  }
+  // 2. one verdict per distinct target cell, on the pre-move grid                      :521-544
+  const uint32_t same = __match_any_sync(FULL, tgt) & gmask;     // snakes of my env entering my cell
+  const int n = __popc(same);
+  const bool first = (__ffs(same) - 1) == (int)lane;             // lowest-index arrival speaks for the cell
+  const uint32_t code = was_alive ? r.grid[tgt] : 0u;
+  const uint32_t owner = (code * 205u) >> 11;
+  const uint32_t kind = code - owner * 10u;
+  const bool lethal = (kind == WALL) | (kind == BODY) | (kind == HEAD);
+  bool died = was_alive && (n > 1 || lethal);
+  const bool credit = died && first && (kind == BODY || kind == HEAD);     // owner paid once per cell (C2)
+  const bool eater = was_alive && !died && kind == FRUIT;
+  const int fruit_taken = __popc(__ballot_sync(FULL, was_alive && first && kind == FRUIT) & gmask);   // (C3)
+  int counter = r.hdr->alive_counter - __popc(__ballot_sync(FULL, died) & gmask);        // :334
+
+  // 3. kill attribution, tail-growth rule                                              :338-346
+  int kl = 0, dec = 0;
+  bool victim = false;
+  const uint32_t my_tail = active ? (uint32_t)r.tail[i] : 0u;
+  for (int j = 0; j < G; ++j) {
+    const int src = gbase + j;
+    const uint32_t oj = __shfl_sync(FULL, credit ? owner : 0xFFu, src);
+    kl += (oj == (uint32_t)i) ? 1 : 0;
+    const uint32_t tj = __shfl_sync(FULL, eater ? my_tail : 0xFFFFFFFFu, src);
+    const bool hit = was_alive && tgt == tj;            // I enter the tail of an eater: it stays (C4)
+    const int hits = __popc(__ballot_sync(FULL, hit) & gmask);
+    victim |= hit;
+    dec += hits;                                        // counted even if already dead
+    if (j == i) kl += hits;
+  }
+  counter -= dec;
+  died |= victim;
+  const bool alive_now = was_alive && !died;
+  const uint32_t alive_m = __ballot_sync(FULL, alive_now) & gmask;
+  const bool won = counter == 1 && ns > 1 && alive_now && (__ffs(alive_m) - 1) == (int)lane;   // :347-352
+
+  // 4. reward: float64, the reference's order, no FMA                                  :365-369
+  double rw = 0.0;
+  if (was_alive) {
+    rw = __dmul_rn(d.r_time, alive_now ? 1.0 : 0.0);
+    rw = __dadd_rn(rw, __dmul_rn(d.r_fruit, eater ? 1.0 : 0.0));
+    rw = __dadd_rn(rw, __dmul_rn(d.r_lose, died ? 1.0 : 0.0));
+    rw = __dadd_rn(rw, __dmul_rn(d.r_kill, (double)kl));
+    rw = __dadd_rn(rw, __dmul_rn(d.r_win, won ? 1.0 : 0.0));
+  }
+
+  // 5. grid update.  The reference walks snakes in index order (:358-373, :546-566); the final grid is
+  //    the same when every clear (vacated tails, bodies of the dead) happens before every write.
+  const int tag = 10 * i;
+  int new_tail = 0;
+  if (was_alive) {
+    if (!alive_now) {
+      int c = r.tail[i];
+      const int hd = r.head[i];
+#pragma unroll 1
+      for (int guard = 0; guard < d.HW; ++guard) {
+        const int nxt = c + dir_delta(dirp_get(r.dirp, c), W);
+        r.grid[c] = (uint8_t)EMPTY;
+        if (c == hd) break;
+        c = nxt;
+      }
+    } else if (!eater) {
+      const int ot = r.tail[i];
+      new_tail = ot + dir_delta(dirp_get(r.dirp, ot), W);
+      r.grid[ot] = (uint8_t)EMPTY;
+    } else {
+      new_tail = r.tail[i];
+    }
+  }
+  __syncwarp();
+  if (active) {
+    if (alive_now) {
+      const int oh = r.head[i];
+      r.grid[oh] = (uint8_t)(BODY + tag);
+      dirp_set_atomic(r.dirp, oh, dirv);
+      r.dir[i] = (uint8_t)dirv;
+      r.tail[i] = (uint16_t)new_tail;
+      if (eater) r.len[i] = (uint16_t)(r.len[i] + 1);
+      r.grid[new_tail] = (uint8_t)(TAIL + tag);        // length 2: overwrites the BODY just written
+      r.head[i] = (uint16_t)tgt;
+      r.grid[tgt] = (uint8_t)(HEAD + tag);
+      r.score[i] = __dadd_rn(r.score[i], rw);          // statistics gate on this step's dones  :385-389
+      r.steps[i] += 1; r.fruits[i] += eater ? 1u : 0u; r.kills[i] += (uint32_t)kl;
+    } else if (was_alive) {
+      r.alive[i] = 0; r.len[i] = 0; r.dir[i] = (uint8_t)dirv;
+    }
+  }
+  __syncwarp();
+
+  // 6. outputs, step cap, episode end                                                  :374, :391-412
+  const int n_done = __popc(__ballot_sync(FULL, active && !alive_now) & gmask);
+  uint32_t ep_len = r.hdr->episode_length + 1u;
+  const bool capped = (double)ep_len >= d.max_steps;
+  const bool fin = d.done_mode == 0 ? (capped || n_done == ns) : (capped || n_done > 0);
+  __syncwarp();
+  if (active) {
+    if (i == 0) { r.hdr->episode_length = ep_len; r.hdr->alive_counter = counter; }
+    p.rew[io] = rw;
+    p.done[io] = (capped || !alive_now || (fin && d.done_mode == 1)) ? 1 : 0;
+  }
+  GroupOut out;
+  out.fruit_taken = fruit_taken;
+  out.finished = fin;
+  out.newly_dead = was_alive && !alive_now;
+  return out;
+}
 
 template <int kNS, int kW, int kOH, int kOW, int kFS>
 __global__ void __launch_bounds__(SNK_MAX_THREADS)
@@ -176,30 +326,28 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const Dims& d = p.d;
   const Shape<kNS, kW, kOH, kOW, kFS> sh(d);
-  const int E = p.E;
+  const uint32_t FULL = 0xffffffffu;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, nwarps = nt >> 5;
   const uint32_t lane = lane_id();
-  const int e0 = blockIdx.x * E;
-  const int ne = min(E, d.N - e0);
-  const int ns = sh.ns();
+  const int ns = sh.ns(), G = sh.group(), EPW = 32 / G;          // environments per warp
   const int fs = sh.fs(), ohw = sh.ohw(), ow = sh.ow(), W = sh.W();
   const int LS = sh.lut_stride();
+  const int e0 = (blockIdx.x * nwarps + warp) * EPW;             // this warp's first environment
+  const int ne = max(0, min(EPW, d.N - e0));
 
-  // shared memory carve-up (offsets computed on the host side the same way, see tile_smem_bytes)
-  uint8_t* s_rec = smem;
-  uint8_t* s_lut = s_rec + (size_t)E * d.rec_bytes;                    // fs==1: uint2[ns*LS]; else uint8[ns*LS]
-  uint8_t* s_stage = s_lut + round_up(ns * LS * (fs == 1 ? 8 : 1), 16);   // fs>1 only
-  uint8_t* s_scr = s_stage + (fs == 1 ? 0 : round_up(E * d.stage_env_bytes, 16));
-  uint8_t* s_fruit = s_scr + (size_t)E * d.scr_bytes;
-  uint8_t* s_flag = s_fruit + E;
+  // shared memory: per-warp slices (records [+ staging when fs > 1]), then the CTA-wide LUT
+  const int warp_bytes = EPW * d.rec_bytes + (fs == 1 ? 0 : round_up(EPW * d.stage_env_bytes, 16));
+  uint8_t* s_rec = smem + (size_t)warp * warp_bytes;
+  uint8_t* s_stage = s_rec + EPW * d.rec_bytes;
+  uint8_t* s_lut = smem + (size_t)nwarps * warp_bytes;           // fs==1: uint2[ns*LS]; else uint8[ns*LS]
 
   // ---- stage the tile's records: HBM -> shared, 128-bit coalesced
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.recs + (size_t)e0 * d.rec_bytes);
     uint4* dst = reinterpret_cast<uint4*>(s_rec);
     const int n16 = ne * (d.rec_bytes >> 4);
-    for (int i = tid; i < n16; i += nt) dst[i] = __ldcs(src + i);
+    for (int k = (int)lane; k < n16; k += 32) dst[k] = __ldcs(src + k);
   }
   // ---- per-viewer lookup table: cell code -> channel bits (expanded to 8 bytes when fs == 1)
   for (int idx = tid; idx < ns * LS; idx += nt) {
@@ -208,80 +356,84 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
     if (fs == 1) reinterpret_cast<uint2*>(s_lut)[idx] = make_uint2(spread4(bits & 15u), spread4(bits >> 4));
     else s_lut[idx] = (uint8_t)bits;
   }
-  __syncthreads();
+  __syncthreads();                                                // the only block barrier
+  if (ne == 0) return;
 
-  // ---- phase L: one thread per environment
-  int deaths = 0, ended = 0;
-  double ret_sum = 0.0; uint32_t len_sum = 0, fruit_sum = 0, kill_sum = 0;
-  if (tid < ne) {
-    const int e = e0 + tid;
-    uint8_t* base = s_rec + (size_t)tid * d.rec_bytes;
-    Rec r = rec_view(base, d);
-    uint8_t flag = 0, fruit = 0;
-    if (p.mode == MODE_STEP) {
-      r.hdr->event += 1;
-      uint32_t err = 0;
-      const StepResult res = env_step_logic(d, base, s_scr + (size_t)tid * d.scr_bytes,
-                                            p.actions + (size_t)e * ns, p.rew + (size_t)e * ns,
-                                            p.done + (size_t)e * ns, &err);
-      if (err) atomicOr(p.err, err);
-      fruit = res.fruit_taken;
-      deaths = res.deaths;
-      if (p.fin) p.fin[e] = res.finished;
-      if (res.finished) {
-        ended = 1;
-        len_sum = r.hdr->episode_length;
-        for (int i = 0; i < ns; ++i) {
-          const size_t o = (size_t)e * ns + i;
-          if (p.rank) p.rank[o] = competition_rank(r.score, ns, i);
-          if (p.ep_scores) p.ep_scores[o] = r.score[i];
-          if (p.ep_steps) p.ep_steps[o] = (int32_t)r.steps[i];
-          if (p.ep_fruits) p.ep_fruits[o] = (int32_t)r.fruits[i];
-          if (p.ep_kills) p.ep_kills[o] = (int32_t)r.kills[i];
-          ret_sum += r.score[i]; fruit_sum += r.fruits[i]; kill_sum += r.kills[i];
-        }
-        for (int i = 0; i < ns; ++i) { r.score[i] = 0.0; r.steps[i] = 0; r.fruits[i] = 0; r.kills[i] = 0; }   // :412
-        if (d.auto_reset) flag |= F_RESET;                                        // wrappers.py:141-143
+  // ---- lane = (environment g of the tile, snake i)
+  const int g = (int)lane / G, i = (int)lane - g * G;
+  const int gbase = g * G;
+  const uint32_t gmask = (G == 32 ? FULL : ((1u << G) - 1u)) << gbase;
+  const bool env_ok = g < ne;
+  const bool active = env_ok && i < ns;
+  const int e = e0 + g;
+  Rec r = rec_view(s_rec + (size_t)(env_ok ? g : 0) * d.rec_bytes, d);
+  const size_t io = (size_t)e * ns + i;
+
+  uint8_t flag = 0;            // per environment (identical on its lanes)
+  int fruit = 0;
+  if (p.mode == MODE_STEP) {
+    if (active && i == 0) r.hdr->event += 1;
+    __syncwarp();
+    const GroupOut res = step_group(p, sh, r, active, i, gmask, gbase, io);
+    fruit = res.fruit_taken;
+    // terminal info, rollout statistics, statistics reset                          :396-412
+    const bool fin = env_ok && res.finished;
+    if (active && i == 0 && p.fin) p.fin[e] = fin ? 1 : 0;
+    const uint32_t fin_m = __ballot_sync(FULL, fin && i == 0);
+    const uint32_t dead_m = __ballot_sync(FULL, res.newly_dead);
+    if (lane == 0 && dead_m) atomicAdd(p.stats + STAT_DEATHS, (double)__popc(dead_m));
+    if (fin_m) {                                                  // some environment of the tile ended
+      const double my_score = active ? r.score[i] : 0.0;
+      int rk = 1;
+      for (int j = 0; j < G; ++j) {
+        const double sj = __shfl_sync(FULL, my_score, gbase + j);
+        rk += (j < ns && sj > my_score) ? 1 : 0;                  // competition rank          :397-404
       }
-    } else {
-      const bool sel = p.mask == nullptr || p.mask[e] != 0;
-      if (!sel) flag = F_SKIP;
-      else if (p.mode == MODE_RESET) { r.hdr->event += 1; flag = F_RESET; }
-      else flag = F_INIT;
-    }
-    s_fruit[tid] = fruit;
-    s_flag[tid] = flag;
-  }
-  if (p.mode == MODE_STEP && warp * 32 < ne) {        // warp-aggregated rollout statistics
-    const int dsum = __reduce_add_sync(0xffffffffu, deaths);
-    const uint32_t any_end = __ballot_sync(0xffffffffu, ended);
-    if (lane == 0 && dsum) atomicAdd(p.stats + STAT_DEATHS, (double)dsum);
-    if (any_end) {
-      const uint32_t ls = __reduce_add_sync(0xffffffffu, len_sum);
-      const uint32_t fsum = __reduce_add_sync(0xffffffffu, fruit_sum);
-      const uint32_t ks = __reduce_add_sync(0xffffffffu, kill_sum);
-      if (ended) atomicAdd(p.stats + STAT_RETURN, ret_sum);
+      double ret = 0.0; uint32_t fr = 0, kl = 0, ln = 0;
+      if (fin && active) {
+        if (p.rank) p.rank[io] = rk;
+        if (p.ep_scores) p.ep_scores[io] = my_score;
+        if (p.ep_steps) p.ep_steps[io] = (int32_t)r.steps[i];
+        if (p.ep_fruits) p.ep_fruits[io] = (int32_t)r.fruits[i];
+        if (p.ep_kills) p.ep_kills[io] = (int32_t)r.kills[i];
+        ret = my_score; fr = r.fruits[i]; kl = r.kills[i];
+        if (i == 0) ln = r.hdr->episode_length;
+        r.score[i] = 0.0; r.steps[i] = 0; r.fruits[i] = 0; r.kills[i] = 0;
+      }
+      for (int o = 16; o; o >>= 1) ret += __shfl_xor_sync(FULL, ret, o);
+      fr = __reduce_add_sync(FULL, fr); kl = __reduce_add_sync(FULL, kl); ln = __reduce_add_sync(FULL, ln);
       if (lane == 0) {
-        atomicAdd(p.stats + STAT_EPISODES, (double)__popc(any_end));
-        atomicAdd(p.stats + STAT_EP_STEPS, (double)ls);
-        atomicAdd(p.stats + STAT_FRUITS, (double)fsum);
-        atomicAdd(p.stats + STAT_KILLS, (double)ks);
+        atomicAdd(p.stats + STAT_EPISODES, (double)__popc(fin_m));
+        atomicAdd(p.stats + STAT_RETURN, ret);
+        atomicAdd(p.stats + STAT_EP_STEPS, (double)ln);
+        atomicAdd(p.stats + STAT_FRUITS, (double)fr);
+        atomicAdd(p.stats + STAT_KILLS, (double)kl);
       }
+      if (fin && d.auto_reset) flag |= F_RESET;                   // wrappers.py:141-143
     }
+  } else {
+    const bool sel = env_ok && (p.mask == nullptr || p.mask[e] != 0);
+    if (!sel) flag = F_SKIP;
+    else if (p.mode == MODE_RESET) { if (i == 0) r.hdr->event += 1; flag = F_RESET; }
+    else flag = F_INIT;
   }
-  __syncthreads();
+  if (!env_ok) flag = F_SKIP;
+  __syncwarp();
 
-  // ---- phase R: rare events, one warp per environment
-  for (int el = warp; el < ne; el += nwarps) {
-    const uint8_t fruit = s_fruit[el], flag = s_flag[el];
-    if (!fruit && !(flag & F_RESET)) continue;
-    Rec r = rec_view(s_rec + (size_t)el * d.rec_bytes, d);
-    if (fruit) place_fruits_warp(p, r, (uint32_t)(e0 + el), fruit, DRAW_STEP_FRUIT);
-    if (flag & F_RESET) reset_env_warp(p, r, (uint32_t)(e0 + el));
+  // ---- rare events, whole warp per environment
+#pragma unroll 1
+  for (int q = 0; q < ne; ++q) {
+    const int qf = __shfl_sync(FULL, fruit, q * G);
+    const int qflag = __shfl_sync(FULL, (int)flag, q * G);
+    if (!qf && !(qflag & F_RESET)) continue;
+    Rec rq = rec_view(s_rec + (size_t)q * d.rec_bytes, d);
+    if (qf) place_fruits_warp(p, rq, (uint32_t)(e0 + q), qf, DRAW_STEP_FRUIT);
+    if (qflag & F_RESET) reset_env_warp(p, rq, (uint32_t)(e0 + q));
   }
-  __syncthreads();
+  __syncwarp();
 
   const bool want_obs = p.obs != nullptr;
+  const int H = d.H, V = d.V;
 
   if (fs == 1) {
     // ---- write the records back: shared -> HBM (nothing below modifies them)
@@ -289,55 +441,56 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
       uint4* dst = reinterpret_cast<uint4*>(p.recs + (size_t)e0 * d.rec_bytes);
       const uint4* src = reinterpret_cast<const uint4*>(s_rec);
       const int n16 = ne * (d.rec_bytes >> 4);
-      for (int i = tid; i < n16; i += nt) dst[i] = src[i];
+      for (int k = (int)lane; k < n16; k += 32) dst[k] = src[k];
     }
-    // ---- fused encode: one warp per (environment, viewer); each lane produces 16 output bytes
-    //      (two cells x 8 channels) per iteration straight from the staged grid through the LUT.
+    // ---- fused encode: whole warp per (environment, viewer); each lane produces 16 output bytes (two
+    //      cells x 8 channels) per iteration straight from the staged grid through the LUT.
     //      snake_env.py:474-519.  A viewer's block of ohw*8 bytes is only 8-byte aligned when ohw is
-    //      odd, so its 16-byte units are laid out from the address parity and the two end units may
-    //      be half units.
+    //      odd, so its 16-byte units are laid out from the address parity and the end units may be half.
     if (want_obs) {
       const uint2* lut_all = reinterpret_cast<const uint2*>(s_lut);
-      const int H = d.H, V = d.V;
-      const int pairs = ne * ns;
-      for (int pv = warp; pv < pairs; pv += nwarps) {
-        const int el = pv / ns, v = pv - el * ns;
-        if (s_flag[el] & F_SKIP) continue;
-        const uint8_t* base = s_rec + (size_t)el * d.rec_bytes;
+#pragma unroll 1
+      for (int q = 0; q < ne; ++q) {
+        const int qflag = __shfl_sync(FULL, (int)flag, q * G);
+        if (qflag & F_SKIP) continue;
+        const uint8_t* base = s_rec + (size_t)q * d.rec_bytes;
         const uint8_t* grid = base;
-        const uint8_t alive = base[d.off_snk + 7 * ns + v];
-        // crop centre: own head, or cell (0,0) when the viewer has no head in the grid   :500-502
-        const int hc = alive ? (int)((const uint16_t*)(base + d.off_snk))[v] : 0;
-        int r0 = 0, c0 = 0;
-        if (V > 0) { const int hr = hc / W; r0 = hr - V; c0 = hc - hr * W - V; }
-        uint8_t* outv = p.obs + ((size_t)(e0 + el) * ns + v) * (size_t)ohw * 8;
-        const int shift = (int)((reinterpret_cast<uintptr_t>(outv) >> 3) & 1);
-        const uint2* lut = lut_all + v * LS;
-        const int units = (ohw + shift + 1) >> 1;
-        for (int u = (int)lane; u < units; u += 32) {
-          const int ca = 2 * u - shift, cb = ca + 1;
-          const bool va = ca >= 0, vb = cb < ohw;
-          uint2 qa = make_uint2(0, 0), qb = make_uint2(0, 0);
-          {
-            const int c = va ? ca : 0;
-            const int i = c / ow, j = c - i * ow;
-            const int rr = r0 + i, cc = c0 + j;
-            uint32_t code = 0;
-            if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
-            qa = lut[code];
+#pragma unroll 1
+        for (int v = 0; v < ns; ++v) {
+          const uint8_t alive = base[d.off_snk + 7 * ns + v];
+          // crop centre: own head, or cell (0,0) when the viewer has no head in the grid   :500-502
+          const int hc = alive ? (int)((const uint16_t*)(base + d.off_snk))[v] : 0;
+          int r0 = 0, c0 = 0;
+          if (V > 0) { const int hr = hc / W; r0 = hr - V; c0 = hc - hr * W - V; }
+          uint8_t* outv = p.obs + ((size_t)(e0 + q) * ns + v) * (size_t)ohw * 8;
+          const int shift = (int)((reinterpret_cast<uintptr_t>(outv) >> 3) & 1);
+          const uint2* lut = lut_all + v * LS;
+          const int units = (ohw + shift + 1) >> 1;
+          for (int u = (int)lane; u < units; u += 32) {
+            const int ca = 2 * u - shift, cb = ca + 1;
+            const bool va = ca >= 0, vb = cb < ohw;
+            uint2 qa, qb;
+            {
+              const int c = va ? ca : 0;
+              const int ci = c / ow, cj = c - ci * ow;
+              const int rr = r0 + ci, cc = c0 + cj;
+              uint32_t code = 0;
+              if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
+              qa = lut[code];
+            }
+            {
+              const int c = vb ? cb : 0;
+              const int ci = c / ow, cj = c - ci * ow;
+              const int rr = r0 + ci, cc = c0 + cj;
+              uint32_t code = 0;
+              if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
+              qb = lut[code];
+            }
+            uint8_t* dst = outv + (ptrdiff_t)ca * 8;
+            if (va && vb) st_cs_128(dst, qa, qb);
+            else if (va) st_cs_64(dst, qa);
+            else st_cs_64(dst + 8, qb);
           }
-          {
-            const int c = vb ? cb : 0;
-            const int i = c / ow, j = c - i * ow;
-            const int rr = r0 + i, cc = c0 + j;
-            uint32_t code = 0;
-            if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
-            qb = lut[code];
-          }
-          uint8_t* dst = outv + (ptrdiff_t)ca * 8;
-          if (va && vb) st_cs_128(dst, qa, qb);
-          else if (va) st_cs_64(dst, qa);
-          else st_cs_64(dst + 8, qb);
         }
       }
     }
@@ -347,47 +500,48 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   // ================= frame_stack > 1: channel-bit frames staged in output order ======================
   // ---- older frames of the stack: history rows -> staging (oldest-first)
   if (want_obs) {
-    const int rows = ne * ns * fs;
-    for (int row = warp; row < rows; row += nwarps) {
-      const int el = row / (ns * fs);
-      const int rem = row - el * ns * fs;
-      const int v = rem / fs, slot = rem - v * fs;
-      if (s_flag[el] & (F_RESET | F_INIT | F_SKIP)) continue;
-      const int hpos = (int)((const EnvHdr*)(s_rec + (size_t)el * d.rec_bytes + d.off_hdr))->hpos;
-      if (slot == hpos) continue;                  // about to be overwritten by the new frame
-      int f = slot - hpos - 1; if (f < 0) f += fs;
-      const uint8_t* src = p.hist + (size_t)(e0 + el) * d.hist_env_bytes + (size_t)(v * fs + slot) * d.ohw_p;
-      uint8_t* dst = s_stage + (size_t)el * d.stage_env_bytes + (size_t)v * ohw * fs + f;
-      for (int c4 = (int)lane * 4; c4 < ohw; c4 += 128) {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(src + c4);
+#pragma unroll 1
+    for (int q = 0; q < ne; ++q) {
+      const int qflag = __shfl_sync(FULL, (int)flag, q * G);
+      if (qflag & (F_RESET | F_INIT | F_SKIP)) continue;
+      const int hpos = (int)((const EnvHdr*)(s_rec + (size_t)q * d.rec_bytes + d.off_hdr))->hpos;
+#pragma unroll 1
+      for (int vs = 0; vs < ns * fs; ++vs) {
+        const int v = vs / fs, slot = vs - v * fs;
+        if (slot == hpos) continue;                  // about to be overwritten by the new frame
+        int f = slot - hpos - 1; if (f < 0) f += fs;
+        const uint8_t* src = p.hist + (size_t)(e0 + q) * d.hist_env_bytes + (size_t)vs * d.ohw_p;
+        uint8_t* dst = s_stage + (size_t)q * d.stage_env_bytes + (size_t)v * ohw * fs + f;
+        for (int c4 = (int)lane * 4; c4 < ohw; c4 += 128) {
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(src + c4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (c4 + k < ohw) dst[(size_t)(c4 + k) * fs] = (uint8_t)(w >> (8 * k));
+          for (int k = 0; k < 4; ++k)
+            if (c4 + k < ohw) dst[(size_t)(c4 + k) * fs] = (uint8_t)(w >> (8 * k));
+        }
       }
     }
   }
-  // ---- phase A: encode the new frame, one warp per (environment, viewer)     snake_env.py:474-519
-  {
-    const int H = d.H, V = d.V;
-    const int pairs = ne * ns;
-    for (int pv = warp; pv < pairs; pv += nwarps) {
-      const int el = pv / ns, v = pv - el * ns;
-      const uint8_t flag = s_flag[el];
-      if (flag & F_SKIP) continue;
-      const uint8_t* base = s_rec + (size_t)el * d.rec_bytes;
-      const uint8_t* grid = base;
+  // ---- encode the new frame, whole warp per (environment, viewer)            snake_env.py:474-519
+#pragma unroll 1
+  for (int q = 0; q < ne; ++q) {
+    const int qflag = __shfl_sync(FULL, (int)flag, q * G);
+    if (qflag & F_SKIP) continue;
+    const uint8_t* base = s_rec + (size_t)q * d.rec_bytes;
+    const uint8_t* grid = base;
+    const bool init = (qflag & (F_RESET | F_INIT)) != 0;
+    const int hpos = (int)((const EnvHdr*)(base + d.off_hdr))->hpos;
+#pragma unroll 1
+    for (int v = 0; v < ns; ++v) {
       const uint8_t alive = base[d.off_snk + 7 * ns + v];
       const int hc = alive ? (int)((const uint16_t*)(base + d.off_snk))[v] : 0;
       int r0 = 0, c0 = 0;
       if (V > 0) { const int hr = hc / W; r0 = hr - V; c0 = hc - hr * W - V; }
-      const bool init = (flag & (F_RESET | F_INIT)) != 0;
-      const int hpos = (int)((const EnvHdr*)(base + d.off_hdr))->hpos;
       const uint8_t* lut = s_lut + v * LS;
-      uint8_t* stg = s_stage + (size_t)el * d.stage_env_bytes + (size_t)v * ohw * fs;
-      uint8_t* hrow = p.hist + (size_t)(e0 + el) * d.hist_env_bytes + (size_t)(v * fs) * d.ohw_p;
+      uint8_t* stg = s_stage + (size_t)q * d.stage_env_bytes + (size_t)v * ohw * fs;
+      uint8_t* hrow = p.hist + (size_t)(e0 + q) * d.hist_env_bytes + (size_t)(v * fs) * d.ohw_p;
       for (int cell = (int)lane; cell < ohw; cell += 32) {
-        const int i = cell / ow, j = cell - i * ow;
-        const int rr = r0 + i, cc = c0 + j;
+        const int ci = cell / ow, cj = cell - ci * ow;
+        const int rr = r0 + ci, cc = c0 + cj;
         uint32_t code = 0;
         if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
         const uint8_t bits = lut[code];
@@ -403,22 +557,20 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
       }
     }
   }
-  __syncthreads();
-  if (tid < ne && !(s_flag[tid] & F_SKIP)) {
-    EnvHdr* h = (EnvHdr*)(s_rec + (size_t)tid * d.rec_bytes + d.off_hdr);
-    h->hpos = (s_flag[tid] & (F_RESET | F_INIT)) ? 0u : (h->hpos + 1u) % (uint32_t)fs;
-  }
-  __syncthreads();
+  __syncwarp();
+  if (active && i == 0 && !(flag & F_SKIP))
+    r.hdr->hpos = (flag & (F_RESET | F_INIT)) ? 0u : (r.hdr->hpos + 1u) % (uint32_t)fs;
+  __syncwarp();
 
   // ---- write the records back: shared -> HBM
   {
     uint4* dst = reinterpret_cast<uint4*>(p.recs + (size_t)e0 * d.rec_bytes);
     const uint4* src = reinterpret_cast<const uint4*>(s_rec);
     const int n16 = ne * (d.rec_bytes >> 4);
-    for (int i = tid; i < n16; i += nt) dst[i] = src[i];
+    for (int k = (int)lane; k < n16; k += 32) dst[k] = src[k];
   }
 
-  // ---- phase B: channel bits -> NHWC uint8, coalesced
+  // ---- channel bits -> NHWC uint8, coalesced
   if (want_obs) {
     uint8_t* out = p.obs + (size_t)e0 * d.obs_env_bytes;
     if (p.mode == MODE_STEP && p.vec16) {
@@ -426,23 +578,25 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
       const int n16 = total >> 1;
       const uint16_t* s2 = reinterpret_cast<const uint16_t*>(s_stage);
       uint4* o4 = reinterpret_cast<uint4*>(out);
-      for (int u = tid; u < n16; u += nt) {
+      for (int u = (int)lane; u < n16; u += 32) {
         const uint32_t two = s2[u];
-        uint4 q;
-        q.x = spread4(two & 15u); q.y = spread4((two >> 4) & 15u);
-        q.z = spread4((two >> 8) & 15u); q.w = spread4(two >> 12);
-        __stcs(o4 + u, q);
+        uint4 qv;
+        qv.x = spread4(two & 15u); qv.y = spread4((two >> 4) & 15u);
+        qv.z = spread4((two >> 8) & 15u); qv.w = spread4(two >> 12);
+        __stcs(o4 + u, qv);
       }
-      if ((total & 1) && tid == 0) {
+      if ((total & 1) && lane == 0) {
         const uint32_t b = s_stage[total - 1];
         __stcs(reinterpret_cast<uint2*>(out) + (total - 1), make_uint2(spread4(b & 15u), spread4(b >> 4)));
       }
     } else {
-      for (int el = 0; el < ne; ++el) {
-        if (s_flag[el] & F_SKIP) continue;
-        const uint8_t* stg = s_stage + (size_t)el * d.stage_env_bytes;
-        uint2* o2 = reinterpret_cast<uint2*>(out + (size_t)el * d.obs_env_bytes);
-        for (int u = tid; u < d.stage_env_bytes; u += nt) {
+#pragma unroll 1
+      for (int q = 0; q < ne; ++q) {
+        const int qflag = __shfl_sync(FULL, (int)flag, q * G);
+        if (qflag & F_SKIP) continue;
+        const uint8_t* stg = s_stage + (size_t)q * d.stage_env_bytes;
+        uint2* o2 = reinterpret_cast<uint2*>(out + (size_t)q * d.obs_env_bytes);
+        for (int u = (int)lane; u < d.stage_env_bytes; u += 32) {
           const uint32_t b = stg[u];
           __stcs(o2 + u, make_uint2(spread4(b & 15u), spread4(b >> 4)));
         }
@@ -517,12 +671,15 @@ __global__ void snk_init_records_kernel(const Dims d, uint8_t* __restrict__ recs
 }
 
 // ---- launch wrappers -----------------------------------------------------------------------------
-size_t tile_smem_bytes(const Dims& d, int E) {
+int tile_group(int ns) { return ns <= 1 ? 1 : ns <= 2 ? 2 : ns <= 4 ? 4 : ns <= 8 ? 8 : ns <= 16 ? 16 : 32; }
+
+// Shared memory of one CTA of `warps` warps (must mirror the carve-up in snk_tile_kernel).
+size_t tile_smem_bytes(const Dims& d, int warps) {
+  const int EPW = 32 / tile_group(d.ns);
   const int LS = 10 * d.ns + 6;
-  size_t b = (size_t)E * d.rec_bytes + (size_t)round_up(d.ns * LS * (d.fs == 1 ? 8 : 1), 16);
-  if (d.fs > 1) b += (size_t)round_up(E * d.stage_env_bytes, 16);
-  b += (size_t)E * d.scr_bytes + 2 * (size_t)E + 16;
-  return b;
+  size_t per_warp = (size_t)EPW * d.rec_bytes;
+  if (d.fs > 1) per_warp += (size_t)round_up(EPW * d.stage_env_bytes, 16);
+  return per_warp * warps + (size_t)round_up(d.ns * LS * (d.fs == 1 ? 8 : 1), 16) + 16;
 }
 
 template <int kNS, int kW, int kOH, int kOW, int kFS>
@@ -534,7 +691,8 @@ static cudaError_t launch_instance(const KParams& p, int threads, size_t smem_by
     if (e != cudaSuccess) return e;
     configured = smem_bytes;
   }
-  const int grid = (p.d.N + p.E - 1) / p.E;
+  const int envs_per_cta = (threads / 32) * (32 / tile_group(p.d.ns));
+  const int grid = (p.d.N + envs_per_cta - 1) / envs_per_cta;
   kern<<<grid, threads, smem_bytes, stream>>>(p);
   return cudaGetLastError();
 }

@@ -34,7 +34,7 @@ struct KParams {
   int32_t* ep_kills;
   const uint8_t* mask;
   int32_t mode;
-  int32_t E;                   // environments per CTA
+  int32_t E;                   // environments per warp tile (32 / group size), informational
   int32_t vec16;               // 128-bit observation stores are legal for every tile (fs > 1 path)
   int32_t force_generic;       // run the unspecialised kernel instance (tests)
 };
@@ -44,7 +44,8 @@ struct StateView {
   int32_t* alive_counter; int32_t* episode_length; int32_t* cells; int32_t max_cells;
 };
 
-size_t tile_smem_bytes(const Dims& d, int E);
+int tile_group(int ns);
+size_t tile_smem_bytes(const Dims& d, int warps);
 cudaError_t launch_tile_kernel(const KParams& p, int threads, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_get_state(const Dims& d, const uint8_t* recs, const StateView& sv, cudaStream_t s);
 cudaError_t launch_set_state(const Dims& d, uint8_t* recs, const StateView& sv, cudaStream_t s);
