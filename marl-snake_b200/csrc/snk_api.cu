@@ -43,6 +43,8 @@ struct snk_env {
   int64_t* replay_off = nullptr;
   uint32_t* err = nullptr;
   double* stats = nullptr;
+  uint8_t* enc_blob = nullptr;
+  int enc_blob_bytes = 0, enc_tab_off = 0, use_tab = 0;
   // device mirrors used by the *_host entry points
   uint8_t* h_actions = nullptr; uint8_t* h_obs = nullptr; double* h_rew = nullptr; uint8_t* h_done = nullptr;
   cudaStream_t own_stream = nullptr;
@@ -68,6 +70,7 @@ static KParams base_params(const snk_env* h) {
   p.err = h->err; p.stats = h->stats;
   p.E = h->tile_envs;
   p.force_generic = h->force_generic;
+  p.enc_blob = h->enc_blob; p.enc_blob_bytes = h->enc_blob_bytes; p.enc_tab_off = h->enc_tab_off; p.use_tab = h->use_tab;
   return p;
 }
 
@@ -107,7 +110,7 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
 
   // tile shape: a warp owns 32/G environments (G = num_snakes rounded up to a power of two); the CTA
   // is `threads`/32 independent warps sharing only the lookup table.
-  int threads = env_int("SNK_THREADS", 128);
+  int threads = env_int("SNK_THREADS", 64);
   if (threads < 32 || threads > SNK_MAX_THREADS || (threads & 31)) { delete h; return fail(SNK_E_INVALID, "SNK_THREADS must be a multiple of 32 in 32..%d", SNK_MAX_THREADS); }
   while (threads > 32 && tile_smem_bytes(d, threads / 32) > 200 * 1024) threads -= 32;
   h->tile_envs = 32 / tile_group(d.ns); h->threads = threads;
@@ -129,6 +132,16 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
   CUH(cudaMalloc(&h->stats, STAT_COUNT * sizeof(double)));
   CUH(cudaMalloc(&h->replay_off, ((size_t)d.N + 1) * sizeof(int64_t)));
   CUH(cudaMemcpy(h->spawn, table.data(), table.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  if (d.fs == 1) {
+    size_t tab_off = 0;
+    const size_t nb = encode_blob_bytes(d, &tab_off);
+    std::vector<uint8_t> blob(nb, 0);
+    encode_blob_fill(d, blob.data());
+    CUH(cudaMalloc(&h->enc_blob, nb));
+    CUH(cudaMemcpy(h->enc_blob, blob.data(), nb, cudaMemcpyHostToDevice));
+    h->enc_blob_bytes = (int)nb; h->enc_tab_off = (int)tab_off;
+    h->use_tab = encode_uses_table(d) && !env_int("SNK_NO_TABLE", 0) ? 1 : 0;
+  }
   CUH(cudaMemset(h->err, 0, sizeof(uint32_t)));
   CUH(cudaMemset(h->stats, 0, STAT_COUNT * sizeof(double)));
   CUH(cudaMemset(h->replay_off, 0, ((size_t)d.N + 1) * sizeof(int64_t)));
@@ -145,7 +158,7 @@ extern "C" int snk_destroy(snk_env* h) {
   if (!h) return SNK_OK;
   cudaSetDevice(h->device);
   cudaFree(h->recs); cudaFree(h->hist); cudaFree(h->spawn); cudaFree(h->replay); cudaFree(h->replay_off);
-  cudaFree(h->err); cudaFree(h->stats);
+  cudaFree(h->err); cudaFree(h->stats); cudaFree(h->enc_blob);
   cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_rew); cudaFree(h->h_done);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;

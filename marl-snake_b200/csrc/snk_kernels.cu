@@ -179,6 +179,17 @@ struct Shape {
 __device__ __forceinline__ void st_cs_128(void* p, uint2 a, uint2 b) { __stcs(reinterpret_cast<uint4*>(p), make_uint4(a.x, a.y, b.x, b.y)); }
 __device__ __forceinline__ void st_cs_64(void* p, uint2 a) { __stcs(reinterpret_cast<uint2*>(p), a); }
 
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+
 // Several lanes of one environment may update plane bytes that share a word: atomic read-modify-write.
 __device__ __forceinline__ void dirp_set_atomic(uint8_t* dirp, int c, int v) {
   uint32_t* w = reinterpret_cast<uint32_t*>(dirp) + (c >> 4);
@@ -349,12 +360,17 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
     const int n16 = ne * (d.rec_bytes >> 4);
     for (int k = (int)lane; k < n16; k += 32) dst[k] = __ldcs(src + k);
   }
-  // ---- per-viewer lookup table: cell code -> channel bits (expanded to 8 bytes when fs == 1)
-  for (int idx = tid; idx < ns * LS; idx += nt) {
-    const int v = idx / LS, code = idx - v * LS;
-    const uint32_t bits = cell_bits((uint32_t)code, (uint32_t)v);
-    if (fs == 1) reinterpret_cast<uint2*>(s_lut)[idx] = make_uint2(spread4(bits & 15u), spread4(bits >> 4));
-    else s_lut[idx] = (uint8_t)bits;
+  // ---- encode tables.  fs == 1: host-built blob {cell code -> 8 output bytes per viewer, window-cell
+  //      table}, L2-resident, copied with 128-bit loads.  fs > 1: cell code -> channel-bit byte.
+  if (fs == 1) {
+    const uint4* src = reinterpret_cast<const uint4*>(p.enc_blob);
+    uint4* dst = reinterpret_cast<uint4*>(s_lut);
+    for (int k = tid; k < (p.enc_blob_bytes >> 4); k += nt) dst[k] = __ldg(src + k);
+  } else {
+    for (int idx = tid; idx < ns * LS; idx += nt) {
+      const int v = idx / LS, code = idx - v * LS;
+      s_lut[idx] = (uint8_t)cell_bits((uint32_t)code, (uint32_t)v);
+    }
   }
   __syncthreads();                                                // the only block barrier
   if (ne == 0) return;
@@ -447,14 +463,21 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
     //      cells x 8 channels) per iteration straight from the staged grid through the LUT.
     //      snake_env.py:474-519.  A viewer's block of ohw*8 bytes is only 8-byte aligned when ohw is
     //      odd, so its 16-byte units are laid out from the address parity and the end units may be half.
+    //      Per window cell a host-built table gives {row bit | column bit << 16, grid offset}; the
+    //      zero padding outside the grid (:506-515) is one AND/compare against the viewer's valid
+    //      row / column masks.
     if (want_obs) {
+      const uint32_t lut32 = (uint32_t)__cvta_generic_to_shared(s_lut);
+      const uint32_t tab32 = lut32 + (uint32_t)p.enc_tab_off + 8u;       // entry of window cell 0
       const uint2* lut_all = reinterpret_cast<const uint2*>(s_lut);
+      const int oh = sh.oh();
 #pragma unroll 1
       for (int q = 0; q < ne; ++q) {
         const int qflag = __shfl_sync(FULL, (int)flag, q * G);
         if (qflag & F_SKIP) continue;
         const uint8_t* base = s_rec + (size_t)q * d.rec_bytes;
         const uint8_t* grid = base;
+        const uint32_t grid32 = (uint32_t)__cvta_generic_to_shared(grid);
 #pragma unroll 1
         for (int v = 0; v < ns; ++v) {
           const uint8_t alive = base[d.off_snk + 7 * ns + v];
@@ -464,32 +487,71 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
           if (V > 0) { const int hr = hc / W; r0 = hr - V; c0 = hc - hr * W - V; }
           uint8_t* outv = p.obs + ((size_t)(e0 + q) * ns + v) * (size_t)ohw * 8;
           const int shift = (int)((reinterpret_cast<uintptr_t>(outv) >> 3) & 1);
-          const uint2* lut = lut_all + v * LS;
           const int units = (ohw + shift + 1) >> 1;
-          for (int u = (int)lane; u < units; u += 32) {
-            const int ca = 2 * u - shift, cb = ca + 1;
-            const bool va = ca >= 0, vb = cb < ohw;
-            uint2 qa, qb;
-            {
-              const int c = va ? ca : 0;
-              const int ci = c / ow, cj = c - ci * ow;
-              const int rr = r0 + ci, cc = c0 + cj;
-              uint32_t code = 0;
-              if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
-              qa = lut[code];
+          if (p.use_tab) {
+            uint32_t maskpk = 0;
+            if (V > 0) {
+              const int rlo = max(0, -r0), rhi = min(oh, H - r0), clo = max(0, -c0), chi = min(ow, W - c0);
+              const uint32_t rm = ((1u << rhi) - 1u) & ~((1u << rlo) - 1u);
+              const uint32_t cm = ((1u << chi) - 1u) & ~((1u << clo) - 1u);
+              maskpk = rm | (cm << 16);
             }
-            {
-              const int c = vb ? cb : 0;
-              const int ci = c / ow, cj = c - ci * ow;
-              const int rr = r0 + ci, cc = c0 + cj;
-              uint32_t code = 0;
-              if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
-              qb = lut[code];
+            const uint32_t lutv32 = lut32 + (uint32_t)(v * LS) * 8u;     // entry 0 is all zero
+            const uint32_t gorg = grid32 + (uint32_t)(r0 * W + c0);
+            // two units per lane per trip: all table loads, then all grid bytes, then all LUT rows,
+            // so the three dependent shared-memory round trips of both units overlap
+            for (int u0 = (int)lane; u0 < units; u0 += 64) {
+              const int u1 = u0 + 32;
+              const bool has1 = u1 < units;
+              const int ca0 = 2 * u0 - shift, ca1 = 2 * (has1 ? u1 : u0) - shift;
+              const uint2 ea0 = lds_v2(tab32 + (uint32_t)(ca0 * 8));
+              const uint2 eb0 = lds_v2(tab32 + (uint32_t)(ca0 * 8 + 8));
+              const uint2 ea1 = lds_v2(tab32 + (uint32_t)(ca1 * 8));
+              const uint2 eb1 = lds_v2(tab32 + (uint32_t)(ca1 * 8 + 8));
+              const uint32_t aa0 = ((ea0.x & maskpk) == ea0.x) ? gorg + ea0.y : lutv32;
+              const uint32_t ab0 = ((eb0.x & maskpk) == eb0.x) ? gorg + eb0.y : lutv32;
+              const uint32_t aa1 = ((ea1.x & maskpk) == ea1.x) ? gorg + ea1.y : lutv32;
+              const uint32_t ab1 = ((eb1.x & maskpk) == eb1.x) ? gorg + eb1.y : lutv32;
+              const uint32_t ka0 = lds_u8(aa0), kb0 = lds_u8(ab0), ka1 = lds_u8(aa1), kb1 = lds_u8(ab1);
+              const uint2 qa0 = lds_v2(lutv32 + ka0 * 8u), qb0 = lds_v2(lutv32 + kb0 * 8u);
+              const uint2 qa1 = lds_v2(lutv32 + ka1 * 8u), qb1 = lds_v2(lutv32 + kb1 * 8u);
+              uint8_t* dst0 = outv + (ptrdiff_t)ca0 * 8;
+              if (ca0 >= 0 && ca0 + 1 < ohw) st_cs_128(dst0, qa0, qb0);
+              else if (ca0 >= 0) st_cs_64(dst0, qa0);
+              else st_cs_64(dst0 + 8, qb0);
+              if (has1) {
+                uint8_t* dst1 = outv + (ptrdiff_t)ca1 * 8;
+                if (ca1 + 1 < ohw) st_cs_128(dst1, qa1, qb1);
+                else st_cs_64(dst1, qa1);
+              }
             }
-            uint8_t* dst = outv + (ptrdiff_t)ca * 8;
-            if (va && vb) st_cs_128(dst, qa, qb);
-            else if (va) st_cs_64(dst, qa);
-            else st_cs_64(dst + 8, qb);
+          } else {
+            const uint2* lut = lut_all + v * LS;
+            for (int u = (int)lane; u < units; u += 32) {
+              const int ca = 2 * u - shift, cb = ca + 1;
+              const bool va = ca >= 0, vb = cb < ohw;
+              uint2 qa, qb;
+              {
+                const int c = va ? ca : 0;
+                const int ci = c / ow, cj = c - ci * ow;
+                const int rr = r0 + ci, cc = c0 + cj;
+                uint32_t code = 0;
+                if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
+                qa = lut[code];
+              }
+              {
+                const int c = vb ? cb : 0;
+                const int ci = c / ow, cj = c - ci * ow;
+                const int rr = r0 + ci, cc = c0 + cj;
+                uint32_t code = 0;
+                if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
+                qb = lut[code];
+              }
+              uint8_t* dst = outv + (ptrdiff_t)ca * 8;
+              if (va && vb) st_cs_128(dst, qa, qb);
+              else if (va) st_cs_64(dst, qa);
+              else st_cs_64(dst + 8, qb);
+            }
           }
         }
       }
@@ -674,12 +736,50 @@ __global__ void snk_init_records_kernel(const Dims d, uint8_t* __restrict__ recs
 int tile_group(int ns) { return ns <= 1 ? 1 : ns <= 2 ? 2 : ns <= 4 ? 4 : ns <= 8 ? 8 : ns <= 16 ? 16 : 32; }
 
 // Shared memory of one CTA of `warps` warps (must mirror the carve-up in snk_tile_kernel).
+bool encode_uses_table(const Dims& d) {
+  return d.fs == 1 && (d.V == 0 || (d.oh <= 16 && d.ow <= 16)) && (size_t)(d.ohw + 2) * 8 <= 16 * 1024;
+}
+
+// fs == 1 encode blob: uint2 lut[ns][10*ns+6] then (optionally) uint2 tab[-1 .. ohw] per window cell.
+size_t encode_blob_bytes(const Dims& d, size_t* tab_off) {
+  const size_t lut = (size_t)d.ns * (10 * d.ns + 6) * 8;
+  if (tab_off) *tab_off = lut;
+  return (size_t)round_up((int)(lut + (encode_uses_table(d) ? (size_t)(d.ohw + 2) * 8 : 0)), 16);
+}
+
+void encode_blob_fill(const Dims& d, uint8_t* out) {
+  const int LS = 10 * d.ns + 6;
+  uint32_t* w = reinterpret_cast<uint32_t*>(out);
+  for (int v = 0; v < d.ns; ++v)
+    for (int code = 0; code < LS; ++code) {
+      const uint32_t bits = cell_bits((uint32_t)code, (uint32_t)v);
+      w[2 * (v * LS + code)] = spread4(bits & 15u);
+      w[2 * (v * LS + code) + 1] = spread4(bits >> 4);
+    }
+  if (!encode_uses_table(d)) return;
+  size_t off;
+  encode_blob_bytes(d, &off);
+  uint32_t* t = reinterpret_cast<uint32_t*>(out + off);
+  for (int c = -1; c <= d.ohw; ++c) {
+    uint32_t bits = 0xFFFFFFFFu, goff = 0;            // out-of-window sentinels never validate
+    if (c >= 0 && c < d.ohw) {
+      const int ci = c / d.ow, cj = c % d.ow;
+      bits = d.V > 0 ? ((1u << ci) | (1u << (16 + cj))) : 0u;
+      goff = (uint32_t)(ci * d.W + cj);
+    }
+    t[2 * (c + 1)] = bits;
+    t[2 * (c + 1) + 1] = goff;
+  }
+}
+
+// Shared memory of one CTA of `warps` warps (must mirror the carve-up in snk_tile_kernel).
 size_t tile_smem_bytes(const Dims& d, int warps) {
   const int EPW = 32 / tile_group(d.ns);
   const int LS = 10 * d.ns + 6;
   size_t per_warp = (size_t)EPW * d.rec_bytes;
   if (d.fs > 1) per_warp += (size_t)round_up(EPW * d.stage_env_bytes, 16);
-  return per_warp * warps + (size_t)round_up(d.ns * LS * (d.fs == 1 ? 8 : 1), 16) + 16;
+  const size_t tables = d.fs == 1 ? encode_blob_bytes(d, nullptr) : (size_t)round_up(d.ns * LS, 16);
+  return per_warp * warps + tables + 16;
 }
 
 template <int kNS, int kW, int kOH, int kOW, int kFS>

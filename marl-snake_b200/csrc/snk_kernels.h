@@ -37,6 +37,10 @@ struct KParams {
   int32_t E;                   // environments per warp tile (32 / group size), informational
   int32_t vec16;               // 128-bit observation stores are legal for every tile (fs > 1 path)
   int32_t force_generic;       // run the unspecialised kernel instance (tests)
+  const uint8_t* enc_blob;     // fs == 1: host-built encode tables (see encode_blob_fill)
+  int32_t enc_blob_bytes;
+  int32_t enc_tab_off;         // byte offset of the window-cell table inside the blob
+  int32_t use_tab;
 };
 
 struct StateView {
@@ -46,6 +50,9 @@ struct StateView {
 
 int tile_group(int ns);
 size_t tile_smem_bytes(const Dims& d, int warps);
+bool encode_uses_table(const Dims& d);
+size_t encode_blob_bytes(const Dims& d, size_t* tab_off);
+void encode_blob_fill(const Dims& d, uint8_t* out);
 cudaError_t launch_tile_kernel(const KParams& p, int threads, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_get_state(const Dims& d, const uint8_t* recs, const StateView& sv, cudaStream_t s);
 cudaError_t launch_set_state(const Dims& d, uint8_t* recs, const StateView& sv, cudaStream_t s);
