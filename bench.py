@@ -60,6 +60,31 @@ def cpu_leg(seconds, chunk=250):
                              f'incl. resets, {wall:.1f} s wall, Python {sys.version.split()[0]}')
 
 
+def cpu_native_leg(seconds=4.0, n_envs=256):
+    """Extra context, single thread: the device rule source compiled for the host (tests/hostsim, test
+    infrastructure) stepping `n_envs` envs -- what one CPU core does with native code instead of Python."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, 'tests'))
+        import numpy as np
+        from hostsim_util import HostSim
+        hs = HostSim(n_envs, ENV_KW, rng_mode=0, auto_reset=1, seed=1)
+        hs.reset()
+        rng = np.random.RandomState(0)
+        acts = rng.randint(0, 3, size=(64, n_envs, ENV_KW['num_snakes'])).astype(np.uint8)
+        for t in range(8):
+            hs.step(acts[t])
+        t0, steps = time.perf_counter(), 0
+        while time.perf_counter() - t0 < seconds:
+            hs.step(acts[steps % 64])
+            steps += 1
+        wall = time.perf_counter() - t0
+        return {'value': steps * n_envs * ENV_KW['num_snakes'] / wall, 'unit': 'agent-steps/s', 'cores': 1,
+                'kind': 'native C++ host build of the rule source (tests/hostsim), incl. NumPy marshalling',
+                'sample': f'{n_envs} envs x {steps} steps, {wall:.1f} s'}
+    except Exception as exc:      # noqa: BLE001
+        return {'unavailable': repr(exc)}
+
+
 def reference_arm(args):
     """--impl reference: the reference's CPU path (oracle port; the Python reference cannot travel to the
     GPU box) on all host cores.  One 'step' = every worker process advances its env by 250 env-steps."""
@@ -150,6 +175,7 @@ def ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, sample = cpu_leg(args.cpu_seconds)
         cpu = {'value': v, 'unit': 'agent-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+        cpu_native = cpu_native_leg()
 
     N, ns = args.envs_per_gpu, ENV_KW['num_snakes']
     batch = SnakeBatch(N, device=local, seed=0, rng='philox', auto_reset=True, env_id_offset=rank * N, **ENV_KW)
@@ -253,13 +279,14 @@ def ours(args):
                     'h2d_bytes_per_step': N * ns, 'd2h_bytes_per_step': N * (batch.obs_shape[0] * batch.obs_shape[1] *
                                                                              batch.obs_shape[2] * batch.obs_shape[3]) + N * ns * 9,
                     'steps': K2, 'ms_per_step': 1e3 * e2e_s / K2, 'api': 'snk_step_host (C ABI, pinned host buffers)'},
-            'gpu_launches': args.steps,
+            'gpu_launches': args.steps * world,
             'clocks': sampler.summary(),
             'rollout_stats': dict(zip(('episodes', 'return_sum', 'episode_steps_sum', 'fruits_sum', 'kills_sum',
                                        'deaths'), stats_host[:6])),
         }
         if cpu:
             out['cpu_baseline'] = cpu
+            out['cpu_native_1thread'] = cpu_native
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

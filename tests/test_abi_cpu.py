@@ -1,0 +1,99 @@
+"""CPU-side checks of the C-ABI library: it loads without a GPU, exports every symbol include/snk.h
+declares, validates configurations before touching CUDA, and its host-side spawn table equals the
+reference's dfs_sweep_empty enumeration (golden tables)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from golden_util import load_spawn_tables
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import marl_snake_b200 as m
+    header = open(os.path.join(ROOT, 'include', 'snk.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = set(re.findall(r'\b(snk_[a-z_0-9]+)\s*\(', header))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(m.lib, name), f'{name} declared in snk.h but not exported by libsnk.so'
+    from marl_snake_b200._lib import PROTOTYPES
+    assert declared == set(PROTOTYPES), declared ^ set(PROTOTYPES)
+    assert m.lib.snk_abi_version() == 1
+
+
+def test_config_struct_matches_header_layout():
+    from marl_snake_b200._lib import SnkConfig
+    # 14 int32, 2 uint64, 6 double, naturally aligned
+    assert C.sizeof(SnkConfig) == 14 * 4 + 2 * 8 + 6 * 8
+    assert SnkConfig.seed.offset == 56 and SnkConfig.max_episode_steps.offset == 72
+
+
+def test_invalid_configs_are_rejected_without_cuda():
+    from hostsim_util import make_config
+    import marl_snake_b200 as m
+    h = C.c_void_p()
+    for bad in (dict(num_snakes=26), dict(snake_length=1), dict(snake_length=26), dict(height=3),
+                dict(frame_stack=0), dict(num_fruits=33), dict(height=300, width=300)):
+        cfg = make_config(4, dict(bad))
+        assert m.lib.snk_create(C.byref(cfg), C.byref(h)) == -1, bad
+        assert len(m.lib.snk_last_error()) > 0
+    cfg = make_config(4, {})
+    cfg.abi_version = 99
+    assert m.lib.snk_create(C.byref(cfg), C.byref(h)) == -1
+
+
+def test_spawn_table_matches_reference_enumeration():
+    import marl_snake_b200 as m
+    tables, _ = load_spawn_tables()
+    for (H, W, k), ref in tables.items():
+        n = m.lib.snk_spawn_count(H, W, k)
+        assert n == len(ref), (H, W, k)
+        out = np.zeros((n, k), dtype=np.int32)
+        assert m.lib.snk_spawn_cells(H, W, k, out.ctypes.data_as(C.c_void_p), n) == 0
+        want = ref[..., 0].astype(np.int32) * W + ref[..., 1]
+        assert np.array_equal(out, want), (H, W, k)
+    assert m.lib.snk_spawn_count(64, 64, 5) == 362344          # SURVEY probe for the cfg4 shape
+
+
+def test_no_cpu_fallback():
+    import torch
+    import marl_snake_b200 as m
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(RuntimeError):
+        m.SnakeBatch(4)
+    with pytest.raises(KeyError):
+        m.SnakeBatch(4, reward_dict={'fruit': 1.0})
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'marl-snake_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.cpp', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert 'import oracle' not in text and 'from oracle' not in text and 'hostsim' not in text.replace(
+                    'tests/hostsim', ''), f
+
+
+def test_reference_import_paths_resolve():
+    """`from marlenv.marlenv.wrappers import make_snake, RenderGUI` (test_env.py:1) and `import marlenv`."""
+    import sys
+    saved = {k: v for k, v in sys.modules.items() if k == 'marlenv' or k.startswith('marlenv.')}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        from marlenv.marlenv.wrappers import make_snake, RenderGUI
+        import marlenv
+        import marl_snake_b200 as m
+        assert make_snake is m.make_snake and RenderGUI is m.RenderGUI
+        assert marlenv.envs.SnakeEnv is m.SnakeEnv and marlenv.wrappers.make_snake is m.make_snake
+    finally:
+        for k in [k for k in sys.modules if k == 'marlenv' or k.startswith('marlenv.')]:
+            del sys.modules[k]
+        sys.modules.update(saved)
