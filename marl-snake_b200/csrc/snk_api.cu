@@ -132,7 +132,7 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
   CUH(cudaMalloc(&h->stats, STAT_COUNT * sizeof(double)));
   CUH(cudaMalloc(&h->replay_off, ((size_t)d.N + 1) * sizeof(int64_t)));
   CUH(cudaMemcpy(h->spawn, table.data(), table.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
-  if (d.fs == 1) {
+  {
     size_t tab_off = 0;
     const size_t nb = encode_blob_bytes(d, &tab_off);
     std::vector<uint8_t> blob(nb, 0);
@@ -185,7 +185,7 @@ extern "C" size_t snk_algorithmic_bytes_per_env_step(const snk_env* h) {
 
 static int check_vec16(const snk_env* h, const uint8_t* obs) {
   if (!obs) return 0;
-  return (((uintptr_t)obs & 15) == 0 && ((size_t)h->tile_envs * h->d.obs_env_bytes) % 16 == 0) ? 1 : 0;
+  return (((uintptr_t)obs & 15) == 0 && h->d.obs_env_bytes % 16 == 0) ? 1 : 0;    // every env block 16-byte aligned
 }
 
 extern "C" int snk_reset(snk_env* h, const uint8_t* mask_dev, uint8_t* obs_dev, void* stream) {

@@ -348,7 +348,7 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   const int ne = max(0, min(EPW, d.N - e0));
 
   // shared memory: per-warp slices (records [+ staging when fs > 1]), then the CTA-wide LUT
-  const int warp_bytes = EPW * d.rec_bytes + (fs == 1 ? 0 : round_up(EPW * d.stage_env_bytes, 16));
+  const int warp_bytes = EPW * d.rec_bytes + (fs == 1 ? 0 : round_up(d.stage_env_bytes, 16));   // staging: one env
   uint8_t* s_rec = smem + (size_t)warp * warp_bytes;
   uint8_t* s_stage = s_rec + EPW * d.rec_bytes;
   uint8_t* s_lut = smem + (size_t)nwarps * warp_bytes;           // fs==1: uint2[ns*LS]; else uint8[ns*LS]
@@ -360,17 +360,12 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
     const int n16 = ne * (d.rec_bytes >> 4);
     for (int k = (int)lane; k < n16; k += 32) dst[k] = __ldcs(src + k);
   }
-  // ---- encode tables.  fs == 1: host-built blob {cell code -> 8 output bytes per viewer, window-cell
-  //      table}, L2-resident, copied with 128-bit loads.  fs > 1: cell code -> channel-bit byte.
-  if (fs == 1) {
+  // ---- encode tables: host-built blob, L2-resident, copied with 128-bit loads.  fs == 1: {cell code ->
+  //      8 output bytes per viewer, window-cell table}; fs > 1: {cell code -> channel-bit byte, table}.
+  {
     const uint4* src = reinterpret_cast<const uint4*>(p.enc_blob);
     uint4* dst = reinterpret_cast<uint4*>(s_lut);
     for (int k = tid; k < (p.enc_blob_bytes >> 4); k += nt) dst[k] = __ldg(src + k);
-  } else {
-    for (int idx = tid; idx < ns * LS; idx += nt) {
-      const int v = idx / LS, code = idx - v * LS;
-      s_lut[idx] = (uint8_t)cell_bits((uint32_t)code, (uint32_t)v);
-    }
   }
   __syncthreads();                                                // the only block barrier
   if (ne == 0) return;
@@ -559,67 +554,133 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
     return;
   }
 
-  // ================= frame_stack > 1: channel-bit frames staged in output order ======================
-  // ---- older frames of the stack: history rows -> staging (oldest-first)
-  if (want_obs) {
+  // ================= frame_stack > 1 ==================================================================
+  // Per environment: channel-bit bytes of all fs frames are staged in output order ([viewer][cell][frame],
+  // oldest first) in a per-warp staging area, then expanded to NHWC with flat 128-bit stores.  The frame
+  // history lives in HBM as one byte per window cell per stored frame, rows of a ring (hist layout).
+  {
+    const uint32_t lut32 = (uint32_t)__cvta_generic_to_shared(s_lut);          // uint8 lut[ns][LS]
+    const uint32_t tab32 = lut32 + (uint32_t)p.enc_tab_off + 8u;
+    const int oh = sh.oh();
+    const bool vec16 = want_obs && p.vec16 != 0;
 #pragma unroll 1
     for (int q = 0; q < ne; ++q) {
       const int qflag = __shfl_sync(FULL, (int)flag, q * G);
-      if (qflag & (F_RESET | F_INIT | F_SKIP)) continue;
-      const int hpos = (int)((const EnvHdr*)(s_rec + (size_t)q * d.rec_bytes + d.off_hdr))->hpos;
+      if (qflag & F_SKIP) continue;
+      const uint8_t* base = s_rec + (size_t)q * d.rec_bytes;
+      const uint8_t* grid = base;
+      const uint32_t grid32 = (uint32_t)__cvta_generic_to_shared(grid);
+      const bool init = (qflag & (F_RESET | F_INIT)) != 0;
+      const int hpos = (int)((const EnvHdr*)(base + d.off_hdr))->hpos;
 #pragma unroll 1
-      for (int vs = 0; vs < ns * fs; ++vs) {
-        const int v = vs / fs, slot = vs - v * fs;
-        if (slot == hpos) continue;                  // about to be overwritten by the new frame
-        int f = slot - hpos - 1; if (f < 0) f += fs;
-        const uint8_t* src = p.hist + (size_t)(e0 + q) * d.hist_env_bytes + (size_t)vs * d.ohw_p;
-        uint8_t* dst = s_stage + (size_t)q * d.stage_env_bytes + (size_t)v * ohw * fs + f;
-        for (int c4 = (int)lane * 4; c4 < ohw; c4 += 128) {
-          const uint32_t w = *reinterpret_cast<const uint32_t*>(src + c4);
+      for (int v = 0; v < ns; ++v) {
+        const uint8_t alive = base[d.off_snk + 7 * ns + v];
+        const int hc = alive ? (int)((const uint16_t*)(base + d.off_snk))[v] : 0;
+        int r0 = 0, c0 = 0;
+        if (V > 0) { const int hr = hc / W; r0 = hr - V; c0 = hc - hr * W - V; }
+        uint8_t* stg = s_stage + (size_t)v * ohw * fs;
+        uint8_t* hrow = p.hist + (size_t)(e0 + q) * d.hist_env_bytes + (size_t)(v * fs) * d.ohw_p;
+        if (kFS == 4 && p.use_tab) {
+          // four consecutive window cells per lane: the new frame's bits as one word, the three kept
+          // history rows as one word each, 4x4 byte transpose to per-cell words of four frames
+          uint32_t maskpk = 0;
+          if (V > 0) {
+            const int rlo = max(0, -r0), rhi = min(oh, H - r0), clo = max(0, -c0), chi = min(ow, W - c0);
+            maskpk = (((1u << rhi) - 1u) & ~((1u << rlo) - 1u)) | ((((1u << chi) - 1u) & ~((1u << clo) - 1u)) << 16);
+          }
+          const uint32_t lutv32 = lut32 + (uint32_t)(v * LS);               // entry 0 is zero
+          const uint32_t gorg = grid32 + (uint32_t)(r0 * W + c0);
+          for (int c4 = (int)lane * 4; c4 < ohw; c4 += 128) {
+            uint32_t nw = 0;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (c4 + k < ohw) dst[(size_t)(c4 + k) * fs] = (uint8_t)(w >> (8 * k));
-        }
-      }
-    }
-  }
-  // ---- encode the new frame, whole warp per (environment, viewer)            snake_env.py:474-519
+            for (int k = 0; k < 4; ++k) {
+              const int c = min(c4 + k, ohw);                                 // c == ohw: sentinel entry
+              const uint2 en = lds_v2(tab32 + (uint32_t)(c * 8));
+              const uint32_t a = ((en.x & maskpk) == en.x) ? gorg + en.y : lutv32;
+              nw |= lds_u8(lutv32 + lds_u8(a)) << (8 * k);
+            }
+            uint32_t f0, f1, f2;
+            if (!init) {
+              f0 = __ldcs(reinterpret_cast<const uint32_t*>(hrow + (size_t)((hpos + 1) & 3) * d.ohw_p + c4));
+              f1 = __ldcs(reinterpret_cast<const uint32_t*>(hrow + (size_t)((hpos + 2) & 3) * d.ohw_p + c4));
+              f2 = __ldcs(reinterpret_cast<const uint32_t*>(hrow + (size_t)((hpos + 3) & 3) * d.ohw_p + c4));
+              *reinterpret_cast<uint32_t*>(hrow + (size_t)hpos * d.ohw_p + c4) = nw;
+            } else {                                   // reset: every slot holds the first frame (:452-457)
+              f0 = f1 = f2 = nw;
+#pragma unroll
+              for (int f = 0; f < 4; ++f) *reinterpret_cast<uint32_t*>(hrow + (size_t)f * d.ohw_p + c4) = nw;
+            }
+            if (want_obs) {
+              const uint32_t t0 = __byte_perm(f0, f1, 0x5140), t1 = __byte_perm(f2, nw, 0x5140);
+              const uint32_t t2 = __byte_perm(f0, f1, 0x7362), t3 = __byte_perm(f2, nw, 0x7362);
+              uint32_t* dst = reinterpret_cast<uint32_t*>(stg) + c4;
+              dst[0] = __byte_perm(t0, t1, 0x5410);
+              if (c4 + 1 < ohw) dst[1] = __byte_perm(t0, t1, 0x7632);
+              if (c4 + 2 < ohw) dst[2] = __byte_perm(t2, t3, 0x5410);
+              if (c4 + 3 < ohw) dst[3] = __byte_perm(t2, t3, 0x7632);
+            }
+          }
+        } else {
+          if (want_obs && !init) {
 #pragma unroll 1
-  for (int q = 0; q < ne; ++q) {
-    const int qflag = __shfl_sync(FULL, (int)flag, q * G);
-    if (qflag & F_SKIP) continue;
-    const uint8_t* base = s_rec + (size_t)q * d.rec_bytes;
-    const uint8_t* grid = base;
-    const bool init = (qflag & (F_RESET | F_INIT)) != 0;
-    const int hpos = (int)((const EnvHdr*)(base + d.off_hdr))->hpos;
-#pragma unroll 1
-    for (int v = 0; v < ns; ++v) {
-      const uint8_t alive = base[d.off_snk + 7 * ns + v];
-      const int hc = alive ? (int)((const uint16_t*)(base + d.off_snk))[v] : 0;
-      int r0 = 0, c0 = 0;
-      if (V > 0) { const int hr = hc / W; r0 = hr - V; c0 = hc - hr * W - V; }
-      const uint8_t* lut = s_lut + v * LS;
-      uint8_t* stg = s_stage + (size_t)q * d.stage_env_bytes + (size_t)v * ohw * fs;
-      uint8_t* hrow = p.hist + (size_t)(e0 + q) * d.hist_env_bytes + (size_t)(v * fs) * d.ohw_p;
-      for (int cell = (int)lane; cell < ohw; cell += 32) {
-        const int ci = cell / ow, cj = cell - ci * ow;
-        const int rr = r0 + ci, cc = c0 + cj;
-        uint32_t code = 0;
-        if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
-        const uint8_t bits = lut[code];
-        if (!init) {
-          stg[(size_t)cell * fs + (fs - 1)] = bits;
-          hrow[(size_t)hpos * d.ohw_p + cell] = bits;
-        } else {                                   // reset: every slot holds the first frame (:452-457)
-          for (int f = 0; f < fs; ++f) {
-            stg[(size_t)cell * fs + f] = bits;
-            hrow[(size_t)f * d.ohw_p + cell] = bits;
+            for (int slot = 0; slot < fs; ++slot) {
+              if (slot == hpos) continue;                // about to be overwritten by the new frame
+              int f = slot - hpos - 1; if (f < 0) f += fs;
+              const uint8_t* src = hrow + (size_t)slot * d.ohw_p;
+              for (int c4 = (int)lane * 4; c4 < ohw; c4 += 128) {
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(src + c4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (c4 + k < ohw) stg[(size_t)(c4 + k) * fs + f] = (uint8_t)(w >> (8 * k));
+              }
+            }
+          }
+          const uint8_t* lut = s_lut + v * LS;
+          for (int cell = (int)lane; cell < ohw; cell += 32) {
+            const int ci = cell / ow, cj = cell - ci * ow;
+            const int rr = r0 + ci, cc = c0 + cj;
+            uint32_t code = 0;
+            if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
+            const uint8_t bits = lut[code];
+            if (!init) {
+              if (want_obs) stg[(size_t)cell * fs + (fs - 1)] = bits;
+              hrow[(size_t)hpos * d.ohw_p + cell] = bits;
+            } else {
+              for (int f = 0; f < fs; ++f) {
+                if (want_obs) stg[(size_t)cell * fs + f] = bits;
+                hrow[(size_t)f * d.ohw_p + cell] = bits;
+              }
+            }
           }
         }
       }
+      __syncwarp();
+      // ---- channel bits -> NHWC uint8, coalesced
+      if (want_obs) {
+        uint8_t* out = p.obs + (size_t)(e0 + q) * d.obs_env_bytes;
+        const int total = d.stage_env_bytes;                 // staging bytes == 8-byte output units
+        if (vec16) {
+          const uint16_t* s2 = reinterpret_cast<const uint16_t*>(s_stage);
+          uint4* o4 = reinterpret_cast<uint4*>(out);
+#pragma unroll 2
+          for (int u = (int)lane; u < (total >> 1); u += 32) {
+            const uint32_t two = s2[u];
+            uint4 qv;
+            qv.x = spread4(two & 15u); qv.y = spread4((two >> 4) & 15u);
+            qv.z = spread4((two >> 8) & 15u); qv.w = spread4(two >> 12);
+            __stcs(o4 + u, qv);
+          }
+        } else {
+          uint2* o2 = reinterpret_cast<uint2*>(out);
+          for (int u = (int)lane; u < total; u += 32) {
+            const uint32_t b = s_stage[u];
+            __stcs(o2 + u, make_uint2(spread4(b & 15u), spread4(b >> 4)));
+          }
+        }
+      }
+      __syncwarp();
     }
   }
-  __syncwarp();
   if (active && i == 0 && !(flag & F_SKIP))
     r.hdr->hpos = (flag & (F_RESET | F_INIT)) ? 0u : (r.hdr->hpos + 1u) % (uint32_t)fs;
   __syncwarp();
@@ -630,40 +691,6 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
     const uint4* src = reinterpret_cast<const uint4*>(s_rec);
     const int n16 = ne * (d.rec_bytes >> 4);
     for (int k = (int)lane; k < n16; k += 32) dst[k] = src[k];
-  }
-
-  // ---- channel bits -> NHWC uint8, coalesced
-  if (want_obs) {
-    uint8_t* out = p.obs + (size_t)e0 * d.obs_env_bytes;
-    if (p.mode == MODE_STEP && p.vec16) {
-      const int total = ne * d.stage_env_bytes;             // staging bytes == 8-byte output units
-      const int n16 = total >> 1;
-      const uint16_t* s2 = reinterpret_cast<const uint16_t*>(s_stage);
-      uint4* o4 = reinterpret_cast<uint4*>(out);
-      for (int u = (int)lane; u < n16; u += 32) {
-        const uint32_t two = s2[u];
-        uint4 qv;
-        qv.x = spread4(two & 15u); qv.y = spread4((two >> 4) & 15u);
-        qv.z = spread4((two >> 8) & 15u); qv.w = spread4(two >> 12);
-        __stcs(o4 + u, qv);
-      }
-      if ((total & 1) && lane == 0) {
-        const uint32_t b = s_stage[total - 1];
-        __stcs(reinterpret_cast<uint2*>(out) + (total - 1), make_uint2(spread4(b & 15u), spread4(b >> 4)));
-      }
-    } else {
-#pragma unroll 1
-      for (int q = 0; q < ne; ++q) {
-        const int qflag = __shfl_sync(FULL, (int)flag, q * G);
-        if (qflag & F_SKIP) continue;
-        const uint8_t* stg = s_stage + (size_t)q * d.stage_env_bytes;
-        uint2* o2 = reinterpret_cast<uint2*>(out + (size_t)q * d.obs_env_bytes);
-        for (int u = (int)lane; u < d.stage_env_bytes; u += 32) {
-          const uint32_t b = stg[u];
-          __stcs(o2 + u, make_uint2(spread4(b & 15u), spread4(b >> 4)));
-        }
-      }
-    }
   }
 }
 
@@ -735,14 +762,14 @@ __global__ void snk_init_records_kernel(const Dims d, uint8_t* __restrict__ recs
 // ---- launch wrappers -----------------------------------------------------------------------------
 int tile_group(int ns) { return ns <= 1 ? 1 : ns <= 2 ? 2 : ns <= 4 ? 4 : ns <= 8 ? 8 : ns <= 16 ? 16 : 32; }
 
-// Shared memory of one CTA of `warps` warps (must mirror the carve-up in snk_tile_kernel).
 bool encode_uses_table(const Dims& d) {
-  return d.fs == 1 && (d.V == 0 || (d.oh <= 16 && d.ow <= 16)) && (size_t)(d.ohw + 2) * 8 <= 16 * 1024;
+  return (d.V == 0 || (d.oh <= 16 && d.ow <= 16)) && (size_t)(d.ohw + 2) * 8 <= 16 * 1024;
 }
 
-// fs == 1 encode blob: uint2 lut[ns][10*ns+6] then (optionally) uint2 tab[-1 .. ohw] per window cell.
+// Encode blob: per-viewer LUT over cell codes (uint2 = 8 output bytes when fs == 1, one channel-bit byte
+// when fs > 1), then (optionally) uint2 tab[-1 .. ohw] per window cell.
 size_t encode_blob_bytes(const Dims& d, size_t* tab_off) {
-  const size_t lut = (size_t)d.ns * (10 * d.ns + 6) * 8;
+  const size_t lut = (size_t)round_up(d.ns * (10 * d.ns + 6) * (d.fs == 1 ? 8 : 1), 16);
   if (tab_off) *tab_off = lut;
   return (size_t)round_up((int)(lut + (encode_uses_table(d) ? (size_t)(d.ohw + 2) * 8 : 0)), 16);
 }
@@ -753,8 +780,12 @@ void encode_blob_fill(const Dims& d, uint8_t* out) {
   for (int v = 0; v < d.ns; ++v)
     for (int code = 0; code < LS; ++code) {
       const uint32_t bits = cell_bits((uint32_t)code, (uint32_t)v);
-      w[2 * (v * LS + code)] = spread4(bits & 15u);
-      w[2 * (v * LS + code) + 1] = spread4(bits >> 4);
+      if (d.fs == 1) {
+        w[2 * (v * LS + code)] = spread4(bits & 15u);
+        w[2 * (v * LS + code) + 1] = spread4(bits >> 4);
+      } else {
+        out[v * LS + code] = (uint8_t)bits;
+      }
     }
   if (!encode_uses_table(d)) return;
   size_t off;
@@ -777,9 +808,9 @@ size_t tile_smem_bytes(const Dims& d, int warps) {
   const int EPW = 32 / tile_group(d.ns);
   const int LS = 10 * d.ns + 6;
   size_t per_warp = (size_t)EPW * d.rec_bytes;
-  if (d.fs > 1) per_warp += (size_t)round_up(EPW * d.stage_env_bytes, 16);
-  const size_t tables = d.fs == 1 ? encode_blob_bytes(d, nullptr) : (size_t)round_up(d.ns * LS, 16);
-  return per_warp * warps + tables + 16;
+  if (d.fs > 1) per_warp += (size_t)round_up(d.stage_env_bytes, 16);
+  (void)LS;
+  return per_warp * warps + encode_blob_bytes(d, nullptr) + 16;
 }
 
 template <int kNS, int kW, int kOH, int kOW, int kFS>
