@@ -267,7 +267,7 @@ def ours(args):
                        'l2': 'no flush: per-step working set (records %.0f MB read + written, obs %.0f MB written) '
                              'exceeds the 126 MB L2' % (N * rec_bytes / 1e6, N * obs_bytes / 1e6),
                        'parallelism': f'env-shard x{world}', 'rng': 'philox seed 0',
-                       'tile_envs': os.environ.get('SNK_TILE_ENVS', 'auto'), 'threads': os.environ.get('SNK_THREADS', '64'),
+                       'tile_envs': os.environ.get('SNK_TILE_ENVS', 'auto'), 'threads': os.environ.get('SNK_THREADS', 'auto'),
                        'mean_episode_steps_rank0': st_after['episode_steps_sum'] / max(st_after['episodes'], 1.0),
                        'device_errors': errs},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libsnk.so')
+LIB_PATH = os.environ.get('SNK_LIB_PATH') or os.path.join(_HERE, 'libsnk.so')   # override: A/B builds
 
 SNK_ABI_VERSION = 1
 SNK_RNG_PHILOX, SNK_RNG_REPLAY = 0, 1

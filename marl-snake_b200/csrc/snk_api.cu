@@ -49,7 +49,7 @@ struct snk_env {
   uint8_t* h_actions = nullptr; uint8_t* h_obs = nullptr; double* h_rew = nullptr; uint8_t* h_done = nullptr;
   cudaStream_t own_stream = nullptr;
   double env_steps = 0.0;
-  int force_generic = 0;
+  int force_generic = 0, coop = 0, lut_dual = 0;
   bool was_reset = false;
 };
 
@@ -71,6 +71,7 @@ static KParams base_params(const snk_env* h) {
   p.E = h->tile_envs;
   p.force_generic = h->force_generic;
   p.enc_blob = h->enc_blob; p.enc_blob_bytes = h->enc_blob_bytes; p.enc_tab_off = h->enc_tab_off; p.use_tab = h->use_tab;
+  p.lut_dual = h->lut_dual; p.coop = h->coop;
   return p;
 }
 
@@ -108,14 +109,20 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
   spawn_enumerate(d.H, d.W, d.K, table.data(), nullptr, n_cand);
   d.n_cand = (uint32_t)n_cand;
 
-  // tile shape: a warp owns 32/G environments (G = num_snakes rounded up to a power of two); the CTA
-  // is `threads`/32 independent warps sharing only the lookup table.
-  int threads = env_int("SNK_THREADS", 64);
-  if (threads < 32 || threads > SNK_MAX_THREADS || (threads & 31)) { delete h; return fail(SNK_E_INVALID, "SNK_THREADS must be a multiple of 32 in 32..%d", SNK_MAX_THREADS); }
-  while (threads > 32 && tile_smem_bytes(d, threads / 32) > 200 * 1024) threads -= 32;
-  h->tile_envs = 32 / tile_group(d.ns); h->threads = threads;
+  // tile shape: a tile is 32/G environments (G = num_snakes rounded up to a power of two).  Large
+  // batches: every warp owns a tile, the CTA's warps share only the encode tables.  Small batches or
+  // large records: the CTA owns one tile and its warps share the tile's viewers (coop).
+  const int EPW = 32 / tile_group(d.ns);
+  const int64_t tiles = ((int64_t)d.N + EPW - 1) / EPW;
+  int coop = env_int("SNK_COOP", -1);
+  if (coop < 0) coop = (tiles < 148 * 24 || (size_t)EPW * d.rec_bytes > 8 * 1024) ? 1 : 0;
+  int threads = env_int("SNK_THREADS", coop ? 128 : 32);
+  const int max_threads = coop ? SNK_MAX_THREADS_COOP : SNK_MAX_THREADS;
+  if (threads < 32 || threads > max_threads || (threads & 31)) { delete h; return fail(SNK_E_INVALID, "SNK_THREADS must be a multiple of 32 in 32..%d", max_threads); }
+  while (threads > 32 && tile_smem_bytes(d, threads / 32, coop != 0) > 200 * 1024) threads -= 32;
+  h->tile_envs = EPW; h->threads = threads; h->coop = coop;
   h->force_generic = env_int("SNK_FORCE_GENERIC", 0);
-  h->smem_bytes = tile_smem_bytes(d, threads / 32);
+  h->smem_bytes = tile_smem_bytes(d, threads / 32, coop != 0);
   if (h->smem_bytes > 227 * 1024) {
     const size_t need = h->smem_bytes;
     delete h;
@@ -140,7 +147,8 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
     CUH(cudaMalloc(&h->enc_blob, nb));
     CUH(cudaMemcpy(h->enc_blob, blob.data(), nb, cudaMemcpyHostToDevice));
     h->enc_blob_bytes = (int)nb; h->enc_tab_off = (int)tab_off;
-    h->use_tab = encode_uses_table(d) && !env_int("SNK_NO_TABLE", 0) ? 1 : 0;
+    h->lut_dual = encode_lut_dual(d) ? 1 : 0;
+    h->use_tab = encode_uses_table(d) && (h->lut_dual || !env_int("SNK_NO_TABLE", 0)) ? 1 : 0;
   }
   CUH(cudaMemset(h->err, 0, sizeof(uint32_t)));
   CUH(cudaMemset(h->stats, 0, STAT_COUNT * sizeof(double)));

@@ -170,6 +170,8 @@ struct Shape {
   __device__ __forceinline__ int ohw() const { return oh() * ow(); }
   __device__ __forceinline__ int fs() const { return kFS ? kFS : d.fs; }
   __device__ __forceinline__ int lut_stride() const { return 10 * ns() + 6; }   // cell codes 0 .. 10*(ns-1)+5
+  // the {as-other, as-own} LUT pair is only ever used when one LUT per viewer would exceed 8 KB
+  static constexpr bool kMayDual = kNS == 0 || kNS * (10 * kNS + 6) * 8 > 8 * 1024;
   __device__ __forceinline__ int group() const {                                // lanes per environment
     const int n = ns();
     return n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : 32;
@@ -331,46 +333,16 @@ __device__ __forceinline__ GroupOut step_group(const KParams& p, const SH& sh, R
   return out;
 }
 
-template <int kNS, int kW, int kOH, int kOW, int kFS>
-__global__ void __launch_bounds__(SNK_MAX_THREADS)
-snk_tile_kernel(const __grid_constant__ KParams p) {
-  extern __shared__ __align__(16) uint8_t smem[];
+// ---- one warp: rules + terminal info + rollout statistics + rare events for a tile ----------------
+// Leaves per-environment flags in s_flag[] (F_RESET / F_INIT / F_SKIP).
+template <class SH>
+__device__ __forceinline__ void tile_rules(const KParams& p, const SH& sh, uint8_t* s_rec, int e0, int ne,
+                                           uint8_t* s_flag) {
   const Dims& d = p.d;
-  const Shape<kNS, kW, kOH, kOW, kFS> sh(d);
   const uint32_t FULL = 0xffffffffu;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int warp = tid >> 5, nwarps = nt >> 5;
   const uint32_t lane = lane_id();
-  const int ns = sh.ns(), G = sh.group(), EPW = 32 / G;          // environments per warp
-  const int fs = sh.fs(), ohw = sh.ohw(), ow = sh.ow(), W = sh.W();
-  const int LS = sh.lut_stride();
-  const int e0 = (blockIdx.x * nwarps + warp) * EPW;             // this warp's first environment
-  const int ne = max(0, min(EPW, d.N - e0));
-
-  // shared memory: per-warp slices (records [+ staging when fs > 1]), then the CTA-wide LUT
-  const int warp_bytes = EPW * d.rec_bytes + (fs == 1 ? 0 : round_up(d.stage_env_bytes, 16));   // staging: one env
-  uint8_t* s_rec = smem + (size_t)warp * warp_bytes;
-  uint8_t* s_stage = s_rec + EPW * d.rec_bytes;
-  uint8_t* s_lut = smem + (size_t)nwarps * warp_bytes;           // fs==1: uint2[ns*LS]; else uint8[ns*LS]
-
-  // ---- stage the tile's records: HBM -> shared, 128-bit coalesced
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(p.recs + (size_t)e0 * d.rec_bytes);
-    uint4* dst = reinterpret_cast<uint4*>(s_rec);
-    const int n16 = ne * (d.rec_bytes >> 4);
-    for (int k = (int)lane; k < n16; k += 32) dst[k] = __ldcs(src + k);
-  }
-  // ---- encode tables: host-built blob, L2-resident, copied with 128-bit loads.  fs == 1: {cell code ->
-  //      8 output bytes per viewer, window-cell table}; fs > 1: {cell code -> channel-bit byte, table}.
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(p.enc_blob);
-    uint4* dst = reinterpret_cast<uint4*>(s_lut);
-    for (int k = tid; k < (p.enc_blob_bytes >> 4); k += nt) dst[k] = __ldg(src + k);
-  }
-  __syncthreads();                                                // the only block barrier
-  if (ne == 0) return;
-
-  // ---- lane = (environment g of the tile, snake i)
+  const int ns = sh.ns(), G = sh.group();
+  // lane = (environment g of the tile, snake i)
   const int g = (int)lane / G, i = (int)lane - g * G;
   const int gbase = g * G;
   const uint32_t gmask = (G == 32 ? FULL : ((1u << G) - 1u)) << gbase;
@@ -436,15 +408,299 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   for (int q = 0; q < ne; ++q) {
     const int qf = __shfl_sync(FULL, fruit, q * G);
     const int qflag = __shfl_sync(FULL, (int)flag, q * G);
+    if (lane == 0) s_flag[q] = (uint8_t)qflag;
     if (!qf && !(qflag & F_RESET)) continue;
     Rec rq = rec_view(s_rec + (size_t)q * d.rec_bytes, d);
     if (qf) place_fruits_warp(p, rq, (uint32_t)(e0 + q), qf, DRAW_STEP_FRUIT);
     if (qflag & F_RESET) reset_env_warp(p, rq, (uint32_t)(e0 + q));
   }
   __syncwarp();
+}
+
+// Crop origin of viewer v: own head, or cell (0,0) when it has no head in the grid       :500-502
+__device__ __forceinline__ void viewer_origin(const Dims& d, const uint8_t* base, int ns, int W, int V, int v,
+                                              int& r0, int& c0) {
+  const uint8_t alive = base[d.off_snk + 7 * ns + v];
+  const int hc = alive ? (int)((const uint16_t*)(base + d.off_snk))[v] : 0;
+  r0 = 0; c0 = 0;
+  if (V > 0) { const int hr = hc / W; r0 = hr - V; c0 = hc - hr * W - V; }
+}
+
+// Valid window rows / columns of a viewer as bit masks (rows in bits 0..15, columns in 16..31).
+__device__ __forceinline__ uint32_t window_mask(int V, int oh, int ow, int H, int W, int r0, int c0) {
+  if (V <= 0) return 0u;
+  const int rlo = max(0, -r0), rhi = min(oh, H - r0), clo = max(0, -c0), chi = min(ow, W - c0);
+  return (((1u << rhi) - 1u) & ~((1u << rlo) - 1u)) | ((((1u << chi) - 1u) & ~((1u << clo) - 1u)) << 16);
+}
+
+// frame_stack 1: one warp encodes one viewer straight to global memory.  snake_env.py:474-519.
+// Each lane produces 16 output bytes (two window cells x 8 channels) per unit: window-table entry ->
+// AND/compare against the viewer's valid row/column masks (the zero padding of :506-515) -> grid byte
+// -> LUT row -> one 128-bit streaming store.  A viewer block of ohw*8 bytes is only 8-byte aligned
+// when ohw is odd, so units are laid out from the address parity and the end units may be half units.
+template <class SH>
+__device__ __forceinline__ void encode_viewer_fs1(const KParams& p, const SH& sh, const uint8_t* base,
+                                                  uint32_t grid32, int v, uint8_t* outv, uint32_t lut32) {
+  const Dims& d = p.d;
+  const uint32_t lane = lane_id();
+  const int ns = sh.ns(), W = sh.W(), ohw = sh.ohw(), ow = sh.ow(), oh = sh.oh(), LS = sh.lut_stride();
+  const int H = d.H, V = d.V;
+  const uint8_t* grid = base;
+  int r0, c0;
+  viewer_origin(d, base, ns, W, V, v, r0, c0);
+  const int shift = (int)((reinterpret_cast<uintptr_t>(outv) >> 3) & 1);
+  const int units = (ohw + shift + 1) >> 1;
+  if (p.use_tab) {
+    const uint32_t tab32 = lut32 + (uint32_t)p.enc_tab_off + 8u;       // entry of window cell 0
+    const uint32_t maskpk = window_mask(V, oh, ow, H, W, r0, c0);
+    // per-viewer LUT (small ns) or the {as-other, as-own} pair selected per cell by owner == v
+    const bool dual = SH::kMayDual && p.lut_dual != 0;
+    const uint32_t lutv32 = dual ? lut32 : lut32 + (uint32_t)(v * LS) * 8u;   // entry 0 is all zero
+    const uint32_t lutown = lut32 + (uint32_t)LS * 8u;
+    const uint32_t gorg = grid32 + (uint32_t)(r0 * W + c0);
+    // two units per lane per trip: all table loads, then all grid bytes, then all LUT rows, so the
+    // three dependent shared-memory round trips of both units overlap
+    for (int u0 = (int)lane; u0 < units; u0 += 64) {
+      const int u1 = u0 + 32;
+      const bool has1 = u1 < units;
+      const int ca0 = 2 * u0 - shift, ca1 = 2 * (has1 ? u1 : u0) - shift;
+      const uint2 ea0 = lds_v2(tab32 + (uint32_t)(ca0 * 8));
+      const uint2 eb0 = lds_v2(tab32 + (uint32_t)(ca0 * 8 + 8));
+      const uint2 ea1 = lds_v2(tab32 + (uint32_t)(ca1 * 8));
+      const uint2 eb1 = lds_v2(tab32 + (uint32_t)(ca1 * 8 + 8));
+      const uint32_t aa0 = ((ea0.x & maskpk) == ea0.x) ? gorg + ea0.y : lutv32;
+      const uint32_t ab0 = ((eb0.x & maskpk) == eb0.x) ? gorg + eb0.y : lutv32;
+      const uint32_t aa1 = ((ea1.x & maskpk) == ea1.x) ? gorg + ea1.y : lutv32;
+      const uint32_t ab1 = ((eb1.x & maskpk) == eb1.x) ? gorg + eb1.y : lutv32;
+      const uint32_t ka0 = lds_u8(aa0), kb0 = lds_u8(ab0), ka1 = lds_u8(aa1), kb1 = lds_u8(ab1);
+      uint32_t la0 = lutv32, lb0 = lutv32, la1 = lutv32, lb1 = lutv32;
+      if (dual) {
+        la0 = (((ka0 * 205u) >> 11) == (uint32_t)v) ? lutown : lut32;
+        lb0 = (((kb0 * 205u) >> 11) == (uint32_t)v) ? lutown : lut32;
+        la1 = (((ka1 * 205u) >> 11) == (uint32_t)v) ? lutown : lut32;
+        lb1 = (((kb1 * 205u) >> 11) == (uint32_t)v) ? lutown : lut32;
+      }
+      const uint2 qa0 = lds_v2(la0 + ka0 * 8u), qb0 = lds_v2(lb0 + kb0 * 8u);
+      const uint2 qa1 = lds_v2(la1 + ka1 * 8u), qb1 = lds_v2(lb1 + kb1 * 8u);
+      uint8_t* dst0 = outv + (ptrdiff_t)ca0 * 8;
+      if (ca0 >= 0 && ca0 + 1 < ohw) st_cs_128(dst0, qa0, qb0);
+      else if (ca0 >= 0) st_cs_64(dst0, qa0);
+      else st_cs_64(dst0 + 8, qb0);
+      if (has1) {
+        uint8_t* dst1 = outv + (ptrdiff_t)ca1 * 8;
+        if (ca1 + 1 < ohw) st_cs_128(dst1, qa1, qb1);
+        else st_cs_64(dst1, qa1);
+      }
+    }
+  } else {                       // windows wider than 16 cells: plain index arithmetic, per-viewer LUT
+    const uint2* lut = reinterpret_cast<const uint2*>(__cvta_shared_to_generic(lut32)) + v * LS;
+    for (int u = (int)lane; u < units; u += 32) {
+      const int ca = 2 * u - shift, cb = ca + 1;
+      const bool va = ca >= 0, vb = cb < ohw;
+      uint2 qa, qb;
+      {
+        const int c = va ? ca : 0;
+        const int ci = c / ow, cj = c - ci * ow;
+        const int rr = r0 + ci, cc = c0 + cj;
+        uint32_t code = 0;
+        if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
+        qa = lut[code];
+      }
+      {
+        const int c = vb ? cb : 0;
+        const int ci = c / ow, cj = c - ci * ow;
+        const int rr = r0 + ci, cc = c0 + cj;
+        uint32_t code = 0;
+        if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
+        qb = lut[code];
+      }
+      uint8_t* dst = outv + (ptrdiff_t)ca * 8;
+      if (va && vb) st_cs_128(dst, qa, qb);
+      else if (va) st_cs_64(dst, qa);
+      else st_cs_64(dst + 8, qb);
+    }
+  }
+}
+
+// frame_stack > 1: one warp encodes one environment.  Channel-bit bytes of all fs frames are staged in
+// output order ([viewer][cell][frame], oldest first) in the warp's staging area, then expanded to NHWC
+// with flat 128-bit stores.  The frame history lives in HBM as one byte per window cell per stored frame,
+// rows of a ring (hist layout); each step reads fs-1 rows and writes one.
+template <class SH, int kFS>
+__device__ __forceinline__ void encode_env_stacked(const KParams& p, const SH& sh, const uint8_t* base, int e,
+                                                   int qflag, uint8_t* s_stage, uint32_t lut32, const uint8_t* s_lut) {
+  const Dims& d = p.d;
+  const uint32_t lane = lane_id();
+  const int ns = sh.ns(), W = sh.W(), ohw = sh.ohw(), ow = sh.ow(), oh = sh.oh(), LS = sh.lut_stride(), fs = sh.fs();
+  const int H = d.H, V = d.V;
+  const bool want_obs = p.obs != nullptr;
+  const bool vec16 = want_obs && p.vec16 != 0;
+  const uint32_t tab32 = lut32 + (uint32_t)p.enc_tab_off + 8u;
+  const uint8_t* grid = base;
+  const uint32_t grid32 = (uint32_t)__cvta_generic_to_shared(grid);
+  const bool init = (qflag & (F_RESET | F_INIT)) != 0;
+  const int hpos = (int)((const EnvHdr*)(base + d.off_hdr))->hpos;
+#pragma unroll 1
+  for (int v = 0; v < ns; ++v) {
+    int r0, c0;
+    viewer_origin(d, base, ns, W, V, v, r0, c0);
+    uint8_t* stg = s_stage + (size_t)v * ohw * fs;
+    uint8_t* hrow = p.hist + (size_t)e * d.hist_env_bytes + (size_t)(v * fs) * d.ohw_p;
+    if (kFS == 4 && p.use_tab) {
+      // four consecutive window cells per lane: the new frame's bits as one word, the three kept history
+      // rows as one word each, 4x4 byte transpose to per-cell words of four frames
+      const uint32_t maskpk = window_mask(V, oh, ow, H, W, r0, c0);
+      const uint32_t lutv32 = lut32 + (uint32_t)(v * LS);               // entry 0 is zero
+      const uint32_t gorg = grid32 + (uint32_t)(r0 * W + c0);
+      for (int c4 = (int)lane * 4; c4 < ohw; c4 += 128) {
+        uint32_t nw = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = min(c4 + k, ohw);                                 // c == ohw: sentinel entry
+          const uint2 en = lds_v2(tab32 + (uint32_t)(c * 8));
+          const uint32_t a = ((en.x & maskpk) == en.x) ? gorg + en.y : lutv32;
+          nw |= lds_u8(lutv32 + lds_u8(a)) << (8 * k);
+        }
+        uint32_t f0, f1, f2;
+        if (!init) {
+          f0 = __ldcs(reinterpret_cast<const uint32_t*>(hrow + (size_t)((hpos + 1) & 3) * d.ohw_p + c4));
+          f1 = __ldcs(reinterpret_cast<const uint32_t*>(hrow + (size_t)((hpos + 2) & 3) * d.ohw_p + c4));
+          f2 = __ldcs(reinterpret_cast<const uint32_t*>(hrow + (size_t)((hpos + 3) & 3) * d.ohw_p + c4));
+          *reinterpret_cast<uint32_t*>(hrow + (size_t)hpos * d.ohw_p + c4) = nw;
+        } else {                                   // reset: every slot holds the first frame (:452-457)
+          f0 = f1 = f2 = nw;
+#pragma unroll
+          for (int f = 0; f < 4; ++f) *reinterpret_cast<uint32_t*>(hrow + (size_t)f * d.ohw_p + c4) = nw;
+        }
+        if (want_obs) {
+          const uint32_t t0 = __byte_perm(f0, f1, 0x5140), t1 = __byte_perm(f2, nw, 0x5140);
+          const uint32_t t2 = __byte_perm(f0, f1, 0x7362), t3 = __byte_perm(f2, nw, 0x7362);
+          uint32_t* dst = reinterpret_cast<uint32_t*>(stg) + c4;
+          dst[0] = __byte_perm(t0, t1, 0x5410);
+          if (c4 + 1 < ohw) dst[1] = __byte_perm(t0, t1, 0x7632);
+          if (c4 + 2 < ohw) dst[2] = __byte_perm(t2, t3, 0x5410);
+          if (c4 + 3 < ohw) dst[3] = __byte_perm(t2, t3, 0x7632);
+        }
+      }
+    } else {
+      if (want_obs && !init) {
+#pragma unroll 1
+        for (int slot = 0; slot < fs; ++slot) {
+          if (slot == hpos) continue;                // about to be overwritten by the new frame
+          int f = slot - hpos - 1; if (f < 0) f += fs;
+          const uint8_t* src = hrow + (size_t)slot * d.ohw_p;
+          for (int c4 = (int)lane * 4; c4 < ohw; c4 += 128) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(src + c4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (c4 + k < ohw) stg[(size_t)(c4 + k) * fs + f] = (uint8_t)(w >> (8 * k));
+          }
+        }
+      }
+      const uint8_t* lut = s_lut + v * LS;
+      for (int cell = (int)lane; cell < ohw; cell += 32) {
+        const int ci = cell / ow, cj = cell - ci * ow;
+        const int rr = r0 + ci, cc = c0 + cj;
+        uint32_t code = 0;
+        if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
+        const uint8_t bits = lut[code];
+        if (!init) {
+          if (want_obs) stg[(size_t)cell * fs + (fs - 1)] = bits;
+          hrow[(size_t)hpos * d.ohw_p + cell] = bits;
+        } else {
+          for (int f = 0; f < fs; ++f) {
+            if (want_obs) stg[(size_t)cell * fs + f] = bits;
+            hrow[(size_t)f * d.ohw_p + cell] = bits;
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  // ---- channel bits -> NHWC uint8, coalesced
+  if (want_obs) {
+    uint8_t* out = p.obs + (size_t)e * d.obs_env_bytes;
+    const int total = d.stage_env_bytes;                 // staging bytes == 8-byte output units
+    if (vec16) {
+      const uint16_t* s2 = reinterpret_cast<const uint16_t*>(s_stage);
+      uint4* o4 = reinterpret_cast<uint4*>(out);
+#pragma unroll 2
+      for (int u = (int)lane; u < (total >> 1); u += 32) {
+        const uint32_t two = s2[u];
+        uint4 qv;
+        qv.x = spread4(two & 15u); qv.y = spread4((two >> 4) & 15u);
+        qv.z = spread4((two >> 8) & 15u); qv.w = spread4(two >> 12);
+        __stcs(o4 + u, qv);
+      }
+    } else {
+      uint2* o2 = reinterpret_cast<uint2*>(out);
+      for (int u = (int)lane; u < total; u += 32) {
+        const uint32_t b = s_stage[u];
+        __stcs(o2 + u, make_uint2(spread4(b & 15u), spread4(b >> 4)));
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// ---- the fused step / reset / encode kernel -------------------------------------------------------
+// kCoop = false: every warp owns its own tile (records in a private shared-memory slice), no block
+//                barrier after the table copy -- the mode for large batches.
+// kCoop = true:  the CTA owns ONE tile; all threads move the records, warp 0 runs the rules, then the
+//                warps share the tile's viewers -- for small batches and large records, where one warp per
+//                tile leaves the GPU short of parallel work.
+template <int kNS, int kW, int kOH, int kOW, int kFS, bool kCoop>
+__global__ void __launch_bounds__(kCoop ? SNK_MAX_THREADS_COOP : SNK_MAX_THREADS)
+snk_tile_kernel(const __grid_constant__ KParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const Dims& d = p.d;
+  const Shape<kNS, kW, kOH, kOW, kFS> sh(d);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, nwarps = nt >> 5;
+  const uint32_t lane = lane_id();
+  const int ns = sh.ns(), G = sh.group(), EPW = 32 / G;          // environments per tile
+  const int fs = sh.fs(), ohw = sh.ohw();
+  const int tile = kCoop ? (int)blockIdx.x : (int)blockIdx.x * nwarps + warp;
+  const int e0 = tile * EPW;
+  const int ne = max(0, min(EPW, d.N - e0));
+
+  // shared memory (mirrored by tile_smem_bytes): tiles' records, per-warp staging (fs > 1), per-tile
+  // flags, then the CTA-wide encode tables
+  const int tile_bytes = EPW * d.rec_bytes;
+  const int stage_bytes = fs == 1 ? 0 : round_up(d.stage_env_bytes, 16);
+  const int ntiles = kCoop ? 1 : nwarps;
+  uint8_t* s_rec = smem + (size_t)(kCoop ? 0 : warp) * tile_bytes;
+  uint8_t* s_stage = smem + (size_t)ntiles * tile_bytes + (size_t)warp * stage_bytes;
+  uint8_t* s_flag = smem + (size_t)ntiles * tile_bytes + (size_t)nwarps * stage_bytes + (size_t)(kCoop ? 0 : warp) * 32;
+  uint8_t* s_lut = smem + (size_t)ntiles * tile_bytes + (size_t)nwarps * stage_bytes + (size_t)ntiles * 32;
+
+  // ---- stage the tile's records: HBM -> shared, 128-bit coalesced
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.recs + (size_t)e0 * d.rec_bytes);
+    uint4* dst = reinterpret_cast<uint4*>(s_rec);
+    const int n16 = ne * (d.rec_bytes >> 4);
+    if (kCoop) { for (int k = tid; k < n16; k += nt) dst[k] = __ldcs(src + k); }
+    else { for (int k = (int)lane; k < n16; k += 32) dst[k] = __ldcs(src + k); }
+  }
+  // ---- encode tables: host-built blob, L2-resident, copied with 128-bit loads.  fs == 1: {cell code ->
+  //      8 output bytes, window-cell table}; fs > 1: {cell code -> channel-bit byte, table}.
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.enc_blob);
+    uint4* dst = reinterpret_cast<uint4*>(s_lut);
+    for (int k = tid; k < (p.enc_blob_bytes >> 4); k += nt) dst[k] = __ldg(src + k);
+  }
+  __syncthreads();
+  if (!kCoop && ne == 0) return;
+
+  if (!kCoop || warp == 0) {
+    if (ne > 0) tile_rules(p, sh, s_rec, e0, ne, s_flag);
+  }
+  if (kCoop) __syncthreads();
+  if (ne == 0) return;
 
   const bool want_obs = p.obs != nullptr;
-  const int H = d.H, V = d.V;
+  const uint32_t lut32 = (uint32_t)__cvta_generic_to_shared(s_lut);
+  const int wfirst = kCoop ? warp : 0, wstep = kCoop ? nwarps : 1;
 
   if (fs == 1) {
     // ---- write the records back: shared -> HBM (nothing below modifies them)
@@ -452,245 +708,57 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
       uint4* dst = reinterpret_cast<uint4*>(p.recs + (size_t)e0 * d.rec_bytes);
       const uint4* src = reinterpret_cast<const uint4*>(s_rec);
       const int n16 = ne * (d.rec_bytes >> 4);
-      for (int k = (int)lane; k < n16; k += 32) dst[k] = src[k];
+      if (kCoop) { for (int k = tid; k < n16; k += nt) dst[k] = src[k]; }
+      else { for (int k = (int)lane; k < n16; k += 32) dst[k] = src[k]; }
     }
-    // ---- fused encode: whole warp per (environment, viewer); each lane produces 16 output bytes (two
-    //      cells x 8 channels) per iteration straight from the staged grid through the LUT.
-    //      snake_env.py:474-519.  A viewer's block of ohw*8 bytes is only 8-byte aligned when ohw is
-    //      odd, so its 16-byte units are laid out from the address parity and the end units may be half.
-    //      Per window cell a host-built table gives {row bit | column bit << 16, grid offset}; the
-    //      zero padding outside the grid (:506-515) is one AND/compare against the viewer's valid
-    //      row / column masks.
     if (want_obs) {
-      const uint32_t lut32 = (uint32_t)__cvta_generic_to_shared(s_lut);
-      const uint32_t tab32 = lut32 + (uint32_t)p.enc_tab_off + 8u;       // entry of window cell 0
-      const uint2* lut_all = reinterpret_cast<const uint2*>(s_lut);
-      const int oh = sh.oh();
+      if (kCoop) {
 #pragma unroll 1
-      for (int q = 0; q < ne; ++q) {
-        const int qflag = __shfl_sync(FULL, (int)flag, q * G);
-        if (qflag & F_SKIP) continue;
-        const uint8_t* base = s_rec + (size_t)q * d.rec_bytes;
-        const uint8_t* grid = base;
-        const uint32_t grid32 = (uint32_t)__cvta_generic_to_shared(grid);
-#pragma unroll 1
-        for (int v = 0; v < ns; ++v) {
-          const uint8_t alive = base[d.off_snk + 7 * ns + v];
-          // crop centre: own head, or cell (0,0) when the viewer has no head in the grid   :500-502
-          const int hc = alive ? (int)((const uint16_t*)(base + d.off_snk))[v] : 0;
-          int r0 = 0, c0 = 0;
-          if (V > 0) { const int hr = hc / W; r0 = hr - V; c0 = hc - hr * W - V; }
+        for (int pv = wfirst; pv < ne * ns; pv += wstep) {
+          const int q = pv / ns, v = pv - q * ns;
+          if (s_flag[q] & F_SKIP) continue;
+          const uint8_t* base = s_rec + (size_t)q * d.rec_bytes;
           uint8_t* outv = p.obs + ((size_t)(e0 + q) * ns + v) * (size_t)ohw * 8;
-          const int shift = (int)((reinterpret_cast<uintptr_t>(outv) >> 3) & 1);
-          const int units = (ohw + shift + 1) >> 1;
-          if (p.use_tab) {
-            uint32_t maskpk = 0;
-            if (V > 0) {
-              const int rlo = max(0, -r0), rhi = min(oh, H - r0), clo = max(0, -c0), chi = min(ow, W - c0);
-              const uint32_t rm = ((1u << rhi) - 1u) & ~((1u << rlo) - 1u);
-              const uint32_t cm = ((1u << chi) - 1u) & ~((1u << clo) - 1u);
-              maskpk = rm | (cm << 16);
-            }
-            const uint32_t lutv32 = lut32 + (uint32_t)(v * LS) * 8u;     // entry 0 is all zero
-            const uint32_t gorg = grid32 + (uint32_t)(r0 * W + c0);
-            // two units per lane per trip: all table loads, then all grid bytes, then all LUT rows,
-            // so the three dependent shared-memory round trips of both units overlap
-            for (int u0 = (int)lane; u0 < units; u0 += 64) {
-              const int u1 = u0 + 32;
-              const bool has1 = u1 < units;
-              const int ca0 = 2 * u0 - shift, ca1 = 2 * (has1 ? u1 : u0) - shift;
-              const uint2 ea0 = lds_v2(tab32 + (uint32_t)(ca0 * 8));
-              const uint2 eb0 = lds_v2(tab32 + (uint32_t)(ca0 * 8 + 8));
-              const uint2 ea1 = lds_v2(tab32 + (uint32_t)(ca1 * 8));
-              const uint2 eb1 = lds_v2(tab32 + (uint32_t)(ca1 * 8 + 8));
-              const uint32_t aa0 = ((ea0.x & maskpk) == ea0.x) ? gorg + ea0.y : lutv32;
-              const uint32_t ab0 = ((eb0.x & maskpk) == eb0.x) ? gorg + eb0.y : lutv32;
-              const uint32_t aa1 = ((ea1.x & maskpk) == ea1.x) ? gorg + ea1.y : lutv32;
-              const uint32_t ab1 = ((eb1.x & maskpk) == eb1.x) ? gorg + eb1.y : lutv32;
-              const uint32_t ka0 = lds_u8(aa0), kb0 = lds_u8(ab0), ka1 = lds_u8(aa1), kb1 = lds_u8(ab1);
-              const uint2 qa0 = lds_v2(lutv32 + ka0 * 8u), qb0 = lds_v2(lutv32 + kb0 * 8u);
-              const uint2 qa1 = lds_v2(lutv32 + ka1 * 8u), qb1 = lds_v2(lutv32 + kb1 * 8u);
-              uint8_t* dst0 = outv + (ptrdiff_t)ca0 * 8;
-              if (ca0 >= 0 && ca0 + 1 < ohw) st_cs_128(dst0, qa0, qb0);
-              else if (ca0 >= 0) st_cs_64(dst0, qa0);
-              else st_cs_64(dst0 + 8, qb0);
-              if (has1) {
-                uint8_t* dst1 = outv + (ptrdiff_t)ca1 * 8;
-                if (ca1 + 1 < ohw) st_cs_128(dst1, qa1, qb1);
-                else st_cs_64(dst1, qa1);
-              }
-            }
-          } else {
-            const uint2* lut = lut_all + v * LS;
-            for (int u = (int)lane; u < units; u += 32) {
-              const int ca = 2 * u - shift, cb = ca + 1;
-              const bool va = ca >= 0, vb = cb < ohw;
-              uint2 qa, qb;
-              {
-                const int c = va ? ca : 0;
-                const int ci = c / ow, cj = c - ci * ow;
-                const int rr = r0 + ci, cc = c0 + cj;
-                uint32_t code = 0;
-                if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
-                qa = lut[code];
-              }
-              {
-                const int c = vb ? cb : 0;
-                const int ci = c / ow, cj = c - ci * ow;
-                const int rr = r0 + ci, cc = c0 + cj;
-                uint32_t code = 0;
-                if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
-                qb = lut[code];
-              }
-              uint8_t* dst = outv + (ptrdiff_t)ca * 8;
-              if (va && vb) st_cs_128(dst, qa, qb);
-              else if (va) st_cs_64(dst, qa);
-              else st_cs_64(dst + 8, qb);
-            }
-          }
+          encode_viewer_fs1(p, sh, base, (uint32_t)__cvta_generic_to_shared(base), v, outv, lut32);
+        }
+      } else {
+#pragma unroll 1
+        for (int q = 0; q < ne; ++q) {
+          if (s_flag[q] & F_SKIP) continue;
+          const uint8_t* base = s_rec + (size_t)q * d.rec_bytes;
+          const uint32_t grid32 = (uint32_t)__cvta_generic_to_shared(base);
+          uint8_t* outq = p.obs + (size_t)(e0 + q) * ns * (size_t)ohw * 8;
+#pragma unroll 1
+          for (int v = 0; v < ns; ++v) encode_viewer_fs1(p, sh, base, grid32, v, outq + (size_t)v * ohw * 8, lut32);
         }
       }
     }
     return;
   }
 
-  // ================= frame_stack > 1 ==================================================================
-  // Per environment: channel-bit bytes of all fs frames are staged in output order ([viewer][cell][frame],
-  // oldest first) in a per-warp staging area, then expanded to NHWC with flat 128-bit stores.  The frame
-  // history lives in HBM as one byte per window cell per stored frame, rows of a ring (hist layout).
-  {
-    const uint32_t lut32 = (uint32_t)__cvta_generic_to_shared(s_lut);          // uint8 lut[ns][LS]
-    const uint32_t tab32 = lut32 + (uint32_t)p.enc_tab_off + 8u;
-    const int oh = sh.oh();
-    const bool vec16 = want_obs && p.vec16 != 0;
+  // ---- frame_stack > 1
 #pragma unroll 1
-    for (int q = 0; q < ne; ++q) {
-      const int qflag = __shfl_sync(FULL, (int)flag, q * G);
-      if (qflag & F_SKIP) continue;
-      const uint8_t* base = s_rec + (size_t)q * d.rec_bytes;
-      const uint8_t* grid = base;
-      const uint32_t grid32 = (uint32_t)__cvta_generic_to_shared(grid);
-      const bool init = (qflag & (F_RESET | F_INIT)) != 0;
-      const int hpos = (int)((const EnvHdr*)(base + d.off_hdr))->hpos;
-#pragma unroll 1
-      for (int v = 0; v < ns; ++v) {
-        const uint8_t alive = base[d.off_snk + 7 * ns + v];
-        const int hc = alive ? (int)((const uint16_t*)(base + d.off_snk))[v] : 0;
-        int r0 = 0, c0 = 0;
-        if (V > 0) { const int hr = hc / W; r0 = hr - V; c0 = hc - hr * W - V; }
-        uint8_t* stg = s_stage + (size_t)v * ohw * fs;
-        uint8_t* hrow = p.hist + (size_t)(e0 + q) * d.hist_env_bytes + (size_t)(v * fs) * d.ohw_p;
-        if (kFS == 4 && p.use_tab) {
-          // four consecutive window cells per lane: the new frame's bits as one word, the three kept
-          // history rows as one word each, 4x4 byte transpose to per-cell words of four frames
-          uint32_t maskpk = 0;
-          if (V > 0) {
-            const int rlo = max(0, -r0), rhi = min(oh, H - r0), clo = max(0, -c0), chi = min(ow, W - c0);
-            maskpk = (((1u << rhi) - 1u) & ~((1u << rlo) - 1u)) | ((((1u << chi) - 1u) & ~((1u << clo) - 1u)) << 16);
-          }
-          const uint32_t lutv32 = lut32 + (uint32_t)(v * LS);               // entry 0 is zero
-          const uint32_t gorg = grid32 + (uint32_t)(r0 * W + c0);
-          for (int c4 = (int)lane * 4; c4 < ohw; c4 += 128) {
-            uint32_t nw = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int c = min(c4 + k, ohw);                                 // c == ohw: sentinel entry
-              const uint2 en = lds_v2(tab32 + (uint32_t)(c * 8));
-              const uint32_t a = ((en.x & maskpk) == en.x) ? gorg + en.y : lutv32;
-              nw |= lds_u8(lutv32 + lds_u8(a)) << (8 * k);
-            }
-            uint32_t f0, f1, f2;
-            if (!init) {
-              f0 = __ldcs(reinterpret_cast<const uint32_t*>(hrow + (size_t)((hpos + 1) & 3) * d.ohw_p + c4));
-              f1 = __ldcs(reinterpret_cast<const uint32_t*>(hrow + (size_t)((hpos + 2) & 3) * d.ohw_p + c4));
-              f2 = __ldcs(reinterpret_cast<const uint32_t*>(hrow + (size_t)((hpos + 3) & 3) * d.ohw_p + c4));
-              *reinterpret_cast<uint32_t*>(hrow + (size_t)hpos * d.ohw_p + c4) = nw;
-            } else {                                   // reset: every slot holds the first frame (:452-457)
-              f0 = f1 = f2 = nw;
-#pragma unroll
-              for (int f = 0; f < 4; ++f) *reinterpret_cast<uint32_t*>(hrow + (size_t)f * d.ohw_p + c4) = nw;
-            }
-            if (want_obs) {
-              const uint32_t t0 = __byte_perm(f0, f1, 0x5140), t1 = __byte_perm(f2, nw, 0x5140);
-              const uint32_t t2 = __byte_perm(f0, f1, 0x7362), t3 = __byte_perm(f2, nw, 0x7362);
-              uint32_t* dst = reinterpret_cast<uint32_t*>(stg) + c4;
-              dst[0] = __byte_perm(t0, t1, 0x5410);
-              if (c4 + 1 < ohw) dst[1] = __byte_perm(t0, t1, 0x7632);
-              if (c4 + 2 < ohw) dst[2] = __byte_perm(t2, t3, 0x5410);
-              if (c4 + 3 < ohw) dst[3] = __byte_perm(t2, t3, 0x7632);
-            }
-          }
-        } else {
-          if (want_obs && !init) {
-#pragma unroll 1
-            for (int slot = 0; slot < fs; ++slot) {
-              if (slot == hpos) continue;                // about to be overwritten by the new frame
-              int f = slot - hpos - 1; if (f < 0) f += fs;
-              const uint8_t* src = hrow + (size_t)slot * d.ohw_p;
-              for (int c4 = (int)lane * 4; c4 < ohw; c4 += 128) {
-                const uint32_t w = *reinterpret_cast<const uint32_t*>(src + c4);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  if (c4 + k < ohw) stg[(size_t)(c4 + k) * fs + f] = (uint8_t)(w >> (8 * k));
-              }
-            }
-          }
-          const uint8_t* lut = s_lut + v * LS;
-          for (int cell = (int)lane; cell < ohw; cell += 32) {
-            const int ci = cell / ow, cj = cell - ci * ow;
-            const int rr = r0 + ci, cc = c0 + cj;
-            uint32_t code = 0;
-            if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
-            const uint8_t bits = lut[code];
-            if (!init) {
-              if (want_obs) stg[(size_t)cell * fs + (fs - 1)] = bits;
-              hrow[(size_t)hpos * d.ohw_p + cell] = bits;
-            } else {
-              for (int f = 0; f < fs; ++f) {
-                if (want_obs) stg[(size_t)cell * fs + f] = bits;
-                hrow[(size_t)f * d.ohw_p + cell] = bits;
-              }
-            }
-          }
-        }
-      }
-      __syncwarp();
-      // ---- channel bits -> NHWC uint8, coalesced
-      if (want_obs) {
-        uint8_t* out = p.obs + (size_t)(e0 + q) * d.obs_env_bytes;
-        const int total = d.stage_env_bytes;                 // staging bytes == 8-byte output units
-        if (vec16) {
-          const uint16_t* s2 = reinterpret_cast<const uint16_t*>(s_stage);
-          uint4* o4 = reinterpret_cast<uint4*>(out);
-#pragma unroll 2
-          for (int u = (int)lane; u < (total >> 1); u += 32) {
-            const uint32_t two = s2[u];
-            uint4 qv;
-            qv.x = spread4(two & 15u); qv.y = spread4((two >> 4) & 15u);
-            qv.z = spread4((two >> 8) & 15u); qv.w = spread4(two >> 12);
-            __stcs(o4 + u, qv);
-          }
-        } else {
-          uint2* o2 = reinterpret_cast<uint2*>(out);
-          for (int u = (int)lane; u < total; u += 32) {
-            const uint32_t b = s_stage[u];
-            __stcs(o2 + u, make_uint2(spread4(b & 15u), spread4(b >> 4)));
-          }
-        }
-      }
-      __syncwarp();
+  for (int q = wfirst; q < ne; q += wstep) {
+    const int qflag = s_flag[q];
+    if (qflag & F_SKIP) continue;
+    encode_env_stacked<Shape<kNS, kW, kOH, kOW, kFS>, kFS>(p, sh, s_rec + (size_t)q * d.rec_bytes, e0 + q, qflag,
+                                                           s_stage, lut32, s_lut);
+  }
+  if (kCoop) __syncthreads(); else __syncwarp();
+  if (!kCoop || warp == 0) {
+    if ((int)lane < ne && !(s_flag[lane] & F_SKIP)) {
+      EnvHdr* h = (EnvHdr*)(s_rec + (size_t)lane * d.rec_bytes + d.off_hdr);
+      h->hpos = (s_flag[lane] & (F_RESET | F_INIT)) ? 0u : (h->hpos + 1u) % (uint32_t)fs;
     }
   }
-  if (active && i == 0 && !(flag & F_SKIP))
-    r.hdr->hpos = (flag & (F_RESET | F_INIT)) ? 0u : (r.hdr->hpos + 1u) % (uint32_t)fs;
-  __syncwarp();
-
+  if (kCoop) __syncthreads(); else __syncwarp();
   // ---- write the records back: shared -> HBM
   {
     uint4* dst = reinterpret_cast<uint4*>(p.recs + (size_t)e0 * d.rec_bytes);
     const uint4* src = reinterpret_cast<const uint4*>(s_rec);
     const int n16 = ne * (d.rec_bytes >> 4);
-    for (int k = (int)lane; k < n16; k += 32) dst[k] = src[k];
+    if (kCoop) { for (int k = tid; k < n16; k += nt) dst[k] = src[k]; }
+    else { for (int k = (int)lane; k < n16; k += 32) dst[k] = src[k]; }
   }
 }
 
@@ -765,11 +833,17 @@ int tile_group(int ns) { return ns <= 1 ? 1 : ns <= 2 ? 2 : ns <= 4 ? 4 : ns <= 
 bool encode_uses_table(const Dims& d) {
   return (d.V == 0 || (d.oh <= 16 && d.ow <= 16)) && (size_t)(d.ohw + 2) * 8 <= 16 * 1024;
 }
+// fs == 1 with many snakes: one {as-other, as-own} LUT pair instead of one LUT per viewer
+bool encode_lut_dual(const Dims& d) {
+  return d.fs == 1 && encode_uses_table(d) && (size_t)d.ns * (10 * d.ns + 6) * 8 > 8 * 1024;
+}
 
-// Encode blob: per-viewer LUT over cell codes (uint2 = 8 output bytes when fs == 1, one channel-bit byte
-// when fs > 1), then (optionally) uint2 tab[-1 .. ohw] per window cell.
+// Encode blob: LUT over cell codes, then (optionally) uint2 tab[-1 .. ohw] per window cell.
+//   fs == 1: uint2 (8 output bytes) per code, per viewer -- or {as-other, as-own} when encode_lut_dual
+//   fs  > 1: one channel-bit byte per code, per viewer
 size_t encode_blob_bytes(const Dims& d, size_t* tab_off) {
-  const size_t lut = (size_t)round_up(d.ns * (10 * d.ns + 6) * (d.fs == 1 ? 8 : 1), 16);
+  const int LS = 10 * d.ns + 6;
+  const size_t lut = (size_t)round_up(d.fs == 1 ? (encode_lut_dual(d) ? 2 : d.ns) * LS * 8 : d.ns * LS, 16);
   if (tab_off) *tab_off = lut;
   return (size_t)round_up((int)(lut + (encode_uses_table(d) ? (size_t)(d.ohw + 2) * 8 : 0)), 16);
 }
@@ -777,16 +851,27 @@ size_t encode_blob_bytes(const Dims& d, size_t* tab_off) {
 void encode_blob_fill(const Dims& d, uint8_t* out) {
   const int LS = 10 * d.ns + 6;
   uint32_t* w = reinterpret_cast<uint32_t*>(out);
-  for (int v = 0; v < d.ns; ++v)
-    for (int code = 0; code < LS; ++code) {
-      const uint32_t bits = cell_bits((uint32_t)code, (uint32_t)v);
-      if (d.fs == 1) {
-        w[2 * (v * LS + code)] = spread4(bits & 15u);
-        w[2 * (v * LS + code) + 1] = spread4(bits >> 4);
-      } else {
-        out[v * LS + code] = (uint8_t)bits;
+  if (encode_lut_dual(d)) {
+    for (int own = 0; own < 2; ++own)
+      for (int code = 0; code < LS; ++code) {
+        // viewer = owner of the code for the as-own half, some other snake for the as-other half
+        const uint32_t owner = (uint32_t)code / 10u;
+        const uint32_t bits = cell_bits((uint32_t)code, own ? owner : owner + 1u);
+        w[2 * (own * LS + code)] = spread4(bits & 15u);
+        w[2 * (own * LS + code) + 1] = spread4(bits >> 4);
       }
-    }
+  } else {
+    for (int v = 0; v < d.ns; ++v)
+      for (int code = 0; code < LS; ++code) {
+        const uint32_t bits = cell_bits((uint32_t)code, (uint32_t)v);
+        if (d.fs == 1) {
+          w[2 * (v * LS + code)] = spread4(bits & 15u);
+          w[2 * (v * LS + code) + 1] = spread4(bits >> 4);
+        } else {
+          out[v * LS + code] = (uint8_t)bits;
+        }
+      }
+  }
   if (!encode_uses_table(d)) return;
   size_t off;
   encode_blob_bytes(d, &off);
@@ -804,28 +889,34 @@ void encode_blob_fill(const Dims& d, uint8_t* out) {
 }
 
 // Shared memory of one CTA of `warps` warps (must mirror the carve-up in snk_tile_kernel).
-size_t tile_smem_bytes(const Dims& d, int warps) {
+size_t tile_smem_bytes(const Dims& d, int warps, bool coop) {
   const int EPW = 32 / tile_group(d.ns);
-  const int LS = 10 * d.ns + 6;
-  size_t per_warp = (size_t)EPW * d.rec_bytes;
-  if (d.fs > 1) per_warp += (size_t)round_up(d.stage_env_bytes, 16);
-  (void)LS;
-  return per_warp * warps + encode_blob_bytes(d, nullptr) + 16;
+  const size_t ntiles = coop ? 1 : (size_t)warps;
+  size_t b = ntiles * (size_t)EPW * d.rec_bytes;
+  if (d.fs > 1) b += (size_t)warps * (size_t)round_up(d.stage_env_bytes, 16);
+  b += ntiles * 32;
+  return b + encode_blob_bytes(d, nullptr) + 16;
 }
 
-template <int kNS, int kW, int kOH, int kOW, int kFS>
+template <int kNS, int kW, int kOH, int kOW, int kFS, bool kCoop>
 static cudaError_t launch_instance(const KParams& p, int threads, size_t smem_bytes, cudaStream_t stream) {
   static size_t configured = 0;
-  auto kern = snk_tile_kernel<kNS, kW, kOH, kOW, kFS>;
+  auto kern = snk_tile_kernel<kNS, kW, kOH, kOW, kFS, kCoop>;
   if (smem_bytes > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     configured = smem_bytes;
   }
-  const int envs_per_cta = (threads / 32) * (32 / tile_group(p.d.ns));
+  const int envs_per_cta = (kCoop ? 1 : threads / 32) * (32 / tile_group(p.d.ns));
   const int grid = (p.d.N + envs_per_cta - 1) / envs_per_cta;
   kern<<<grid, threads, smem_bytes, stream>>>(p);
   return cudaGetLastError();
+}
+
+template <int kNS, int kW, int kOH, int kOW, int kFS>
+static cudaError_t launch_mode(const KParams& p, int threads, size_t smem_bytes, cudaStream_t stream) {
+  return p.coop ? launch_instance<kNS, kW, kOH, kOW, kFS, true>(p, threads, smem_bytes, stream)
+                : launch_instance<kNS, kW, kOH, kOW, kFS, false>(p, threads, smem_bytes, stream);
 }
 
 // Specialised instances for the BASELINE shapes; everything else runs the generic instance.
@@ -834,13 +925,13 @@ cudaError_t launch_tile_kernel(const KParams& p, int threads, size_t smem_bytes,
   const bool generic = p.force_generic != 0;
 #define SNK_TRY(NS, W_, OH, OW, FS)                                                              \
   if (!generic && d.ns == NS && d.W == W_ && d.oh == OH && d.ow == OW && d.fs == FS)             \
-    return launch_instance<NS, W_, OH, OW, FS>(p, threads, smem_bytes, stream);
+    return launch_mode<NS, W_, OH, OW, FS>(p, threads, smem_bytes, stream);
   SNK_TRY(4, 20, 11, 11, 1)      // cfg1 / cfg5: 20x20, 4 snakes, vision 5
   SNK_TRY(4, 20, 20, 20, 1)      // cfg2: full-grid observation
   SNK_TRY(4, 20, 11, 11, 4)      // cfg3: frame_stack 4
   SNK_TRY(16, 64, 15, 15, 1)     // cfg4: 64x64, 16 snakes, vision 7
 #undef SNK_TRY
-  return launch_instance<0, 0, 0, 0, 0>(p, threads, smem_bytes, stream);
+  return launch_mode<0, 0, 0, 0, 0>(p, threads, smem_bytes, stream);
 }
 
 cudaError_t launch_get_state(const Dims& d, const uint8_t* recs, const StateView& sv, cudaStream_t s) {

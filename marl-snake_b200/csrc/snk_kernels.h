@@ -5,7 +5,9 @@
 
 #include "snk_core.cuh"
 
-#define SNK_MAX_THREADS 512
+// Launch bounds: tight bounds let ptxas keep the encode loop free of spills (48 registers at 128).
+#define SNK_MAX_THREADS 128
+#define SNK_MAX_THREADS_COOP 256
 
 namespace snk {
 
@@ -41,6 +43,8 @@ struct KParams {
   int32_t enc_blob_bytes;
   int32_t enc_tab_off;         // byte offset of the window-cell table inside the blob
   int32_t use_tab;
+  int32_t lut_dual;            // fs == 1: {as-other, as-own} LUT pair instead of one LUT per viewer
+  int32_t coop;                // CTA-cooperative tile (small batches / large records)
 };
 
 struct StateView {
@@ -49,7 +53,8 @@ struct StateView {
 };
 
 int tile_group(int ns);
-size_t tile_smem_bytes(const Dims& d, int warps);
+size_t tile_smem_bytes(const Dims& d, int warps, bool coop);
+bool encode_lut_dual(const Dims& d);
 bool encode_uses_table(const Dims& d);
 size_t encode_blob_bytes(const Dims& d, size_t* tab_off);
 void encode_blob_fill(const Dims& d, uint8_t* out);

@@ -229,3 +229,34 @@ def test_gpu_rollout_stats():
     assert st['env_steps'] == 200 * N
     t = b.stats_tensor()
     assert float(t[0]) == eps
+
+
+@pytest.mark.parametrize('coop', ['0', '1'])
+@pytest.mark.parametrize('kw,N', [
+    (dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5), 2051),
+    (dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5, frame_stack=4), 515),
+    (dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5, frame_stack=3), 260),
+    (dict(height=64, width=64, num_snakes=16, snake_length=5, vision_range=7), 37),
+    (dict(height=24, width=24, num_snakes=9, snake_length=3, vision_range=9), 50),     # window > 16: no table
+    (dict(height=12, width=12, num_snakes=2, snake_length=3), 300),
+])
+def test_gpu_tile_modes(monkeypatch, coop, kw, N):
+    """Both tile modes (warp-private tiles / CTA-cooperative tile) against the host build of the rule
+    source; by default the mode is chosen from the batch size, so each is forced here."""
+    from hostsim_util import HostSim
+    monkeypatch.setenv('SNK_COOP', coop)
+    ns = kw['num_snakes']
+    hs = HostSim(N, kw, rng_mode=0, auto_reset=1, seed=21)
+    be = GpuBackend(N, kw, rng_mode=0, auto_reset=1, seed=21)
+    assert np.array_equal(hs.reset(), be.reset())
+    rng = np.random.RandomState(5)
+    for t in range(100):
+        a = rng.randint(0, 3, size=(N, ns)).astype(np.uint8)
+        o1, r1, d1, i1 = hs.step(a)
+        o2, r2, d2, i2 = be.step(a)
+        assert np.array_equal(r1, r2) and np.array_equal(d1, d2.astype(np.uint8)), t
+        assert np.array_equal(o1, o2), t
+        assert np.array_equal(i1['finished'].astype(bool), i2['finished']), t
+    assert np.array_equal(hs.grid()[0], be.grid()[0])
+    assert be.errors() == 0
+    be.close()
