@@ -115,7 +115,7 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
   const int EPW = 32 / tile_group(d.ns);
   const int64_t tiles = ((int64_t)d.N + EPW - 1) / EPW;
   int coop = env_int("SNK_COOP", -1);
-  if (coop < 0) coop = (tiles < 148 * 24 || (size_t)EPW * d.rec_bytes > 8 * 1024) ? 1 : 0;
+  if (coop < 0) coop = (tiles < 148 * 24 || (size_t)EPW * d.rec_bytes > 8 * 1024 || d.fs > 1) ? 1 : 0;   // measured: profiles/README.md
   int threads = env_int("SNK_THREADS", coop ? 128 : 32);
   const int max_threads = coop ? SNK_MAX_THREADS_COOP : SNK_MAX_THREADS;
   if (threads < 32 || threads > max_threads || (threads & 31)) { delete h; return fail(SNK_E_INVALID, "SNK_THREADS must be a multiple of 32 in 32..%d", max_threads); }

@@ -172,6 +172,7 @@ struct Shape {
   __device__ __forceinline__ int lut_stride() const { return 10 * ns() + 6; }   // cell codes 0 .. 10*(ns-1)+5
   // the {as-other, as-own} LUT pair is only ever used when one LUT per viewer would exceed 8 KB
   static constexpr bool kMayDual = kNS == 0 || kNS * (10 * kNS + 6) * 8 > 8 * 1024;
+  static constexpr int kNSc = kNS;                                              // 0 = runtime
   __device__ __forceinline__ int group() const {                                // lanes per environment
     const int n = ns();
     return n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : 32;
@@ -540,8 +541,22 @@ __device__ __forceinline__ void encode_env_stacked(const KParams& p, const SH& s
   const uint32_t grid32 = (uint32_t)__cvta_generic_to_shared(grid);
   const bool init = (qflag & (F_RESET | F_INIT)) != 0;
   const int hpos = (int)((const EnvHdr*)(base + d.off_hdr))->hpos;
-#pragma unroll 1
-  for (int v = 0; v < ns; ++v) {
+  // fs == 4, up to 4 viewers, window <= 128 cells: fetch the kept history words of ALL viewers first so the
+  // environment pays one HBM round trip instead of one per viewer
+  constexpr int kPre = (kFS == 4 && SH::kNSc >= 1 && SH::kNSc <= 4) ? SH::kNSc : 0;
+  uint32_t pre[kPre > 0 ? kPre : 1][3];
+  const bool prefetched = kPre > 0 && p.use_tab && ohw <= 128 && !init;
+  if (prefetched && (int)lane * 4 < ohw) {
+#pragma unroll
+    for (int v = 0; v < kPre; ++v) {
+      const uint8_t* hr = p.hist + (size_t)e * d.hist_env_bytes + (size_t)(v * 4) * d.ohw_p + lane * 4;
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        pre[v][k] = __ldcs(reinterpret_cast<const uint32_t*>(hr + (size_t)((hpos + 1 + k) & 3) * d.ohw_p));
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < (kPre > 0 ? kPre : ns); ++v) {
     int r0, c0;
     viewer_origin(d, base, ns, W, V, v, r0, c0);
     uint8_t* stg = s_stage + (size_t)v * ohw * fs;
@@ -562,7 +577,10 @@ __device__ __forceinline__ void encode_env_stacked(const KParams& p, const SH& s
           nw |= lds_u8(lutv32 + lds_u8(a)) << (8 * k);
         }
         uint32_t f0, f1, f2;
-        if (!init) {
+        if (prefetched) {
+          f0 = pre[kPre > 0 ? v : 0][0]; f1 = pre[kPre > 0 ? v : 0][1]; f2 = pre[kPre > 0 ? v : 0][2];
+          *reinterpret_cast<uint32_t*>(hrow + (size_t)hpos * d.ohw_p + c4) = nw;
+        } else if (!init) {
           f0 = __ldcs(reinterpret_cast<const uint32_t*>(hrow + (size_t)((hpos + 1) & 3) * d.ohw_p + c4));
           f1 = __ldcs(reinterpret_cast<const uint32_t*>(hrow + (size_t)((hpos + 2) & 3) * d.ohw_p + c4));
           f2 = __ldcs(reinterpret_cast<const uint32_t*>(hrow + (size_t)((hpos + 3) & 3) * d.ohw_p + c4));
