@@ -324,7 +324,19 @@ class SnakeEnv:
             sym = {0: '.', 1: '#', 2: 'o', 3: 'H', 4: 'b', 5: 't'}
             print('\n'.join(''.join(sym[int(v) % 10] for v in row) for row in self.grid))
         elif mode == 'rgb_array':
-            raise NotImplementedError('rendering is host-side visualisation, outside the step path')
+            from .render import rgb_from_grid
+            return rgb_from_grid(self.grid)
+
+    def render_fancy(self, cell_size=40, save_path=None):
+        """RGB frame of the current state (host-side visualisation; see render.py)."""
+        from .render import render_fancy
+        st = self._batch.get_state()
+        img = render_fancy(st['grid'][0].cpu().numpy(), st['head'][0].cpu().numpy(), st['dir'][0].cpu().numpy(),
+                           cell_size)
+        if save_path:
+            from PIL import Image
+            Image.fromarray(img).save(save_path)
+        return img
 
 
 class CoopSnakeEnv(SnakeEnv):

@@ -1,0 +1,76 @@
+"""GPU-resident rollout plumbing for value-based callers.
+
+The reference's DQN trainer runs one tiny forward per live snake, moves every observation host -> device
+and synchronises with `.item()` per action (train_dqn.py:163-173, 277-308) and keeps its replay buffer in
+a Python deque (:89-100).  With the environment on the GPU the whole loop can stay there: batched
+epsilon-greedy straight from the device observation, transitions written into a device ring buffer, no
+host synchronisation per step.  Everything here is torch tensor plumbing around `SnakeBatch.step`; the
+game itself stays in the CUDA library.
+"""
+import torch
+
+
+def epsilon_greedy(q_values, epsilon, generator=None):
+    """q_values: float [B, n_actions] on the GPU -> uint8 actions [B]; with probability epsilon uniform."""
+    B, n = q_values.shape
+    greedy = q_values.argmax(dim=1)
+    explore = torch.rand(B, device=q_values.device, generator=generator) < epsilon
+    rand = torch.randint(0, n, (B,), device=q_values.device, generator=generator)
+    return torch.where(explore, rand, greedy).to(torch.uint8)
+
+
+class DeviceReplayBuffer:
+    """Fixed-capacity ring of transitions in device memory; observations stay uint8 (NHWC)."""
+
+    def __init__(self, capacity, obs_shape, device):
+        self.capacity, self.size, self.pos = int(capacity), 0, 0
+        self.obs = torch.empty((capacity, *obs_shape), dtype=torch.uint8, device=device)
+        self.next_obs = torch.empty_like(self.obs)
+        self.action = torch.empty(capacity, dtype=torch.uint8, device=device)
+        self.reward = torch.empty(capacity, dtype=torch.float32, device=device)
+        self.done = torch.empty(capacity, dtype=torch.bool, device=device)
+
+    def push(self, obs, action, reward, next_obs, done):
+        """Append a batch of transitions (any leading batch size <= capacity), wrapping around."""
+        n = obs.shape[0]
+        if n == 0:
+            return
+        if n > self.capacity:
+            obs, action, reward, next_obs, done = (t[-self.capacity:] for t in (obs, action, reward, next_obs, done))
+            n = self.capacity
+        idx = (self.pos + torch.arange(n, device=obs.device)) % self.capacity
+        self.obs[idx], self.next_obs[idx] = obs, next_obs
+        self.action[idx], self.reward[idx], self.done[idx] = action, reward.to(torch.float32), done
+        self.pos = (self.pos + n) % self.capacity
+        self.size = min(self.size + n, self.capacity)
+
+    def sample(self, batch_size, generator=None):
+        idx = torch.randint(0, self.size, (batch_size,), device=self.obs.device, generator=generator)
+        return self.obs[idx], self.action[idx], self.reward[idx], self.next_obs[idx], self.done[idx]
+
+
+@torch.no_grad()
+def collect(batch, q_net, steps, buffer=None, epsilon=0.1, generator=None):
+    """Run `steps` env steps of `batch` (SnakeBatch, auto-reset on) with a shared per-snake Q network
+    (input: float NCHW built from the uint8 NHWC observation, as train_dqn.py:168 does per snake).
+    Only snakes that were alive before the step produce transitions (train_dqn.py:290-298).
+    Returns the number of transitions written; nothing is copied to the host."""
+    N, ns = batch.num_envs, batch.num_snakes
+    obs = batch._obs if getattr(batch, '_has_obs', False) else batch.reset()
+    batch._has_obs = True
+    alive = torch.ones((N, ns), dtype=torch.bool, device=obs.device)
+    written = torch.zeros((), dtype=torch.int64, device=obs.device)
+    for _ in range(steps):
+        flat = obs.reshape(N * ns, *obs.shape[2:])
+        q = q_net(flat.permute(0, 3, 1, 2).float())
+        actions = epsilon_greedy(q, epsilon, generator).reshape(N, ns)
+        prev = flat.clone() if buffer is not None else None
+        obs, rew, done, info = batch.step(actions)
+        if buffer is not None:
+            m = alive.reshape(-1)
+            buffer.push(prev[m], actions.reshape(-1)[m], rew.reshape(-1)[m],
+                        obs.reshape(N * ns, *obs.shape[2:])[m], done.reshape(-1)[m])
+            written += m.sum()
+        # a finished env was reset inside the step: all of its snakes are alive again
+        alive = torch.where(info['finished'][:, None], torch.ones_like(done), ~done)
+    return written

@@ -69,14 +69,43 @@ class SingleMultiAgent(_Wrapper):
 
 
 class RenderGUI(_Wrapper):
-    """Placeholder for the reference's cv2 window wrapper (wrappers.py:20-82): visualisation is
-    outside the accelerated path.  step/reset pass through; render() returns None."""
+    """The reference's window / video wrapper (wrappers.py:20-82): render() draws the env's `render_fancy`
+    frame in a cv2 window and optionally appends it to an mp4.  Needs cv2 and a display; without them
+    render() still returns the RGB frame."""
 
     def __init__(self, env, window_name="Snake AI", save_video=False, video_path="output.mp4", fps=20):
         super().__init__(env)
+        self.window_name, self.render_size = window_name, 30
+        self.save_video, self.video_path, self.fps = save_video, video_path, fps
+        self.window_initialized, self.video_writer = False, None
 
     def render(self):
-        return None
+        img_rgb = self.env.render_fancy(cell_size=self.render_size)
+        try:
+            import cv2
+        except ImportError:
+            return img_rgb
+        img_bgr = cv2.cvtColor(img_rgb, cv2.COLOR_RGB2BGR)
+        try:
+            if not self.window_initialized:
+                cv2.namedWindow(self.window_name, cv2.WINDOW_NORMAL)
+                cv2.resizeWindow(self.window_name, img_bgr.shape[1], img_bgr.shape[0])
+                self.window_initialized = True
+            cv2.imshow(self.window_name, img_bgr)
+            cv2.waitKey(1)
+        except cv2.error:
+            pass                                   # headless box
+        if self.save_video:
+            if self.video_writer is None:
+                h, w, _ = img_bgr.shape
+                self.video_writer = cv2.VideoWriter(self.video_path, cv2.VideoWriter_fourcc(*"mp4v"), self.fps, (w, h))
+            self.video_writer.write(img_bgr)
+        return img_rgb
+
+    def close(self):
+        if self.video_writer is not None:
+            self.video_writer.release()
+        super().close()
 
 
 class VectorSnakeEnv:

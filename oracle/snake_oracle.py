@@ -426,6 +426,19 @@ class OracleSnakeEnv:
         return self._stacked()
 
 
+class CoopOracleSnakeEnv(OracleSnakeEnv):
+    """SnakeCoop-v1: any(dones) ends the episode and turns every done True (envs/coop_snake_env.py:14-22)."""
+
+    def step(self, actions):
+        obs, rews, dones, info = super().step(actions)
+        if self._done_fn(dones):
+            dones = [True] * self.num_snakes
+        return obs, rews, dones, info
+
+    def _done_fn(self, dones):
+        return any(dones)
+
+
 def competition_rank(scores):
     """Standard competition ranking on descending score, ties share (snake_env.py:397-404)."""
     scores = np.asarray(scores, dtype=np.float64)

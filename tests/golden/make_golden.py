@@ -95,14 +95,14 @@ def snake_cells(env, W):
     return alive, dirs, np.array(lens, dtype=np.int32), cells
 
 
-def rollout(name, seed, num_envs, steps, **kw):
+def rollout(name, seed, num_envs, steps, env_id='Snake-v1', **kw):
     """Seeded random rollout of `num_envs` independent reference envs with auto-reset."""
     ns = kw.get('num_snakes', 4)
     rec = dict(kind='rollout', kwargs=repr(kw), seed=seed)
     per_env = []
     act_rng = np.random.RandomState(seed + 777)
     for e in range(num_envs):
-        env = gym.make('Snake-v1', **kw)
+        env = gym.make(env_id, **kw)
         H, W = env.grid_shape
         np.random.seed(seed + e)
         tap = DrawTap()
@@ -155,6 +155,7 @@ def rollout(name, seed, num_envs, steps, **kw):
         for k, v in d.items():
             out[f'e{e}_{k}'] = v
     out['meta_kind'] = np.array('rollout')
+    out['meta_env_id'] = np.array(env_id)
     out['meta_kwargs'] = np.array(repr(kw))
     out['meta_seed'] = np.array(seed)
     out['meta_num_envs'] = np.array(num_envs)
@@ -389,6 +390,8 @@ if __name__ == '__main__':
     rollout('roll_cap', 600, 6, 60, height=8, width=8, num_snakes=2, snake_length=2,
             max_episode_steps=7, reward_dict=custom)
     rollout('roll_rect', 700, 4, 120, height=10, width=14, num_snakes=3, snake_length=4,
+            vision_range=3, frame_stack=2, reward_dict=cfg4_rew)
+    rollout('roll_coop', 900, 4, 120, env_id='SnakeCoop-v1', height=12, width=12, num_snakes=3, snake_length=3,
             vision_range=3, frame_stack=2, reward_dict=cfg4_rew)
     rollout('roll_crowd', 800, 4, 100, height=9, width=9, num_snakes=5, snake_length=3,
             vision_range=2, num_fruits=6, reward_dict=cfg4_rew)

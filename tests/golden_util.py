@@ -6,7 +6,7 @@ import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 ROLLOUTS = ['roll_cfg1', 'roll_full', 'roll_fs4', 'roll_big', 'roll_single', 'roll_cap',
-            'roll_rect', 'roll_crowd']
+            'roll_rect', 'roll_crowd', 'roll_coop']
 
 
 def unpack_obs(packed):
@@ -24,6 +24,8 @@ class Rollout:
         self.num_envs = int(z['meta_num_envs'])
         self.steps = int(z['meta_steps'])
         self.seed = int(z['meta_seed'])
+        self.env_id = str(z['meta_env_id']) if 'meta_env_id' in z.files else 'Snake-v1'
+        self.done_mode = 1 if self.env_id == 'SnakeCoop-v1' else 0
         self.env = [{k[len(f'e{e}_'):]: z[k] for k in z.files if k.startswith(f'e{e}_')}
                     for e in range(self.num_envs)]
 

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize('name', ROLLOUTS)
 def test_gpu_rollout_replay(name):
     g = Rollout(name)
-    be = GpuBackend(g.num_envs, g.kwargs, rng_mode=1, auto_reset=1)
+    be = GpuBackend(g.num_envs, g.kwargs, rng_mode=1, auto_reset=1, done_mode=g.done_mode)
     check_rollout_replay(be, g)
     assert be.errors() == 0
     be.close()
@@ -260,3 +260,34 @@ def test_gpu_tile_modes(monkeypatch, coop, kw, N):
     assert np.array_equal(hs.grid()[0], be.grid()[0])
     assert be.errors() == 0
     be.close()
+
+
+def test_render_export_and_gui_wrapper():
+    """N3: one environment's state exported to the host renderers (render_fancy / rgb_array / RenderGUI)."""
+    from marl_snake_b200 import RenderGUI, make_snake
+    env, _, _, _ = make_snake(num_envs=1, num_snakes=4, vision_range=5)
+    env = RenderGUI(env)
+    env.reset()
+    env.step([0, 1, 2, 0])
+    frame = env.render()
+    assert frame.shape == (20 * 30, 20 * 30, 3) and frame.dtype == np.uint8 and frame.max() > 0
+    rgb = env.unwrapped.render('rgb_array')
+    assert rgb.shape == (20, 20, 3)
+    env.close()
+
+
+def test_device_rollout_with_q_network():
+    """N1: epsilon-greedy from the device observation + device replay buffer, no host sync per step."""
+    from marl_snake_b200 import DeviceReplayBuffer, SnakeBatch, collect
+    torch.manual_seed(0)
+    N, ns = 512, 4
+    b = SnakeBatch(N, num_snakes=ns, vision_range=5, seed=4)
+    net = torch.nn.Sequential(torch.nn.Conv2d(8, 16, 3, padding=1), torch.nn.ReLU(), torch.nn.Flatten(),
+                              torch.nn.Linear(16 * 11 * 11, 3)).cuda()
+    buf = DeviceReplayBuffer(50000, b.obs_shape[1:], b.device)
+    n = int(collect(b, net, 40, buf, epsilon=0.2))
+    assert 0 < n <= 40 * N * ns and buf.size == min(n, 50000)
+    o, a, r, o2, d = buf.sample(256)
+    assert o.shape == (256, 11, 11, 8) and o.dtype == torch.uint8 and int(a.max()) <= 2
+    assert bool((o[:, 5, 5, 5] == 1).all())          # every stored state belongs to a live snake: own head at the centre
+    assert b.device_errors() == 0

@@ -12,7 +12,7 @@ from parity_util import check_against_oracle_philox, check_rollout_replay, check
 @pytest.mark.parametrize('name', ROLLOUTS)
 def test_hostsim_rollout_replay(name):
     g = Rollout(name)
-    hs = HostSim(g.num_envs, g.kwargs, rng_mode=1, auto_reset=1)
+    hs = HostSim(g.num_envs, g.kwargs, rng_mode=1, auto_reset=1, done_mode=g.done_mode)
     check_rollout_replay(hs, g)
     assert hs.errors() == 0
     hs.close()

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from golden_util import ROLLOUTS, Rollout, load_scenarios, load_spawn_tables, unpack_obs
-from oracle.snake_oracle import (OracleSnakeEnv, ReplayDraws, RecordingDraws, TURN,
+from oracle.snake_oracle import (CoopOracleSnakeEnv, OracleSnakeEnv, ReplayDraws, RecordingDraws, TURN,
                                  spawn_candidates, competition_rank)
 
 
@@ -25,7 +25,8 @@ def test_rollout_replay(name):
     g = Rollout(name)
     for e in range(g.num_envs):
         ge = g.env[e]
-        env = OracleSnakeEnv(draws=ReplayDraws(ge['draws']), **g.kwargs)
+        cls = CoopOracleSnakeEnv if g.done_mode else OracleSnakeEnv
+        env = cls(draws=ReplayDraws(ge['draws']), **g.kwargs)
         obs = env.reset()
         assert np.array_equal(obs, unpack_obs(ge['obs0']))
         assert np.array_equal(env.grid, ge['grid0'])
