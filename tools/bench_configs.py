@@ -33,7 +33,7 @@ def run(name, kw, steps, graph=False):
     npool = 251
     pool = torch.randint(0, 3, (npool, N, ns), dtype=torch.uint8, device='cuda', generator=g)
     b.reset()
-    for t in range(300):
+    for t in range(int(os.environ.get('BENCH_BURN', 300))):
         b.step(pool[t % npool], want_info=False)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -78,6 +78,6 @@ def run(name, kw, steps, graph=False):
 if __name__ == '__main__':
     which = sys.argv[1:] or list(CONFIGS)
     for name in which:
-        run(name, CONFIGS[name], 400 if name != 'cfg2' else 2000)
-        if name == 'cfg2':
+        run(name, CONFIGS[name], int(os.environ.get('BENCH_STEPS', 400 if name != 'cfg2' else 2000)))
+        if name == 'cfg2' and 'BENCH_STEPS' not in os.environ:
             run(name, CONFIGS[name], 2000, graph=True)
