@@ -291,3 +291,103 @@ def test_device_rollout_with_q_network():
     assert o.shape == (256, 11, 11, 8) and o.dtype == torch.uint8 and int(a.max()) <= 2
     assert bool((o[:, 5, 5, 5] == 1).all())          # every stored state belongs to a live snake: own head at the centre
     assert b.device_errors() == 0
+
+
+def test_gpu_long_spawn_pose_matches_oracle():
+    """snake_length 6 on a 7x9 grid: bent spawn poses and the head-boxed pruning of the DFS table."""
+    kw = dict(height=7, width=9, num_snakes=2, snake_length=6, vision_range=2, num_fruits=3)
+    be = check_against_oracle_philox(GpuBackend, kw, num_envs=40, steps=60, seed=99)
+    assert be.errors() == 0
+    be.close()
+
+
+@pytest.mark.parametrize('fs', [1, 3])
+def test_gpu_masked_reset(fs):
+    """snk_reset with a mask: only the selected envs restart (and get a fresh observation)."""
+    from marl_snake_b200 import SnakeBatch
+    N, ns = 257, 3
+    b = SnakeBatch(N, num_snakes=ns, vision_range=3, frame_stack=fs, seed=8, auto_reset=False)
+    b.reset()
+    g = torch.Generator(device='cuda').manual_seed(2)
+    for _ in range(25):
+        obs, _, _, _ = b.step(torch.randint(0, 3, (N, ns), dtype=torch.uint8, device='cuda', generator=g))
+    before = {k: v.clone() for k, v in b.get_state(max_cells=12).items()}
+    obs_before = obs.clone()
+    mask = torch.zeros(N, dtype=torch.uint8, device='cuda')
+    mask[::3] = 1
+    sel = mask.bool()
+    obs_after = b.reset(mask=mask).clone()
+    after = b.get_state(max_cells=12)
+    for k in before:
+        assert torch.equal(before[k][~sel], after[k][~sel]), k           # untouched envs keep their state
+    assert torch.equal(obs_after[~sel], obs_before[~sel])                # ... and their observation buffer
+    assert bool(after['alive'][sel].all()) and int(after['episode_length'][sel].abs().sum()) == 0
+    assert bool((after['alive_counter'][sel] == ns).all()) and bool((after['length'][sel] == 3).all())
+    if fs > 1:                                                           # every frame of a reset env is the first frame
+        o = obs_after[sel]
+        assert torch.equal(o[..., :8], o[..., 8:16]) and torch.equal(o[..., :8], o[..., 16:24])
+    assert b.device_errors() == 0
+
+
+@pytest.mark.parametrize('fs', [1, 4])
+def test_gpu_step_without_obs_keeps_history(fs):
+    """want_obs=False steps (obs pointer NULL) must leave state and frame history exactly as if rendered."""
+    from marl_snake_b200 import SnakeBatch
+    N, ns = 300, 4
+    kw = dict(num_snakes=ns, vision_range=5, frame_stack=fs, seed=12)
+    a, b = SnakeBatch(N, **kw), SnakeBatch(N, **kw)
+    a.reset(); b.reset()
+    g = torch.Generator(device='cuda').manual_seed(3)
+    for t in range(60):
+        act = torch.randint(0, 3, (N, ns), dtype=torch.uint8, device='cuda', generator=g)
+        oa, ra, da, _ = a.step(act)
+        ob, rb, db, _ = b.step(act, want_obs=(t % 5 == 4))
+        assert torch.equal(ra, rb) and torch.equal(da, db)
+        if t % 5 == 4:
+            assert torch.equal(oa, ob), t
+
+
+def test_gpu_host_buffer_entry_points():
+    """snk_reset_host / snk_step_host (host pointers, copies inside) against the device-pointer path."""
+    from marl_snake_b200 import SnakeBatch
+    N, ns = 129, 4
+    kw = dict(num_snakes=ns, vision_range=5, seed=31)
+    dev, host = SnakeBatch(N, **kw), SnakeBatch(N, **kw)
+    h_obs = torch.empty((N,) + host.obs_shape, dtype=torch.uint8).pin_memory()
+    h_rew = torch.empty((N, ns), dtype=torch.float64).pin_memory()
+    h_done = torch.empty((N, ns), dtype=torch.uint8).pin_memory()
+    host.reset_host(h_obs)
+    assert torch.equal(dev.reset().cpu(), h_obs)
+    g = torch.Generator().manual_seed(5)
+    for _ in range(30):
+        act = torch.randint(0, 3, (N, ns), dtype=torch.uint8, generator=g)
+        host.step_host(act, h_obs, h_rew, h_done)
+        o, r, d, _ = dev.step(act.cuda())
+        assert torch.equal(o.cpu(), h_obs) and torch.equal(r.cpu(), h_rew) and torch.equal(d.cpu(), h_done.bool())
+
+
+def test_gpu_state_roundtrip():
+    """get_state -> set_state on a second batch reproduces the trajectory (checkpoint / restore)."""
+    from marl_snake_b200 import SnakeBatch
+    N, ns = 200, 4
+    kw = dict(num_snakes=ns, vision_range=5, seed=17)
+    a, b = SnakeBatch(N, **kw), SnakeBatch(N, seed=999, num_snakes=ns, vision_range=5)
+    a.reset(); b.reset()
+    g = torch.Generator(device='cuda').manual_seed(9)
+    for _ in range(40):
+        a.step(torch.randint(0, 3, (N, ns), dtype=torch.uint8, device='cuda', generator=g))
+    st = a.get_state(max_cells=64)
+    obs_b = b.set_state(st['grid'].cpu().numpy(), st['alive'].cpu().numpy(), st['dir'].cpu().numpy(),
+                        st['length'].cpu().numpy(), st['cells'].clamp(min=0).cpu().numpy(),
+                        st['alive_counter'].cpu().numpy(), st['episode_length'].cpu().numpy())
+    st2 = b.get_state(max_cells=64)
+    for k in ('grid', 'head', 'tail', 'length', 'alive', 'alive_counter', 'episode_length', 'cells'):
+        assert torch.equal(st[k], st2[k]), k
+    # same next step; envs that drew randomness this step (fruit respawn, reset) differ by design (other seed)
+    act = torch.randint(0, 3, (N, ns), dtype=torch.uint8, device='cuda', generator=g)
+    oa, ra, da, ia = a.step(act)
+    ob, rb, db, ib = b.step(act)
+    assert torch.equal(ra, rb) and torch.equal(da, db) and torch.equal(ia['finished'], ib['finished'])
+    quiet = (~ia['finished']) & (a.get_state()['grid'] == b.get_state()['grid']).all(2).all(1)
+    assert int(quiet.sum()) > N // 2
+    assert torch.equal(oa[quiet], ob[quiet])
