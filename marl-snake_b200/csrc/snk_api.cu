@@ -49,7 +49,7 @@ struct snk_env {
   uint8_t* h_actions = nullptr; uint8_t* h_obs = nullptr; double* h_rew = nullptr; uint8_t* h_done = nullptr;
   cudaStream_t own_stream = nullptr;
   double env_steps = 0.0;
-  int force_generic = 0, coop = 0, lut_dual = 0;
+  int force_generic = 0, coop = 0, lut_dual = 0, use_tma = 0;
   bool was_reset = false;
 };
 
@@ -71,7 +71,7 @@ static KParams base_params(const snk_env* h) {
   p.E = h->tile_envs;
   p.force_generic = h->force_generic;
   p.enc_blob = h->enc_blob; p.enc_blob_bytes = h->enc_blob_bytes; p.enc_tab_off = h->enc_tab_off; p.use_tab = h->use_tab;
-  p.lut_dual = h->lut_dual; p.coop = h->coop;
+  p.lut_dual = h->lut_dual; p.coop = h->coop; p.use_tma = h->use_tma;
   return p;
 }
 
@@ -122,6 +122,7 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
   while (threads > 32 && tile_smem_bytes(d, threads / 32, coop != 0) > 200 * 1024) threads -= 32;
   h->tile_envs = EPW; h->threads = threads; h->coop = coop;
   h->force_generic = env_int("SNK_FORCE_GENERIC", 0);
+  h->use_tma = env_int("SNK_TMA", 1);
   h->smem_bytes = tile_smem_bytes(d, threads / 32, coop != 0);
   if (h->smem_bytes > 227 * 1024) {
     const size_t need = h->smem_bytes;

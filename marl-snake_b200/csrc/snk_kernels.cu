@@ -193,6 +193,34 @@ __device__ __forceinline__ uint2 lds_v2(uint32_t a) {
   return v;
 }
 
+// ---- 1-D bulk asynchronous copies (TMA engine): cp.async.bulk + mbarrier --------------------------
+// The record tile is one contiguous, 16-byte aligned range, so one elected thread moves it with a single
+// instruction each way; no registers or LSU wavefronts are spent on it.
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t done = 0;
+  int spins = 0;
+  while (!done) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+    if (!done && ++spins > (1 << 22)) __trap();          // never hang the GPU on a lost transaction
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // Several lanes of one environment may update plane bytes that share a word: atomic read-modify-write.
 __device__ __forceinline__ void dirp_set_atomic(uint8_t* dirp, int c, int v) {
   uint32_t* w = reinterpret_cast<uint32_t*>(dirp) + (c >> 4);
@@ -689,11 +717,21 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   const int ntiles = kCoop ? 1 : nwarps;
   uint8_t* s_rec = smem + (size_t)(kCoop ? 0 : warp) * tile_bytes;
   uint8_t* s_stage = smem + (size_t)ntiles * tile_bytes + (size_t)warp * stage_bytes;
-  uint8_t* s_flag = smem + (size_t)ntiles * tile_bytes + (size_t)nwarps * stage_bytes + (size_t)(kCoop ? 0 : warp) * 32;
-  uint8_t* s_lut = smem + (size_t)ntiles * tile_bytes + (size_t)nwarps * stage_bytes + (size_t)ntiles * 32;
+  uint8_t* s_flag = smem + (size_t)ntiles * tile_bytes + (size_t)nwarps * stage_bytes + (size_t)(kCoop ? 0 : warp) * 48;
+  uint8_t* s_lut = smem + (size_t)ntiles * tile_bytes + (size_t)nwarps * stage_bytes + (size_t)ntiles * 48;
 
-  // ---- stage the tile's records: HBM -> shared, 128-bit coalesced
-  {
+  // ---- stage the tile's records: HBM -> shared.  One bulk asynchronous copy (TMA) issued by the tile's
+  //      elected thread and awaited on an mbarrier, or 128-bit coalesced loads (p.use_tma == 0).
+  const bool elected = kCoop ? tid == 0 : lane == 0;
+  const uint32_t rec32 = (uint32_t)__cvta_generic_to_shared(s_rec);
+  const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(s_flag) + 32u;     // flags: 32 B, mbarrier: 8 B
+  const uint32_t tile_load_bytes = (uint32_t)ne * (uint32_t)d.rec_bytes;
+  if (p.use_tma) {
+    if (elected) {
+      mbar_init(mbar, 1);
+      if (ne > 0) bulk_load(rec32, p.recs + (size_t)e0 * d.rec_bytes, tile_load_bytes, mbar);
+    }
+  } else {
     const uint4* src = reinterpret_cast<const uint4*>(p.recs + (size_t)e0 * d.rec_bytes);
     uint4* dst = reinterpret_cast<uint4*>(s_rec);
     const int n16 = ne * (d.rec_bytes >> 4);
@@ -709,9 +747,12 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   }
   __syncthreads();
   if (!kCoop && ne == 0) return;
+  if (p.use_tma && ne > 0) mbar_wait(mbar, 0);
 
   if (!kCoop || warp == 0) {
     if (ne > 0) tile_rules(p, sh, s_rec, e0, ne, s_flag);
+    if (p.use_tma) fence_proxy_async();        // the rules' shared-memory writes -> visible to the bulk store
+    __syncwarp();
   }
   if (kCoop) __syncthreads();
   if (ne == 0) return;
@@ -721,8 +762,11 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   const int wfirst = kCoop ? warp : 0, wstep = kCoop ? nwarps : 1;
 
   if (fs == 1) {
-    // ---- write the records back: shared -> HBM (nothing below modifies them)
-    {
+    // ---- write the records back: shared -> HBM (nothing below modifies them).  The bulk store runs
+    //      asynchronously under the encode; its issuer waits for the shared-memory reads before exiting.
+    if (p.use_tma) {
+      if (elected) bulk_store(p.recs + (size_t)e0 * d.rec_bytes, rec32, tile_load_bytes);
+    } else {
       uint4* dst = reinterpret_cast<uint4*>(p.recs + (size_t)e0 * d.rec_bytes);
       const uint4* src = reinterpret_cast<const uint4*>(s_rec);
       const int n16 = ne * (d.rec_bytes >> 4);
@@ -751,6 +795,7 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
         }
       }
     }
+    if (p.use_tma && elected) bulk_store_wait_read();
     return;
   }
 
@@ -769,9 +814,15 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
       h->hpos = (s_flag[lane] & (F_RESET | F_INIT)) ? 0u : (h->hpos + 1u) % (uint32_t)fs;
     }
   }
+  if (p.use_tma && (!kCoop || warp == 0)) fence_proxy_async();        // hpos updates -> async proxy
   if (kCoop) __syncthreads(); else __syncwarp();
   // ---- write the records back: shared -> HBM
-  {
+  if (p.use_tma) {
+    if (elected) {
+      bulk_store(p.recs + (size_t)e0 * d.rec_bytes, rec32, tile_load_bytes);
+      bulk_store_wait_read();
+    }
+  } else {
     uint4* dst = reinterpret_cast<uint4*>(p.recs + (size_t)e0 * d.rec_bytes);
     const uint4* src = reinterpret_cast<const uint4*>(s_rec);
     const int n16 = ne * (d.rec_bytes >> 4);
@@ -912,7 +963,7 @@ size_t tile_smem_bytes(const Dims& d, int warps, bool coop) {
   const size_t ntiles = coop ? 1 : (size_t)warps;
   size_t b = ntiles * (size_t)EPW * d.rec_bytes;
   if (d.fs > 1) b += (size_t)warps * (size_t)round_up(d.stage_env_bytes, 16);
-  b += ntiles * 32;
+  b += ntiles * 48;
   return b + encode_blob_bytes(d, nullptr) + 16;
 }
 

@@ -45,6 +45,7 @@ struct KParams {
   int32_t use_tab;
   int32_t lut_dual;            // fs == 1: {as-other, as-own} LUT pair instead of one LUT per viewer
   int32_t coop;                // CTA-cooperative tile (small batches / large records)
+  int32_t use_tma;             // move the record tile with cp.async.bulk (TMA) instead of LDG/STG
 };
 
 struct StateView {
