@@ -239,6 +239,9 @@ def test_gpu_rollout_stats():
     (dict(height=64, width=64, num_snakes=16, snake_length=5, vision_range=7), 37),
     (dict(height=24, width=24, num_snakes=9, snake_length=3, vision_range=9), 50),     # window > 16: no table
     (dict(height=12, width=12, num_snakes=2, snake_length=3), 300),
+    (dict(height=30, width=30, num_snakes=20, snake_length=3, vision_range=4), 21),   # one env per warp, dual LUT
+    (dict(height=26, width=26, num_snakes=25, snake_length=2, num_fruits=30), 9),       # max snakes, full-grid obs
+    (dict(height=9, width=9, num_snakes=1, snake_length=3, vision_range=2), 700),      # 32 envs per warp
 ])
 def test_gpu_tile_modes(monkeypatch, coop, kw, N):
     """Both tile modes (warp-private tiles / CTA-cooperative tile) against the host build of the rule
