@@ -240,7 +240,7 @@ struct GroupOut {
 // `active`: this lane holds a real snake of a real environment.  All 32 lanes must call.
 template <class SH>
 __device__ __forceinline__ GroupOut step_group(const KParams& p, const SH& sh, Rec& r, bool active, int i,
-                                               uint32_t gmask, int gbase, size_t io) {
+                                               uint32_t gmask, int gbase, size_t io, uint32_t action) {
   const Dims& d = p.d;
   const uint32_t FULL = 0xffffffffu;
   const uint32_t lane = lane_id();
@@ -251,7 +251,7 @@ __device__ __forceinline__ GroupOut step_group(const KParams& p, const SH& sh, R
   int dirv = 0;
   uint32_t tgt = 0x10000u + lane;                       // unique dummy: never matches a real cell
   if (was_alive) {
-    uint32_t a = p.actions[io];
+    uint32_t a = action;                                  // fetched while the record tile was in flight
     if (a > 2u) { atomicOr(p.err, ERR_BAD_ACTION); a = 0; }
     dirv = (r.dir[i] + (a == 1u ? 3 : a == 2u ? 1 : 0)) & 3;
     tgt = (uint32_t)(r.head[i] + dir_delta(dirv, W));
@@ -366,7 +366,7 @@ __device__ __forceinline__ GroupOut step_group(const KParams& p, const SH& sh, R
 // Leaves per-environment flags in s_flag[] (F_RESET / F_INIT / F_SKIP).
 template <class SH>
 __device__ __forceinline__ void tile_rules(const KParams& p, const SH& sh, uint8_t* s_rec, int e0, int ne,
-                                           uint8_t* s_flag) {
+                                           uint8_t* s_flag, uint32_t action) {
   const Dims& d = p.d;
   const uint32_t FULL = 0xffffffffu;
   const uint32_t lane = lane_id();
@@ -386,7 +386,7 @@ __device__ __forceinline__ void tile_rules(const KParams& p, const SH& sh, uint8
   if (p.mode == MODE_STEP) {
     if (active && i == 0) r.hdr->event += 1;
     __syncwarp();
-    const GroupOut res = step_group(p, sh, r, active, i, gmask, gbase, io);
+    const GroupOut res = step_group(p, sh, r, active, i, gmask, gbase, io, action);
     fruit = res.fruit_taken;
     // terminal info, rollout statistics, statistics reset                          :396-412
     const bool fin = env_ok && res.finished;
@@ -745,12 +745,18 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
     uint4* dst = reinterpret_cast<uint4*>(s_lut);
     for (int k = tid; k < (p.enc_blob_bytes >> 4); k += nt) dst[k] = __ldg(src + k);
   }
+  // this lane's action (lane = environment lane/G of the tile, snake lane%G), fetched before the waits
+  uint32_t action = 0;
+  if (p.mode == MODE_STEP && (!kCoop || warp == 0)) {
+    const int g = (int)lane / G, i = (int)lane - g * G;
+    if (g < ne && i < ns) action = __ldg(p.actions + (size_t)(e0 + g) * ns + i);
+  }
   __syncthreads();
   if (!kCoop && ne == 0) return;
   if (p.use_tma && ne > 0) mbar_wait(mbar, 0);
 
   if (!kCoop || warp == 0) {
-    if (ne > 0) tile_rules(p, sh, s_rec, e0, ne, s_flag);
+    if (ne > 0) tile_rules(p, sh, s_rec, e0, ne, s_flag, action);
     if (p.use_tma) fence_proxy_async();        // the rules' shared-memory writes -> visible to the bulk store
     __syncwarp();
   }
