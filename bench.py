@@ -217,27 +217,44 @@ def ours(args):
     stats = allreduce_stats(batch.stats_tensor().clone())
     stats_host = stats.cpu().tolist()
 
-    # e2e: the reference-shaped call with HOST buffers (pinned), copies inside the timed region
+    # e2e: the reference-shaped call with HOST buffers (pinned), copies inside the timed region.  Default
+    # transport of the C ABI for a block this size: channel bits over PCIe, widened to the reference's 0/1
+    # bytes by the host cores (shared by the ranks of the box); the straight NHWC copy is timed beside it.
     K2 = max(1, args.e2e_steps)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    host_threads = max(1, cores // world)
     h_act = [p.cpu().pin_memory() for p in pool[:4]]
     h_obs = torch.empty((N,) + batch.obs_shape, dtype=torch.uint8).pin_memory()
     h_rew = torch.empty((N, ns), dtype=torch.float64).pin_memory()
     h_done = torch.empty((N, ns), dtype=torch.uint8).pin_memory()
-    for t in range(2):
-        batch.step_host(h_act[t % 4], h_obs, h_rew, h_done)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for t in range(K2):
-        batch.step_host(h_act[t % 4], h_obs, h_rew, h_done)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        ts = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
-        e2e_s = float(ts.item())
-    assert int(h_obs.max()) == 1 and bool((h_done <= 1).all())
+
+    def time_host_steps(mode):
+        batch.set_host_transport(mode, threads=host_threads)
+        for t in range(2):
+            batch.step_host(h_act[t % 4], h_obs, h_rew, h_done)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for t in range(K2):
+            batch.step_host(h_act[t % 4], h_obs, h_rew, h_done)
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        if world > 1:
+            ts = torch.tensor([sec], device=dev, dtype=torch.float64)
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            sec = float(ts.item())
+        assert int(h_obs.max()) == 1 and bool((h_done <= 1).all())
+        return sec
+
+    e2e_raw_s = time_host_steps('raw')
+    e2e_s = time_host_steps('packed')
+    # the delivered block against the device state of the same step: the window centre of a live snake is
+    # its own head (channel 5), a dead snake's window sits on wall cell (0,0)  (byte parity: tests/)
+    V = ENV_KW['vision_range']
+    alive_now = batch.get_state()['alive'].cpu().bool()
+    assert torch.equal(h_obs[:, :, V, V, 5].bool(), alive_now), 'packed transport: observation/state mismatch'
+    assert int(h_obs[:8192].view(-1, 8).sum(1).max()) == 1
 
     if rank == 0:
         peaks = {}
@@ -278,8 +295,14 @@ def ours(args):
             'e2e': {'value': N * world * ns * K2 / e2e_s, 'unit': 'agent-steps/s',
                     'h2d_bytes_per_step': N * ns, 'd2h_bytes_per_step': N * (batch.obs_shape[0] * batch.obs_shape[1] *
                                                                              batch.obs_shape[2] * batch.obs_shape[3]) + N * ns * 9,
-                    'steps': K2, 'ms_per_step': 1e3 * e2e_s / K2, 'api': 'snk_step_host (C ABI, pinned host buffers)'},
-            'gpu_launches': args.steps * world,
+                    'steps': K2, 'ms_per_step': 1e3 * e2e_s / K2,
+                    'api': 'snk_step_host (C ABI, pinned host buffers), packed transport: device packs 8 channel '
+                           'bytes -> 1, %d MB over PCIe in chunks, %d host threads per rank widen to uint8 NHWC'
+                           % (obs_bytes * N // 8 // 1000000, host_threads),
+                    'pcie_obs_bytes_per_step': N * obs_bytes // 8, 'host_threads_per_rank': host_threads,
+                    'raw_transport': {'value': N * world * ns * K2 / e2e_raw_s, 'ms_per_step': 1e3 * e2e_raw_s / K2,
+                                      'pcie_obs_bytes_per_step': N * obs_bytes}},
+            'gpu_launches': args.steps * world,       # timed region of `value`: one snk_tile_kernel per step per rank
             'clocks': sampler.summary(),
             'rollout_stats': dict(zip(('episodes', 'return_sum', 'episode_steps_sum', 'fruits_sum', 'kills_sum',
                                        'deaths'), stats_host[:6])),

@@ -130,12 +130,33 @@ int snk_reset(snk_env* env, const uint8_t* mask_dev, uint8_t* obs_dev, void* str
 int snk_step(snk_env* env, const uint8_t* actions_dev, uint8_t* obs_dev, double* rewards_dev,
              uint8_t* dones_dev, const snk_step_extra* extra, void* stream);
 
-/* Same call with HOST buffers (the reference's step() takes and returns host objects): copies
- * actions in, steps, copies obs / rewards / dones out and synchronises.  Pinned buffers make the
- * copies asynchronous to the host until the final synchronise.  obs_host may be NULL. */
+/* Same call with HOST buffers (the reference's step() takes and returns host objects,
+ * snake_env.py:414): copies actions in, steps, copies obs / rewards / dones out and synchronises.
+ * Pinned buffers make the copies asynchronous to the host until the final synchronise.  obs_host may
+ * be NULL.  The observation block crosses the PCIe link in one of two ways (same bytes land in
+ * obs_host either way):
+ *   SNK_XFER_RAW     one device-to-host copy of the uint8 NHWC block;
+ *   SNK_XFER_PACKED  the device packs the eight 0/1 channel bytes of every (cell, frame) into one
+ *                    channel-bit byte, the block crosses the link 8x smaller in chunks, and a pool of
+ *                    host threads widens each chunk back to 0/1 bytes while the next ones are in flight.
+ * Default: packed when the block is >= 4 MiB, raw below (environment SNK_HOST_TRANSPORT=raw|packed and
+ * SNK_HOST_THREADS override at create time). */
 int snk_step_host(snk_env* env, const uint8_t* actions_host, uint8_t* obs_host,
                   double* rewards_host, uint8_t* dones_host);
 int snk_reset_host(snk_env* env, uint8_t* obs_host);
+
+enum { SNK_XFER_RAW = 0, SNK_XFER_PACKED = 1 };
+/* threads: widening threads of the packed transport, 0 = one per core this process may run on (<= 32) */
+int snk_set_host_transport(snk_env* env, int mode, int threads);
+int snk_get_host_transport(const snk_env* env, int* mode, int* threads);
+
+/* Channel-bit form of an observation block for callers that keep observations on the device (replay
+ * buffers, 8x smaller): bits_dev[u] bit c = obs_dev[8*u + c], u < n_bytes/8.  obs_dev 16-byte aligned,
+ * bits_dev 4-byte aligned, n_bytes a multiple of 8.  One kernel launch on `stream`. */
+int snk_pack_obs(snk_env* env, const uint8_t* obs_dev, uint8_t* bits_dev, size_t n_bytes, void* stream);
+/* Host inverse (no GPU needed): obs_host[8*u + c] = (bits_host[u] >> c) & 1 -- the 0/1 channel bytes of
+ * _encode (snake_env.py:484-492).  threads <= 1: on the calling thread. */
+int snk_widen_bits_host(const uint8_t* bits_host, uint8_t* obs_host, size_t n_units, int threads);
 
 /* ---- parity / checkpoint interface ---------------------------------------------------------- */
 

@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get('SNK_LIB_PATH') or os.path.join(_HERE, 'libsnk.so')   
 
 SNK_ABI_VERSION = 1
 SNK_RNG_PHILOX, SNK_RNG_REPLAY = 0, 1
+SNK_XFER_RAW, SNK_XFER_PACKED = 0, 1
 DEV_ERRORS = {1: 'action outside {0,1,2}', 2: 'replay stream exhausted',
               4: 'replayed draw out of range / replayed spawn overlaps', 8: 'spawn sampling gave up'}
 STAT_NAMES = ('episodes', 'return_sum', 'episode_steps_sum', 'fruits_sum', 'kills_sum', 'deaths',
@@ -56,6 +57,10 @@ PROTOTYPES = {
                            C.POINTER(SnkStepExtra), C.c_void_p]),
     'snk_step_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'snk_reset_host': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'snk_set_host_transport': (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    'snk_get_host_transport': (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    'snk_pack_obs': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'snk_widen_bits_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     'snk_get_state': (C.c_int, [C.c_void_p, C.POINTER(SnkStateView), C.c_void_p]),
     'snk_set_state': (C.c_int, [C.c_void_p, C.POINTER(SnkStateView), C.c_void_p, C.c_void_p]),
     'snk_set_replay': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -10,9 +10,12 @@
 #include <vector>
 
 #include "../../include/snk.h"
+#include "snk_hostxfer.h"
 #include "snk_kernels.h"
 
 using namespace snk;
+
+enum { XFER_RAW = 0, XFER_PACKED = 1, XFER_MAX_CHUNKS = 64 };
 
 static thread_local char g_err[512] = "";
 
@@ -48,6 +51,12 @@ struct snk_env {
   // device mirrors used by the *_host entry points
   uint8_t* h_actions = nullptr; uint8_t* h_obs = nullptr; double* h_rew = nullptr; uint8_t* h_done = nullptr;
   cudaStream_t own_stream = nullptr;
+  // packed host transport (snk_hostxfer.cpp): device channel-bit mirror, pinned staging, widening pool
+  int xfer_mode = XFER_RAW, xfer_threads = 0;
+  uint8_t* d_bits = nullptr; uint8_t* p_bits = nullptr;
+  WidenPool* pool = nullptr;
+  cudaEvent_t chunk_ev[XFER_MAX_CHUNKS] = {};
+  int n_chunk_ev = 0;
   double env_steps = 0.0;
   int force_generic = 0, coop = 0, lut_dual = 0, use_tma = 0;
   bool was_reset = false;
@@ -159,6 +168,15 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
   CUH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   CUH(cudaDeviceSynchronize());
 #undef CUH
+  {
+    // host entry points: ship channel bits and widen on the host once the observation block is large
+    // enough for the PCIe link to matter (SNK_HOST_TRANSPORT = raw | packed overrides)
+    const char* t = getenv("SNK_HOST_TRANSPORT");
+    const bool big = (size_t)d.N * d.obs_env_bytes >= ((size_t)4 << 20);
+    h->xfer_mode = (t && !strcmp(t, "raw")) ? XFER_RAW : (t && !strcmp(t, "packed")) ? XFER_PACKED
+                   : big ? XFER_PACKED : XFER_RAW;
+    h->xfer_threads = env_int("SNK_HOST_THREADS", 0);
+  }
   *out = h;
   return SNK_OK;
 }
@@ -169,6 +187,10 @@ extern "C" int snk_destroy(snk_env* h) {
   cudaFree(h->recs); cudaFree(h->hist); cudaFree(h->spawn); cudaFree(h->replay); cudaFree(h->replay_off);
   cudaFree(h->err); cudaFree(h->stats); cudaFree(h->enc_blob);
   cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_rew); cudaFree(h->h_done);
+  cudaFree(h->d_bits);
+  if (h->p_bits) cudaFreeHost(h->p_bits);
+  delete h->pool;
+  for (int i = 0; i < h->n_chunk_ev; ++i) cudaEventDestroy(h->chunk_ev[i]);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return SNK_OK;
@@ -237,6 +259,50 @@ static int ensure_mirrors(snk_env* h) {
   return SNK_OK;
 }
 
+// Observation block of the device mirror -> obs_host on stream s.  Raw: one D2H of the NHWC bytes.
+// Packed: pack to channel bits on the device, D2H in chunks, widen each chunk on the host pool as soon as
+// its copy lands while the next chunks are still on the link.  Returns with the host buffer complete.
+static int obs_to_host(snk_env* h, uint8_t* obs_host, cudaStream_t s) {
+  const Dims& d = h->d;
+  const size_t total = (size_t)d.N * d.obs_env_bytes;
+  if (h->xfer_mode == XFER_RAW) {
+    CU(cudaMemcpyAsync(obs_host, h->h_obs, total, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return SNK_OK;
+  }
+  const size_t units = total / 8;
+  if (!h->d_bits) CU(cudaMalloc(&h->d_bits, units));
+  if (!h->p_bits) CU(cudaMallocHost(&h->p_bits, units));
+  if (!h->pool) {
+    h->pool = new (std::nothrow) WidenPool(h->xfer_threads > 0 ? h->xfer_threads : default_host_threads());
+    if (!h->pool) return fail(SNK_E_NOMEM, "out of host memory");
+  }
+  CU(launch_pack_obs(h->h_obs, h->d_bits, units, s));
+  size_t chunk = (size_t)8 << 20;
+  if ((units + chunk - 1) / chunk > XFER_MAX_CHUNKS) chunk = ((units + XFER_MAX_CHUNKS - 1) / XFER_MAX_CHUNKS + 4095) / 4096 * 4096;
+  const int nchunks = (int)((units + chunk - 1) / chunk);
+  while (h->n_chunk_ev < nchunks) {
+    CU(cudaEventCreateWithFlags(&h->chunk_ev[h->n_chunk_ev], cudaEventDisableTiming));
+    ++h->n_chunk_ev;
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    const size_t off = (size_t)c * chunk, len = off + chunk < units ? chunk : units - off;
+    CU(cudaMemcpyAsync(h->p_bits + off, h->d_bits + off, len, cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(h->chunk_ev[c], s));
+  }
+  int rc = SNK_OK;
+  for (int c = 0; c < nchunks; ++c) {
+    const size_t off = (size_t)c * chunk, len = off + chunk < units ? chunk : units - off;
+    cudaError_t e = cudaEventSynchronize(h->chunk_ev[c]);
+    if (e != cudaSuccess) { rc = fail(SNK_E_CUDA, "cudaEventSynchronize failed: %s", cudaGetErrorString(e)); break; }
+    h->pool->submit(h->p_bits + off, obs_host + 8 * off, len);
+  }
+  h->pool->wait();
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(s));
+  return SNK_OK;
+}
+
 extern "C" int snk_step_host(snk_env* h, const uint8_t* actions_host, uint8_t* obs_host,
                              double* rewards_host, uint8_t* dones_host) {
   if (!h) return fail(SNK_E_INVALID, "null handle");
@@ -249,9 +315,9 @@ extern "C" int snk_step_host(snk_env* h, const uint8_t* actions_host, uint8_t* o
   CU(cudaMemcpyAsync(h->h_actions, actions_host, (size_t)d.N * d.ns, cudaMemcpyHostToDevice, s));
   rc = snk_step(h, h->h_actions, obs_host ? h->h_obs : nullptr, h->h_rew, h->h_done, nullptr, s);
   if (rc) return rc;
-  if (obs_host) CU(cudaMemcpyAsync(obs_host, h->h_obs, (size_t)d.N * d.obs_env_bytes, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(rewards_host, h->h_rew, (size_t)d.N * d.ns * sizeof(double), cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(dones_host, h->h_done, (size_t)d.N * d.ns, cudaMemcpyDeviceToHost, s));
+  if (obs_host) return obs_to_host(h, obs_host, s);
   CU(cudaStreamSynchronize(s));
   return SNK_OK;
 }
@@ -264,8 +330,42 @@ extern "C" int snk_reset_host(snk_env* h, uint8_t* obs_host) {
   cudaStream_t s = h->own_stream;
   rc = snk_reset(h, nullptr, obs_host ? h->h_obs : nullptr, s);
   if (rc) return rc;
-  if (obs_host) CU(cudaMemcpyAsync(obs_host, h->h_obs, (size_t)h->d.N * h->d.obs_env_bytes, cudaMemcpyDeviceToHost, s));
+  if (obs_host) return obs_to_host(h, obs_host, s);
   CU(cudaStreamSynchronize(s));
+  return SNK_OK;
+}
+
+extern "C" int snk_set_host_transport(snk_env* h, int mode, int threads) {
+  if (!h) return fail(SNK_E_INVALID, "null handle");
+  if (mode != XFER_RAW && mode != XFER_PACKED) return fail(SNK_E_INVALID, "mode must be SNK_XFER_RAW or SNK_XFER_PACKED");
+  if (threads < 0 || threads > 256) return fail(SNK_E_INVALID, "threads must be in 0..256");
+  h->xfer_mode = mode;
+  if (threads != h->xfer_threads) { delete h->pool; h->pool = nullptr; h->xfer_threads = threads; }
+  return SNK_OK;
+}
+
+extern "C" int snk_get_host_transport(const snk_env* h, int* mode, int* threads) {
+  if (!h) return fail(SNK_E_INVALID, "null handle");
+  if (mode) *mode = h->xfer_mode;
+  if (threads) *threads = h->xfer_threads > 0 ? h->xfer_threads : default_host_threads();
+  return SNK_OK;
+}
+
+extern "C" int snk_pack_obs(snk_env* h, const uint8_t* obs_dev, uint8_t* bits_dev, size_t n_bytes, void* stream) {
+  if (!h || !obs_dev || !bits_dev) return fail(SNK_E_INVALID, "null argument");
+  if (((uintptr_t)obs_dev & 15) || ((uintptr_t)bits_dev & 3) || (n_bytes & 7))
+    return fail(SNK_E_INVALID, "obs must be 16-byte aligned, bits 4-byte aligned, n_bytes a multiple of 8");
+  CU(cudaSetDevice(h->device));
+  CU(launch_pack_obs(obs_dev, bits_dev, n_bytes / 8, (cudaStream_t)stream));
+  return SNK_OK;
+}
+
+extern "C" int snk_widen_bits_host(const uint8_t* bits_host, uint8_t* obs_host, size_t n_units, int threads) {
+  if ((!bits_host || !obs_host) && n_units) return fail(SNK_E_INVALID, "null argument");
+  if (threads <= 1) { widen_bits(bits_host, obs_host, n_units); return SNK_OK; }
+  WidenPool pool(threads);
+  pool.submit(bits_host, obs_host, n_units);
+  pool.wait();
   return SNK_OK;
 }
 

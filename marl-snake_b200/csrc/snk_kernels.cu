@@ -896,6 +896,28 @@ __global__ void snk_set_state_kernel(const Dims d, uint8_t* __restrict__ recs, S
   r.hdr->hpos = 0;
 }
 
+// ---- observation bytes -> channel-bit bytes (packed host transport, device replay buffers) ----------
+// Eight consecutive observation bytes are the 0/1 channels of one (cell, frame); a 32-bit multiply gathers
+// four of them into a nibble (bit c = byte c, no cross-term collisions for 0/1 bytes).
+__device__ __forceinline__ uint32_t pack_unit(uint32_t lo, uint32_t hi) {
+  return ((lo * 0x01020408u) >> 24) | (((hi * 0x01020408u) >> 24) << 4);
+}
+__global__ void __launch_bounds__(256) snk_pack_obs_kernel(const uint8_t* __restrict__ obs, uint8_t* __restrict__ bits,
+                                                           size_t n_units) {
+  const size_t n4 = n_units >> 2;                      // four units (32 input bytes) per thread
+  const uint4* in = reinterpret_cast<const uint4*>(obs);
+  uint32_t* out = reinterpret_cast<uint32_t*>(bits);
+  const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  for (size_t i = t0; i < n4; i += stride) {
+    const uint4 a = __ldcs(in + 2 * i), b = __ldcs(in + 2 * i + 1);
+    out[i] = pack_unit(a.x, a.y) | (pack_unit(a.z, a.w) << 8) | (pack_unit(b.x, b.y) << 16) | (pack_unit(b.z, b.w) << 24);
+  }
+  for (size_t u = (n4 << 2) + t0; u < n_units; u += stride) {
+    const uint2 a = *reinterpret_cast<const uint2*>(obs + 8 * u);
+    bits[u] = (uint8_t)pack_unit(a.x, a.y);
+  }
+}
+
 __global__ void snk_init_records_kernel(const Dims d, uint8_t* __restrict__ recs) {
   const size_t n = (size_t)d.N * d.rec_bytes / 16;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -1015,6 +1037,13 @@ cudaError_t launch_get_state(const Dims& d, const uint8_t* recs, const StateView
 }
 cudaError_t launch_set_state(const Dims& d, uint8_t* recs, const StateView& sv, cudaStream_t s) {
   snk_set_state_kernel<<<(d.N + 127) / 128, 128, 0, s>>>(d, recs, sv);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_obs(const uint8_t* obs, uint8_t* bits, size_t n_units, cudaStream_t s) {
+  if (n_units == 0) return cudaSuccess;
+  const size_t want = ((n_units >> 2) + 255) / 256 + 1;
+  const int grid = (int)(want < 148 * 16 ? want : 148 * 16);        // 16 CTAs of 256 threads per SM, grid-stride
+  snk_pack_obs_kernel<<<grid, 256, 0, s>>>(obs, bits, n_units);
   return cudaGetLastError();
 }
 cudaError_t launch_init_records(const Dims& d, uint8_t* recs, cudaStream_t s) {

@@ -63,6 +63,8 @@ cudaError_t launch_tile_kernel(const KParams& p, int threads, size_t smem_bytes,
 cudaError_t launch_get_state(const Dims& d, const uint8_t* recs, const StateView& sv, cudaStream_t s);
 cudaError_t launch_set_state(const Dims& d, uint8_t* recs, const StateView& sv, cudaStream_t s);
 cudaError_t launch_init_records(const Dims& d, uint8_t* recs, cudaStream_t s);
+// obs: n_units * 8 bytes of 0/1 (16-byte aligned) -> bits: n_units bytes, bit c = byte c of the unit
+cudaError_t launch_pack_obs(const uint8_t* obs, uint8_t* bits, size_t n_units, cudaStream_t s);
 
 // host-side spawn table (snk_spawn.cpp)
 int64_t spawn_enumerate(int H, int W, int K, uint64_t* packed_out, int32_t* cells_out, int64_t cap);

@@ -143,6 +143,29 @@ class SnakeBatch:
         check(lib.snk_reset_host(self._h, C.c_void_p(obs.data_ptr()) if obs is not None else C.c_void_p(0)))
         self._host_reset_done = True
 
+    def set_host_transport(self, mode, threads=0):
+        """How step_host / reset_host move the observation block over PCIe: 'raw' (one D2H of the NHWC
+        bytes) or 'packed' (channel bits on the link, widened by `threads` host threads; 0 = all cores)."""
+        check(lib.snk_set_host_transport(self._h, {'raw': _lib.SNK_XFER_RAW, 'packed': _lib.SNK_XFER_PACKED}[mode],
+                                         int(threads)))
+
+    def host_transport(self):
+        mode, threads = C.c_int(0), C.c_int(0)
+        check(lib.snk_get_host_transport(self._h, C.byref(mode), C.byref(threads)))
+        return ('raw', 'packed')[mode.value], threads.value
+
+    def pack_obs(self, obs=None, out=None):
+        """Channel-bit form of an observation tensor (uint8 0/1, last dim a multiple of 8): one byte per
+        (cell, frame), bit c = channel c.  8x smaller for device replay buffers; `unpack_obs` inverts it."""
+        obs = self._obs if obs is None else obs
+        if obs.dtype != torch.uint8 or not obs.is_cuda or not obs.is_contiguous() or obs.shape[-1] % 8:
+            raise ValueError('obs must be a contiguous uint8 CUDA tensor whose last dimension is a multiple of 8')
+        shape = (*obs.shape[:-1], obs.shape[-1] // 8)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.uint8, device=obs.device)
+        check(lib.snk_pack_obs(self._h, _ptr(obs), _ptr(out), obs.numel(), self._stream()))
+        return out
+
     # ---- parity / checkpoint interface ---------------------------------------------------------------
     def get_state(self, max_cells=None):
         N, ns, dev = self.num_envs, self.num_snakes, self.device

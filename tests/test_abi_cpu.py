@@ -60,6 +60,21 @@ def test_spawn_table_matches_reference_enumeration():
     assert m.lib.snk_spawn_count(64, 64, 5) == 362344          # SURVEY probe for the cfg4 shape
 
 
+@pytest.mark.parametrize('n,threads,misalign', [(0, 1, 0), (1, 1, 0), (7, 1, 0), (121 * 4, 1, 0), (100003, 1, 0),
+                                                 (100003, 4, 0), (1 << 20, 8, 0), (4099, 3, 8), (4099, 1, 3)])
+def test_widen_bits_host_is_little_endian_unpackbits(n, threads, misalign):
+    """Host half of the packed transport: byte u, bit c -> obs byte 8*u + c (channel order of
+    snake_env.py:484-492).  Any size, any thread count, any output alignment."""
+    import marl_snake_b200 as m
+    rng = np.random.RandomState(n + threads)
+    bits = rng.randint(0, 256, size=n).astype(np.uint8)
+    buf = np.full(8 * n + 64 + misalign, 0xAB, dtype=np.uint8)
+    out = buf[misalign:misalign + 8 * n]
+    assert m.lib.snk_widen_bits_host(bits.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), n, threads) == 0
+    assert np.array_equal(out, np.unpackbits(bits, bitorder='little'))
+    assert (buf[:misalign] == 0xAB).all() and (buf[misalign + 8 * n:] == 0xAB).all()      # nothing written outside
+
+
 def test_no_cpu_fallback():
     import torch
     import marl_snake_b200 as m

@@ -369,6 +369,60 @@ def test_gpu_host_buffer_entry_points():
         assert torch.equal(o.cpu(), h_obs) and torch.equal(r.cpu(), h_rew) and torch.equal(d.cpu(), h_done.bool())
 
 
+@pytest.mark.parametrize('kw,N', [
+    (dict(num_snakes=4, vision_range=5), 1237),                       # odd window: 8-byte aligned viewers only
+    (dict(num_snakes=3, vision_range=2, frame_stack=3), 811),
+    (dict(num_snakes=4), 300),                                        # full-grid observation
+    (dict(num_snakes=1, vision_range=3), 5),                          # a few hundred bytes
+])
+def test_gpu_packed_host_transport_equals_raw(kw, N):
+    """snk_step_host / snk_reset_host deliver the same bytes whether the observation block crosses PCIe as
+    NHWC bytes or as channel bits widened by the host pool (any thread count, pageable or pinned)."""
+    from marl_snake_b200 import SnakeBatch
+    ns = kw['num_snakes']
+    raw, packed, dev = SnakeBatch(N, seed=3, **kw), SnakeBatch(N, seed=3, **kw), SnakeBatch(N, seed=3, **kw)
+    raw.set_host_transport('raw')
+    packed.set_host_transport('packed', threads=3)
+    assert raw.host_transport()[0] == 'raw' and packed.host_transport() == ('packed', 3)
+    bufs = []
+    for pin in (True, False):
+        o = torch.empty((N,) + raw.obs_shape, dtype=torch.uint8)
+        r, d = torch.empty((N, ns), dtype=torch.float64), torch.empty((N, ns), dtype=torch.uint8)
+        bufs.append(tuple(t.pin_memory() if pin else t for t in (o, r, d)))
+    (o1, r1, d1), (o2, r2, d2) = bufs
+    raw.reset_host(o1); packed.reset_host(o2)
+    assert torch.equal(o1, o2) and torch.equal(dev.reset().cpu(), o2)
+    g = torch.Generator().manual_seed(11)
+    for t in range(25):
+        if t == 12:
+            packed.set_host_transport('packed', threads=0)            # pool rebuilt with one thread per core
+        act = torch.randint(0, 3, (N, ns), dtype=torch.uint8, generator=g)
+        raw.step_host(act, o1, r1, d1); packed.step_host(act, o2, r2, d2)
+        o, r, d, _ = dev.step(act.cuda())
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2), t
+        assert torch.equal(o.cpu(), o2) and torch.equal(r.cpu(), r2)
+
+
+def test_gpu_pack_obs_roundtrip():
+    """snk_pack_obs (device) and snk_widen_bits_host (host) are inverse; the packed form is np.packbits."""
+    import ctypes as C
+    import marl_snake_b200 as m
+    b = m.SnakeBatch(77, num_snakes=4, vision_range=5, frame_stack=2, seed=8)
+    obs = b.reset()
+    for t in range(5):
+        obs, *_ = b.step(torch.randint(0, 3, (77, 4), dtype=torch.uint8, device='cuda'))
+    bits = b.pack_obs()
+    assert bits.shape == (*obs.shape[:-1], obs.shape[-1] // 8)
+    want = np.packbits(obs.cpu().numpy().reshape(-1, 8), axis=1, bitorder='little').reshape(bits.shape)
+    assert np.array_equal(bits.cpu().numpy(), want)
+    back = np.empty(obs.numel(), dtype=np.uint8)
+    src = np.ascontiguousarray(bits.cpu().numpy())
+    assert m.lib.snk_widen_bits_host(src.ctypes.data_as(C.c_void_p), back.ctypes.data_as(C.c_void_p), src.size, 2) == 0
+    assert np.array_equal(back.reshape(obs.shape), obs.cpu().numpy())
+    with pytest.raises(ValueError):
+        b.pack_obs(obs[..., :4])
+
+
 def test_gpu_state_roundtrip():
     """get_state -> set_state on a second batch reproduces the trajectory (checkpoint / restore)."""
     from marl_snake_b200 import SnakeBatch
