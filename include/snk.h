@@ -15,7 +15,8 @@
  * enqueue work on it and never synchronise.  A handle is not thread-safe.
  *
  * Batched layouts (N = num_envs, ns = num_snakes, oh x ow = observation window):
- *   actions  uint8  [N, ns]             0 keep, 1 turn left, 2 turn right
+ *   actions  uint8  [N, ns]             0 keep, 1 turn left, 2 turn right (observer 'snake');
+ *                                       0 noop, 1 left, 2 right, 3 down, 4 up (observer 'human')
  *   obs      uint8  [N, ns, oh, ow, 8*frame_stack]   NHWC, values 0/1, frames oldest->newest
  *   rewards  double [N, ns]
  *   dones    uint8  [N, ns]
@@ -42,13 +43,15 @@ enum {
 
 /* sticky per-handle device error bits, read with snk_device_errors() */
 enum {
-  SNK_DEV_BAD_ACTION = 1,        /* action outside {0,1,2} (reference: KeyError, snake_env.py:606)   */
+  SNK_DEV_BAD_ACTION = 1,        /* observer 'snake': action outside {0,1,2} (reference: KeyError,
+                                    snake_env.py:606); 'human' ignores unknown actions as the reference does */
   SNK_DEV_REPLAY_UNDERRUN = 2,   /* replay stream exhausted                                         */
   SNK_DEV_REPLAY_RANGE = 4,      /* replayed draw out of range / replayed spawn overlaps            */
   SNK_DEV_SPAWN_GIVEUP = 8       /* no overlap-free spawn found within the attempt cap               */
 };
 
 enum { SNK_RNG_PHILOX = 0, SNK_RNG_REPLAY = 1 };
+enum { SNK_OBSERVER_SNAKE = 0, SNK_OBSERVER_HUMAN = 1 };
 
 /* Constructor arguments of SnakeEnv.__init__ (envs/snake_env.py:58-88) plus batching. */
 typedef struct snk_config {
@@ -66,7 +69,9 @@ typedef struct snk_config {
   int32_t done_mode;          /* 0: all(dones) ends the episode (snake_env.py:416);
                                  1: any(dones) (coop_snake_env.py:14-22)                    */
   int32_t rng_mode;           /* SNK_RNG_PHILOX or SNK_RNG_REPLAY                           */
-  int32_t reserved0;
+  int32_t observer;           /* SNK_OBSERVER_SNAKE: actions 0 keep, 1 left, 2 right relative to the heading
+                                 (_next_direction, snake_env.py:598-608); SNK_OBSERVER_HUMAN: 0 noop, 1 left,
+                                 2 right, 3 down, 4 up in grid terms (_next_direction_global, :610-632)   */
   uint64_t seed;              /* Philox key                                                 */
   uint64_t env_id_offset;     /* global id of env 0: streams are keyed by global env id so a
                                  sharded run equals the single-device run                   */

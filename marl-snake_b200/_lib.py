@@ -24,7 +24,7 @@ class SnkConfig(C.Structure):
                 ('height', C.c_int32), ('width', C.c_int32), ('num_snakes', C.c_int32),
                 ('snake_length', C.c_int32), ('vision_range', C.c_int32), ('frame_stack', C.c_int32),
                 ('num_fruits', C.c_int32), ('auto_reset', C.c_int32), ('done_mode', C.c_int32),
-                ('rng_mode', C.c_int32), ('reserved0', C.c_int32),
+                ('rng_mode', C.c_int32), ('observer', C.c_int32),
                 ('seed', C.c_uint64), ('env_id_offset', C.c_uint64),
                 ('max_episode_steps', C.c_double),
                 ('reward_fruit', C.c_double), ('reward_kill', C.c_double), ('reward_lose', C.c_double),

@@ -93,6 +93,7 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
   if (c->height < 4 || c->width < 4 || (int64_t)c->height * c->width > 65535) return fail(SNK_E_INVALID, "grid must be at least 4x4 and at most 65535 cells");
   if (c->vision_range < 0 || c->frame_stack < 1 || c->frame_stack > 64) return fail(SNK_E_INVALID, "bad vision_range / frame_stack");
   if (c->rng_mode != SNK_RNG_PHILOX && c->rng_mode != SNK_RNG_REPLAY) return fail(SNK_E_INVALID, "bad rng_mode");
+  if (c->observer != SNK_OBSERVER_SNAKE && c->observer != SNK_OBSERVER_HUMAN) return fail(SNK_E_INVALID, "bad observer");
   int nfruits = c->num_fruits < 0 ? (int)nearbyint(c->num_snakes * 0.8) : c->num_fruits;   // snake_env.py:87-88
   if (nfruits > MAX_FRUIT_DRAWS) return fail(SNK_E_INVALID, "num_fruits must be <= %d", MAX_FRUIT_DRAWS);
 
@@ -103,6 +104,7 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
   d.N = c->num_envs; d.H = c->height; d.W = c->width; d.ns = c->num_snakes; d.K = c->snake_length;
   d.V = c->vision_range; d.fs = c->frame_stack; d.nfruits = nfruits;
   d.auto_reset = c->auto_reset ? 1 : 0; d.done_mode = c->done_mode ? 1 : 0; d.rng_mode = c->rng_mode;
+  d.observer = c->observer;
   d.seed_lo = (uint32_t)c->seed; d.seed_hi = (uint32_t)(c->seed >> 32);
   d.env_off_lo = (uint32_t)c->env_id_offset; d.env_off_hi = (uint32_t)(c->env_id_offset >> 32);
   d.r_fruit = c->reward_fruit; d.r_kill = c->reward_kill; d.r_lose = c->reward_lose;
@@ -121,18 +123,29 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
   // tile shape: a tile is 32/G environments (G = num_snakes rounded up to a power of two).  Large
   // batches: every warp owns a tile, the CTA's warps share only the encode tables.  Small batches or
   // large records: the CTA owns one tile and its warps share the tile's viewers (coop).
-  const int EPW = 32 / tile_group(d.ns);
-  const int64_t tiles = ((int64_t)d.N + EPW - 1) / EPW;
+  const int EPW_full = 32 / tile_group(d.ns);
+  const int64_t tiles_full = ((int64_t)d.N + EPW_full - 1) / EPW_full;
   int coop = env_int("SNK_COOP", -1);
-  if (coop < 0) coop = (tiles < 148 * 24 || (size_t)EPW * d.rec_bytes > 8 * 1024 || d.fs > 1) ? 1 : 0;   // measured: profiles/README.md
+  if (coop < 0) coop = (tiles_full < 148 * 24 || (size_t)EPW_full * d.rec_bytes > 8 * 1024 || d.fs > 1) ? 1 : 0;   // measured: profiles/README.md
+  // coop tiles may hold fewer environments than the rule warp has lane groups: a small batch then spreads
+  // over more CTAs and each CTA's encode (the latency that bounds a one-wave launch) gets shorter
+  int EPW = env_int("SNK_TILE_ENVS", 0);
+  if (EPW <= 0) {
+    EPW = EPW_full;
+    if (coop) while (EPW > 1 && ((int64_t)d.N + EPW - 1) / EPW < 148 * 8) EPW >>= 1;
+  }
+  if (EPW > EPW_full || (EPW & (EPW - 1)) || (!coop && EPW != EPW_full)) {
+    delete h;
+    return fail(SNK_E_INVALID, "SNK_TILE_ENVS must be a power of two <= %d (and exactly that in warp-private mode)", EPW_full);
+  }
   int threads = env_int("SNK_THREADS", coop ? 128 : 32);
   const int max_threads = coop ? SNK_MAX_THREADS_COOP : SNK_MAX_THREADS;
   if (threads < 32 || threads > max_threads || (threads & 31)) { delete h; return fail(SNK_E_INVALID, "SNK_THREADS must be a multiple of 32 in 32..%d", max_threads); }
-  while (threads > 32 && tile_smem_bytes(d, threads / 32, coop != 0) > 200 * 1024) threads -= 32;
+  while (threads > 32 && tile_smem_bytes(d, threads / 32, coop != 0, EPW) > 200 * 1024) threads -= 32;
   h->tile_envs = EPW; h->threads = threads; h->coop = coop;
   h->force_generic = env_int("SNK_FORCE_GENERIC", 0);
   h->use_tma = env_int("SNK_TMA", 1);
-  h->smem_bytes = tile_smem_bytes(d, threads / 32, coop != 0);
+  h->smem_bytes = tile_smem_bytes(d, threads / 32, coop != 0, EPW);
   if (h->smem_bytes > 227 * 1024) {
     const size_t need = h->smem_bytes;
     delete h;

@@ -50,6 +50,7 @@ struct Dims {
   int32_t oh, ow, ohw;            // observation window
   int32_t ohw_p;                  // history row stride (ohw rounded up to 16)
   int32_t auto_reset, done_mode, rng_mode;
+  int32_t observer;               // 0 'snake': three relative actions; 1 'human': five absolute actions
   // record layout (bytes from record start; grid is at 0)
   int32_t off_dirp, off_snk, off_hdr, off_stats, rec_bytes;
   int32_t hist_env_bytes;         // ns*fs*ohw_p, 0 when fs == 1
@@ -120,6 +121,16 @@ SNK_HD void dirp_set(uint8_t* dirp, int c, int v) {
   dirp[c >> 2] = (uint8_t)((dirp[c >> 2] & ~(3 << sh)) | (v << sh));
 }
 SNK_HD int dir_delta(int dir, int W) { return dir == 0 ? -W : dir == 1 ? 1 : dir == 2 ? W : -1; }
+
+// observer='snake': 0 keep, 1 turn left, 2 turn right (the exact table of the reference's trigonometric
+// _next_direction, snake_env.py:598-608; a > 2 is the reference's KeyError, reported by the caller).
+SNK_HD int turn_relative(int dir, uint32_t a) { return (dir + (a == 1u ? 3 : a == 2u ? 1 : 0)) & 3; }
+// observer='human': 0 noop, 1 left, 2 right, 3 down, 4 up; a horizontal mover may only turn down/up, a
+// vertical one only left/right, anything else keeps the direction      snake_env.py:610-632
+SNK_HD int turn_absolute(int dir, uint32_t a) {
+  if (dir & 1) return a == 3u ? 2 : a == 4u ? 0 : dir;     // RIGHT / LEFT
+  return a == 1u ? 3 : a == 2u ? 1 : dir;                  // UP / DOWN
+}
 
 // ---- Philox4x32-10 counter-based stream ----------------------------------------------------------
 // word(seed; env, event, purpose, idx): counter = {env_lo, env_hi ^ 'SNK1', event, purpose<<24 | idx/4},
@@ -203,8 +214,8 @@ SNK_HD StepResult env_step_logic(const Dims& d, uint8_t* rec_base, uint8_t* scr,
     st[i] = 0; kl[i] = 0; tgt[i] = 0xFFFF;
     if (r.alive[i]) {
       uint32_t a = act[i];
-      if (a > 2u) { *err_bits |= ERR_BAD_ACTION; a = 0; }
-      const int nd = (r.dir[i] + (a == 1u ? 3 : a == 2u ? 1 : 0)) & 3;
+      if (a > 2u && !d.observer) { *err_bits |= ERR_BAD_ACTION; a = 0; }
+      const int nd = d.observer ? turn_absolute(r.dir[i], a) : turn_relative(r.dir[i], a);
       r.dir[i] = (uint8_t)nd;
       tgt[i] = (uint16_t)(r.head[i] + dir_delta(nd, W));
       st[i] = ST_WAS_ALIVE;

@@ -252,8 +252,8 @@ __device__ __forceinline__ GroupOut step_group(const KParams& p, const SH& sh, R
   uint32_t tgt = 0x10000u + lane;                       // unique dummy: never matches a real cell
   if (was_alive) {
     uint32_t a = action;                                  // fetched while the record tile was in flight
-    if (a > 2u) { atomicOr(p.err, ERR_BAD_ACTION); a = 0; }
-    dirv = (r.dir[i] + (a == 1u ? 3 : a == 2u ? 1 : 0)) & 3;
+    if (a > 2u && !d.observer) { atomicOr(p.err, ERR_BAD_ACTION); a = 0; }
+    dirv = d.observer ? turn_absolute(r.dir[i], a) : turn_relative(r.dir[i], a);            // :598-632
     tgt = (uint32_t)(r.head[i] + dir_delta(dirv, W));
   }
   // 2. one verdict per distinct target cell, on the pre-move grid                      :521-544
@@ -704,7 +704,7 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, nwarps = nt >> 5;
   const uint32_t lane = lane_id();
-  const int ns = sh.ns(), G = sh.group(), EPW = 32 / G;          // environments per tile
+  const int ns = sh.ns(), G = sh.group(), EPW = p.E;             // environments per tile (<= 32 / G)
   const int fs = sh.fs(), ohw = sh.ohw();
   const int tile = kCoop ? (int)blockIdx.x : (int)blockIdx.x * nwarps + warp;
   const int e0 = tile * EPW;
@@ -986,8 +986,7 @@ void encode_blob_fill(const Dims& d, uint8_t* out) {
 }
 
 // Shared memory of one CTA of `warps` warps (must mirror the carve-up in snk_tile_kernel).
-size_t tile_smem_bytes(const Dims& d, int warps, bool coop) {
-  const int EPW = 32 / tile_group(d.ns);
+size_t tile_smem_bytes(const Dims& d, int warps, bool coop, int EPW) {
   const size_t ntiles = coop ? 1 : (size_t)warps;
   size_t b = ntiles * (size_t)EPW * d.rec_bytes;
   if (d.fs > 1) b += (size_t)warps * (size_t)round_up(d.stage_env_bytes, 16);
@@ -1004,7 +1003,7 @@ static cudaError_t launch_instance(const KParams& p, int threads, size_t smem_by
     if (e != cudaSuccess) return e;
     configured = smem_bytes;
   }
-  const int envs_per_cta = (kCoop ? 1 : threads / 32) * (32 / tile_group(p.d.ns));
+  const int envs_per_cta = (kCoop ? 1 : threads / 32) * p.E;
   const int grid = (p.d.N + envs_per_cta - 1) / envs_per_cta;
   kern<<<grid, threads, smem_bytes, stream>>>(p);
   return cudaGetLastError();

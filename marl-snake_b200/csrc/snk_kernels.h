@@ -36,7 +36,7 @@ struct KParams {
   int32_t* ep_kills;
   const uint8_t* mask;
   int32_t mode;
-  int32_t E;                   // environments per warp tile (32 / group size), informational
+  int32_t E;                   // environments per tile: 32 / group size, or fewer (a power of two) in coop mode
   int32_t vec16;               // 128-bit observation stores are legal for every tile (fs > 1 path)
   int32_t force_generic;       // run the unspecialised kernel instance (tests)
   const uint8_t* enc_blob;     // fs == 1: host-built encode tables (see encode_blob_fill)
@@ -54,7 +54,7 @@ struct StateView {
 };
 
 int tile_group(int ns);
-size_t tile_smem_bytes(const Dims& d, int warps, bool coop);
+size_t tile_smem_bytes(const Dims& d, int warps, bool coop, int tile_envs);
 bool encode_lut_dual(const Dims& d);
 bool encode_uses_table(const Dims& d);
 size_t encode_blob_bytes(const Dims& d, size_t* tab_off);

@@ -19,6 +19,7 @@ from .spaces import Box, Discrete
 
 DEFAULT_REWARD_DICT = {'fruit': 10.0, 'kill': 0.0, 'lose': -0.5, 'win': 0.0, 'time': -0.001}   # snake_env.py:46-52
 ACTION_ANGLE_DICT = {0: 0.0, 1: np.pi / 2.0, 2: -np.pi / 2.0}                                   # snake_env.py:40-44
+DEFAULT_ACTION_DICT = {'noop': 0, 'left': 1, 'right': 2, 'down': 3, 'up': 4}                    # snake_env.py:32-38
 DEFAULT_MAX_EPISODE_STEPS = 1e4                                                                 # snake_env.py:56
 
 
@@ -36,8 +37,10 @@ class SnakeBatch:
         reward_dict = DEFAULT_REWARD_DICT if reward_dict is None else reward_dict
         if reward_dict.keys() != DEFAULT_REWARD_DICT.keys():                      # snake_env.py:77-80
             raise KeyError(f'reward dict keys must correspond to {DEFAULT_REWARD_DICT.keys()}')
-        if observer != 'snake':
-            raise NotImplementedError("only observer='snake' (three relative actions) is implemented")
+        if observer not in ('snake', 'human'):
+            raise ValueError("observer must be 'snake' (three relative actions) or 'human' (five absolute)")
+        self.observer = observer
+        self.action_dict = ACTION_ANGLE_DICT if observer == 'snake' else DEFAULT_ACTION_DICT   # snake_env.py:101-104
         if rng not in ('philox', 'replay'):
             raise ValueError("rng must be 'philox' or 'replay'")
         if not torch.cuda.is_available():
@@ -60,6 +63,7 @@ class SnakeBatch:
                         num_fruits=self.num_fruits, auto_reset=int(self.auto_reset),
                         done_mode={'all': 0, 'any': 1}[done_mode],
                         rng_mode=_lib.SNK_RNG_REPLAY if rng == 'replay' else _lib.SNK_RNG_PHILOX,
+                        observer=1 if observer == 'human' else 0,
                         seed=int(seed), env_id_offset=int(env_id_offset),
                         max_episode_steps=float(max_episode_steps),
                         reward_fruit=float(reward_dict['fruit']), reward_kill=float(reward_dict['kill']),
@@ -86,7 +90,7 @@ class SnakeBatch:
                                    self._ep_steps.data_ptr(), self._ep_fruits.data_ptr(),
                                    self._ep_kills.data_ptr())
         self.observation_space = Box(0, 1, (N,) + self.obs_shape, np.uint8)
-        self.action_space = Discrete(3)
+        self.action_space = Discrete(len(self.action_dict))
 
     # ---- lifecycle ---------------------------------------------------------------------------------
     def close(self):
@@ -112,7 +116,7 @@ class SnakeBatch:
         return self._obs.clone() if copy else self._obs
 
     def step(self, actions, copy=False, want_obs=True, want_info=True):
-        """actions: uint8 CUDA tensor [N, ns] in {0,1,2}.  Returns (obs, rewards f64, dones bool, info)
+        """actions: uint8 CUDA tensor [N, ns] in {0,1,2} (observer 'snake') or {0..4} ('human').  Returns (obs, rewards f64, dones bool, info)
         where info holds per-env `finished` and, for finished envs, the terminal `rank` / `episode_*`
         arrays the reference puts in its info dict (snake_env.py:396-410).  The returned tensors are
         the batch's own buffers, overwritten by the next call unless copy=True."""
@@ -263,6 +267,7 @@ class SnakeEnv:
     an alias of `reward_dict` (README spelling)."""
 
     default_reward_dict = DEFAULT_REWARD_DICT
+    default_action_dict = DEFAULT_ACTION_DICT
     action_angle_dict = ACTION_ANGLE_DICT
     reward_keys = DEFAULT_REWARD_DICT.keys()
     metadata = {}
@@ -287,7 +292,7 @@ class SnakeEnv:
         self.grid_shape, self.snake_length = b.grid_shape, b.snake_length
         self.vision_range, self.frame_stack, self.observer = vision_range, b.frame_stack, observer
         self.low, self.high, self.image_obs = 0, 1, False
-        self.action_dict = ACTION_ANGLE_DICT
+        self.action_dict = b.action_dict
         self.obs_ch = b.obs_ch
         self.action_space = Discrete(len(self.action_dict) * self.num_snakes)             # snake_env.py:107-109
         self.observation_space = Box(self.low, self.high, b.obs_shape, np.uint8)          # snake_env.py:115-129
@@ -317,6 +322,9 @@ class SnakeEnv:
         for i, ac in enumerate(actions):
             if isinstance(ac, np.ndarray):
                 ac = ac.item()
+            if self.observer == 'human':              # unknown actions keep the direction (:610-632)
+                acts.append(int(ac) if ac in (0, 1, 2, 3, 4) else 0)
+                continue
             if self._alive[i] and ac not in self.action_dict:
                 raise KeyError(ac)                                                        # snake_env.py:606
             acts.append(int(ac) if ac in self.action_dict else 0)

@@ -117,12 +117,12 @@ class VectorSnakeEnv:
         self.batch = SnakeBatch(num_envs, num_snakes=num_snakes, auto_reset=True, **kwargs)
         self.num_envs, self.num_snakes, self.output = num_envs, num_snakes, output
         b = self.batch
-        self.action_dict = ACTION_ANGLE_DICT
+        self.action_dict = b.action_dict
         self.vision_range, self.obs_ch, self.grid_shape = b.vision_range, b.obs_ch, b.grid_shape
         single = b.obs_shape if num_snakes > 1 else b.obs_shape[1:]
         self.single_observation_space = Box(0, 255, single, np.uint8)
         self.observation_space = Box(0, 255, (num_envs, *single), np.uint8)
-        self.single_action_space = self.action_space = Discrete(3)
+        self.single_action_space = self.action_space = Discrete(len(self.action_dict))
         self._act = torch.zeros((num_envs, num_snakes), dtype=torch.uint8, device=b.device)
 
     def _squeeze(self, x):

@@ -150,6 +150,25 @@ class ReplayDraws:
         return ranks
 
 
+def next_direction_global(direction, action):
+    """observer='human': absolute actions 0 noop, 1 left, 2 right, 3 down, 4 up.  A snake moving
+    horizontally may only turn down/up, one moving vertically only left/right; anything else (including
+    values outside 0..4) keeps the direction -- no KeyError on this path.  snake_env.py:610-632."""
+    UP, RIGHT, DOWN, LEFT = 0, 1, 2, 3
+    dr, dc = DELTA[direction]
+    if dr == 0:                       # the reference's `direction.value[0] == 0`: moving left or right
+        if action == 3:
+            return DOWN
+        if action == 4:
+            return UP
+    elif dc == 0:
+        if action == 1:
+            return LEFT
+        if action == 2:
+            return RIGHT
+    return direction
+
+
 # --------------------------------------------------------------------------- the env
 class OracleSnakeEnv:
     """One Snake-v1 environment; same ctor kwargs / reset / step contract as SnakeEnv."""
@@ -159,8 +178,9 @@ class OracleSnakeEnv:
         reward_dict = kwargs.pop('reward_dict', DEFAULT_REWARD)
         if reward_dict.keys() != REWARD_KEYS:                              # snake_env.py:76-80
             raise KeyError(f'reward dict keys must correspond to {REWARD_KEYS}')
-        if observer != 'snake':
-            raise ValueError("oracle covers observer='snake' only")
+        if observer not in ('snake', 'human'):
+            raise ValueError("observer must be 'snake' (three relative actions) or 'human' (five absolute)")
+        self.observer = observer
         self.reward_dict = reward_dict
         self.max_episode_steps = kwargs.pop('max_episode_steps', DEFAULT_MAX_EPISODE_STEPS)
         self.num_snakes = num_snakes
@@ -239,7 +259,10 @@ class OracleSnakeEnv:
         arrivals = {}
         for i in range(ns):
             if was_alive[i]:
-                self.dir[i] = TURN[self.dir[i]][{0: 0, 1: 1, 2: 2}[actions[i]]]   # KeyError like the ref
+                if self.observer == 'human':
+                    self.dir[i] = next_direction_global(self.dir[i], actions[i])
+                else:
+                    self.dir[i] = TURN[self.dir[i]][{0: 0, 1: 1, 2: 2}[actions[i]]]   # KeyError like the ref
                 hr, hc = self.body[i][0]
                 dr, dc = DELTA[self.dir[i]]
                 arrivals.setdefault((hr + dr, hc + dc), []).append(i)

@@ -95,9 +95,15 @@ def snake_cells(env, W):
     return alive, dirs, np.array(lens, dtype=np.int32), cells
 
 
+ONLY = set(sys.argv[1:])          # `make_golden.py roll_human ...` regenerates just the named fixtures
+
+
 def rollout(name, seed, num_envs, steps, env_id='Snake-v1', **kw):
     """Seeded random rollout of `num_envs` independent reference envs with auto-reset."""
+    if ONLY and name not in ONLY:
+        return
     ns = kw.get('num_snakes', 4)
+    n_actions = 5 if kw.get('observer') == 'human' else 3
     rec = dict(kind='rollout', kwargs=repr(kw), seed=seed)
     per_env = []
     act_rng = np.random.RandomState(seed + 777)
@@ -115,7 +121,7 @@ def rollout(name, seed, num_envs, steps, env_id='Snake-v1', **kw):
             info_step, info_rank, info_scores, info_steps, info_fruits, info_kills = [], [], [], [], [], []
             reset_grid = [env.grid.astype(np.uint8).copy()]
             for t in range(steps):
-                a = act_rng.randint(0, 3, size=ns)
+                a = act_rng.randint(0, n_actions, size=ns)
                 obs, rew, done, info = env.step([int(x) for x in a])
                 grid_after_step = env.grid.astype(np.uint8).copy()
                 counter = env.alive_snakes
@@ -311,7 +317,19 @@ def eat_and_grow_crop_stack():
                 actions=[[0, 0], [0, 0], [2, 1], [0, 0], [2, 2]])
 
 
+@scenario
+def human_absolute_actions():
+    # observer='human' (:610-632): 0 heads RIGHT, 1 heads UP.  Step 1: 'up' turns 0; 1 is already vertical
+    # and ignores it.  Step 2: 'left' turns 0, 'right' turns 1.  Step 3: 0 moves horizontally and ignores
+    # 'left', 'down' turns 1.  Step 4: the unknown action 7 is a no-op (no KeyError) and 0 runs into the wall.
+    return dict(H=9, W=9, snakes=[[(5, 3), (5, 2), (5, 1)], [(5, 6), (6, 6), (7, 6)]],
+                kw=dict(observer='human', vision_range=2),
+                actions=[[4, 4], [1, 2], [1, 3], [7, 0]])
+
+
 def run_scenarios():
+    if ONLY and 'scenarios' not in ONLY:
+        return
     out = {}
     names = []
     for fn in SCENARIOS:
@@ -360,6 +378,8 @@ def run_scenarios():
 
 
 def spawn_tables():
+    if ONLY and 'spawn_tables' not in ONLY:
+        return
     out = {}
     for (H, W, k) in [(20, 20, 3), (8, 8, 2), (10, 14, 4), (12, 12, 5), (7, 9, 6)]:
         grid = make_grid(H, W, empty_value=0, wall_value=1)
@@ -395,3 +415,5 @@ if __name__ == '__main__':
             vision_range=3, frame_stack=2, reward_dict=cfg4_rew)
     rollout('roll_crowd', 800, 4, 100, height=9, width=9, num_snakes=5, snake_length=3,
             vision_range=2, num_fruits=6, reward_dict=cfg4_rew)
+    rollout('roll_human', 1000, 4, 150, height=12, width=12, num_snakes=3, snake_length=3,
+            vision_range=4, observer='human', reward_dict=cfg4_rew)

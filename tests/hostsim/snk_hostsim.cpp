@@ -145,7 +145,7 @@ void* hs_create(const snk_config* c) {
   d.N = c->num_envs; d.H = c->height; d.W = c->width; d.ns = c->num_snakes; d.K = c->snake_length;
   d.V = c->vision_range; d.fs = c->frame_stack;
   d.nfruits = c->num_fruits < 0 ? (int)(c->num_snakes * 0.8 + 0.5) : c->num_fruits;
-  d.auto_reset = c->auto_reset; d.done_mode = c->done_mode; d.rng_mode = c->rng_mode;
+  d.auto_reset = c->auto_reset; d.done_mode = c->done_mode; d.rng_mode = c->rng_mode; d.observer = c->observer;
   d.seed_lo = (uint32_t)c->seed; d.seed_hi = (uint32_t)(c->seed >> 32);
   d.env_off_lo = (uint32_t)c->env_id_offset; d.env_off_hi = (uint32_t)(c->env_id_offset >> 32);
   d.r_fruit = c->reward_fruit; d.r_kill = c->reward_kill; d.r_lose = c->reward_lose;

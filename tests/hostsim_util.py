@@ -28,7 +28,8 @@ def make_config(num_envs, kw, rng_mode=1, auto_reset=1, seed=0, env_id_offset=0,
                      width=kw.get('width', 20), num_snakes=ns, snake_length=kw.get('snake_length', 3),
                      vision_range=int(kw.get('vision_range') or 0), frame_stack=kw.get('frame_stack', 1),
                      num_fruits=kw.get('num_fruits', int(round(ns * 0.8))), auto_reset=auto_reset,
-                     done_mode=done_mode, rng_mode=rng_mode, seed=seed, env_id_offset=env_id_offset,
+                     done_mode=done_mode, rng_mode=rng_mode, observer=int(kw.get('observer', 'snake') == 'human'),
+                     seed=seed, env_id_offset=env_id_offset,
                      max_episode_steps=float(kw.get('max_episode_steps', 1e4)),
                      reward_fruit=rd['fruit'], reward_kill=rd['kill'], reward_lose=rd['lose'],
                      reward_win=rd['win'], reward_time=rd['time'])

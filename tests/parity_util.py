@@ -73,8 +73,9 @@ def check_against_oracle_philox(backend_factory, kw, num_envs, steps, seed, env_
     obs = backend.reset()
     assert np.array_equal(obs, ref_obs), 'reset obs'
     rng = np.random.RandomState(action_seed)
+    n_actions = 5 if kw.get('observer') == 'human' else 3
     for t in range(steps):
-        acts = rng.randint(0, 3, size=(num_envs, ns)).astype(np.uint8)
+        acts = rng.randint(0, n_actions, size=(num_envs, ns)).astype(np.uint8)
         obs, rew, done, info = backend.step(acts)
         for e, env in enumerate(envs):
             draws[e].tick()

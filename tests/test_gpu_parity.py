@@ -39,6 +39,7 @@ def test_gpu_scenarios(sc):
     (dict(height=16, width=16, num_snakes=7, snake_length=4, vision_range=7,
           reward_dict={'fruit': 10.0, 'kill': 1.0, 'lose': -1.0, 'win': 0.1, 'time': -0.001}), 9, 80),
     (dict(height=10, width=10, num_snakes=1, snake_length=3, num_fruits=4), 21, 100),
+    (dict(height=14, width=11, num_snakes=4, snake_length=3, vision_range=3, observer='human'), 37, 120),
 ])
 def test_gpu_philox_matches_oracle(kw, num_envs, steps):
     be = check_against_oracle_philox(GpuBackend, kw, num_envs=num_envs, steps=steps, seed=0xC0FFEE1234,
@@ -152,6 +153,25 @@ def test_dropin_api():
     assert o.shape == (16, 4, 11, 11, 8)
     o, r, d, infos = venv.step(np.zeros((16, 4), dtype=np.int64))
     assert r.shape == (16, 4) and d.shape == (16, 4) and len(infos) == 16
+
+
+def test_dropin_human_observer():
+    """observer='human': five absolute actions, Discrete(5*ns) on the env, Discrete(5) behind the wrapper
+    (snake_env.py:101-109, wrappers.py:111), unknown actions are no-ops instead of KeyError (:610-632)."""
+    from marl_snake_b200 import make, make_snake
+    raw = make('Snake-v1', num_snakes=2, observer='human', vision_range=3, seed=4)
+    assert raw.action_space.n == 10 and raw.action_dict == {'noop': 0, 'left': 1, 'right': 2, 'down': 3, 'up': 4}
+    raw.reset()
+    raw.step([9, 4])                                                  # no KeyError on this path
+    env, _, _, props = make_snake(num_envs=1, num_snakes=2, observer='human', vision_range=3)
+    assert props['action_info'] == {'action_n': 5} and env.action_space.n == 5
+    venv, _, _, props = make_snake(num_envs=8, num_snakes=2, observer='human', vision_range=3)
+    assert props['action_info'] == {'action_n': 5}
+    venv.reset()
+    o, r, d, _ = venv.step(np.full((8, 2), 4))
+    assert o.shape == (8, 2, 7, 7, 8)
+    with pytest.raises(ValueError):
+        make('Snake-v1', observer='bird')
 
 
 def test_gpu_generic_kernel_instance(monkeypatch):

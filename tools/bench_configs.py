@@ -70,7 +70,9 @@ def run(name, kw, steps, graph=False):
     gbs = bpe * N * steps / (ms * 1e-3) / 1e9
     out = dict(config=name, graph=graph, num_envs=N, steps=steps, ms_per_step=ms / steps,
                agent_steps_per_sec=N * ns * steps / (ms * 1e-3), bytes_per_agent_step=bpe / ns,
-               achieved_gbs=gbs, frac_of_measured_peak=gbs / peak, device_errors=b.device_errors())
+               achieved_gbs=gbs, frac_of_measured_peak=gbs / peak, device_errors=b.device_errors(),
+               tile_envs=os.environ.get('SNK_TILE_ENVS', 'auto'), threads=os.environ.get('SNK_THREADS', 'auto'),
+               coop=os.environ.get('SNK_COOP', 'auto'))
     print(json.dumps(out), flush=True)
     b.close()
 
