@@ -58,7 +58,7 @@ struct snk_env {
   cudaEvent_t chunk_ev[XFER_MAX_CHUNKS] = {};
   int n_chunk_ev = 0;
   double env_steps = 0.0;
-  int force_generic = 0, coop = 0, lut_dual = 0, use_tma = 0;
+  int force_generic = 0, coop = 0, lut_dual = 0, use_tma = 0, enc_flavour = 0;
   bool was_reset = false;
 };
 
@@ -81,6 +81,10 @@ static KParams base_params(const snk_env* h) {
   p.force_generic = h->force_generic;
   p.enc_blob = h->enc_blob; p.enc_blob_bytes = h->enc_blob_bytes; p.enc_tab_off = h->enc_tab_off; p.use_tab = h->use_tab;
   p.lut_dual = h->lut_dual; p.coop = h->coop; p.use_tma = h->use_tma;
+  p.enc_flavour = h->enc_flavour;
+  p.enc_copy_bytes = (h->enc_flavour == ENC_LEGACY) ? h->enc_blob_bytes : h->enc_tab_off;     // LUT only
+  p.view_bits = h->d.oh + h->d.ow;
+  p.view_bias = h->d.V * h->d.W + h->d.V;
   return p;
 }
 
@@ -125,20 +129,27 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
   // large records: the CTA owns one tile and its warps share the tile's viewers (coop).
   const int EPW_full = 32 / tile_group(d.ns);
   const int64_t tiles_full = ((int64_t)d.N + EPW_full - 1) / EPW_full;
+  // Measured on the B200 (profiles/README.md, tools/sweep_tiles*.sh): warp-private tiles win once the batch
+  // is several waves deep; below that, and for large records or frame stacks, the CTA-cooperative mode does.
   int coop = env_int("SNK_COOP", -1);
-  if (coop < 0) coop = (tiles_full < 148 * 24 || (size_t)EPW_full * d.rec_bytes > 8 * 1024 || d.fs > 1) ? 1 : 0;   // measured: profiles/README.md
-  // coop tiles may hold fewer environments than the rule warp has lane groups: a small batch then spreads
-  // over more CTAs and each CTA's encode (the latency that bounds a one-wave launch) gets shorter
+  if (coop < 0) coop = (tiles_full < 148 * 192 || (size_t)EPW_full * d.rec_bytes > 8 * 1024 || d.fs > 1) ? 1 : 0;
+  // A coop tile may hold fewer environments than the rule warp has lane groups: shorter per-CTA latency
+  // (the rule phase of one warp, then the tile's encode) and more rule warps in flight.  Shrink until a
+  // tile's observation block is <= 32 KB, and further while the launch would not fill every SM 16 times.
   int EPW = env_int("SNK_TILE_ENVS", 0);
   if (EPW <= 0) {
     EPW = EPW_full;
-    if (coop) while (EPW > 1 && ((int64_t)d.N + EPW - 1) / EPW < 148 * 8) EPW >>= 1;
+    if (coop) {
+      while (EPW > 1 && (size_t)EPW * d.obs_env_bytes > 32 * 1024) EPW >>= 1;
+      while (EPW > 1 && ((int64_t)d.N + EPW - 1) / EPW < 148 * 16) EPW >>= 1;
+    }
   }
-  if (EPW > EPW_full || (EPW & (EPW - 1)) || (!coop && EPW != EPW_full)) {
+  if (EPW > EPW_full || (EPW & (EPW - 1))) {
     delete h;
-    return fail(SNK_E_INVALID, "SNK_TILE_ENVS must be a power of two <= %d (and exactly that in warp-private mode)", EPW_full);
+    return fail(SNK_E_INVALID, "SNK_TILE_ENVS must be a power of two <= %d", EPW_full);
   }
-  int threads = env_int("SNK_THREADS", coop ? 128 : 32);
+  // frame_stack > 1 encodes one environment per warp, so more warps than environments would idle
+  int threads = env_int("SNK_THREADS", !coop ? 32 : d.fs > 1 ? 32 * (EPW < 8 ? EPW : 8) : 128);
   const int max_threads = coop ? SNK_MAX_THREADS_COOP : SNK_MAX_THREADS;
   if (threads < 32 || threads > max_threads || (threads & 31)) { delete h; return fail(SNK_E_INVALID, "SNK_THREADS must be a multiple of 32 in 32..%d", max_threads); }
   while (threads > 32 && tile_smem_bytes(d, threads / 32, coop != 0, EPW) > 200 * 1024) threads -= 32;
@@ -172,6 +183,7 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
     h->enc_blob_bytes = (int)nb; h->enc_tab_off = (int)tab_off;
     h->lut_dual = encode_lut_dual(d) ? 1 : 0;
     h->use_tab = encode_uses_table(d) && (h->lut_dual || !env_int("SNK_NO_TABLE", 0)) ? 1 : 0;
+    h->enc_flavour = env_int("SNK_ENC_LEGACY", 0) ? ENC_LEGACY : encode_flavour(d);
   }
   CUH(cudaMemset(h->err, 0, sizeof(uint32_t)));
   CUH(cudaMemset(h->stats, 0, STAT_COUNT * sizeof(double)));

@@ -551,6 +551,109 @@ __device__ __forceinline__ void encode_viewer_fs1(const KParams& p, const SH& sh
   }
 }
 
+// ---- ENC_REG / ENC_DIRECT ------------------------------------------------------------------------
+// Packed words (B = view_bits = oh + ow):
+//   cell word    bits [0,oh) one-hot window row | bits [oh,B) one-hot window column | grid offset << B;
+//                bit 31 set for a cell outside the viewer block (half units at the block ends)
+//   viewer word  bits [0,B) rows / columns of the window that fall OUTSIDE the grid | (origin + bias) << B
+// A window cell reads the grid iff (cell & (viewer | 1<<31)) has no bit in [0,B) or bit 31; otherwise it
+// reads LUT entry 0 (all zero), the reference's zero padding (snake_env.py:506-515).
+struct CellWords { uint32_t w[2][4]; };     // [address parity of the viewer block][unit 0 cell a, b, unit 1 cell a, b]
+
+template <class SH>
+__device__ __forceinline__ CellWords make_cell_words(const SH& sh, int B) {
+  const int lane = (int)lane_id(), ohw = sh.ohw(), ow = sh.ow(), oh = sh.oh(), W = sh.W();
+  CellWords cw;
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = 2 * (lane + 32 * (k >> 1)) - s + (k & 1);
+      uint32_t w = 0x80000000u;
+      if (c >= 0 && c < ohw) {
+        const int ci = c / ow, cj = c - ci * ow;
+        w = (1u << ci) | (1u << (oh + cj)) | ((uint32_t)(ci * W + cj) << B);
+      }
+      cw.w[s][k] = w;
+    }
+  return cw;
+}
+
+// Viewer word of snake v of the record at `base` (rule warp, after rules and resets).
+template <class SH>
+__device__ __forceinline__ uint32_t make_viewer_word(const KParams& p, const SH& sh, const uint8_t* base, int v) {
+  const Dims& d = p.d;
+  const int W = sh.W(), oh = sh.oh(), ow = sh.ow(), B = p.view_bits;
+  int r0, c0;
+  viewer_origin(d, base, sh.ns(), W, d.V, v, r0, c0);
+  const int rlo = max(0, -r0), rhi = min(oh, d.H - r0), clo = max(0, -c0), chi = min(ow, W - c0);
+  const uint32_t valid = (((1u << rhi) - 1u) & ~((1u << rlo) - 1u)) | ((((1u << chi) - 1u) & ~((1u << clo) - 1u)) << oh);
+  return (~valid & ((1u << B) - 1u)) | ((uint32_t)(r0 * W + c0 + p.view_bias) << B);
+}
+
+template <class SH>
+__device__ __forceinline__ void encode_viewer_reg(const KParams& p, const SH& sh, uint32_t grid32, uint32_t vw,
+                                                  const CellWords& cw, int v, uint8_t* outv, uint32_t lut32) {
+  const int lane = (int)lane_id();
+  const int ohw = sh.ohw(), B = p.view_bits;
+  const uint32_t lutv32 = lut32 + (uint32_t)(v * sh.lut_stride()) * 8u;          // entry 0 is all zero
+  const uint32_t bad = (vw & ((1u << B) - 1u)) | 0x80000000u;
+  const uint32_t gorg = grid32 + (vw >> B) - (uint32_t)p.view_bias;
+  const int shift = (int)((reinterpret_cast<uintptr_t>(outv) >> 3) & 1);
+  const int units = (ohw + shift + 1) >> 1;                                       // <= 64
+  const uint32_t e0 = shift ? cw.w[1][0] : cw.w[0][0], e1 = shift ? cw.w[1][1] : cw.w[0][1];
+  const uint32_t e2 = shift ? cw.w[1][2] : cw.w[0][2], e3 = shift ? cw.w[1][3] : cw.w[0][3];
+  const uint32_t a0 = (e0 & bad) ? lutv32 : gorg + ((e0 & 0x7fffffffu) >> B);
+  const uint32_t a1 = (e1 & bad) ? lutv32 : gorg + ((e1 & 0x7fffffffu) >> B);
+  const uint32_t a2 = (e2 & bad) ? lutv32 : gorg + ((e2 & 0x7fffffffu) >> B);
+  const uint32_t a3 = (e3 & bad) ? lutv32 : gorg + ((e3 & 0x7fffffffu) >> B);
+  const uint32_t k0 = lds_u8(a0), k1 = lds_u8(a1), k2 = lds_u8(a2), k3 = lds_u8(a3);
+  const uint2 q0 = lds_v2(lutv32 + k0 * 8u), q1 = lds_v2(lutv32 + k1 * 8u);
+  const uint2 q2 = lds_v2(lutv32 + k2 * 8u), q3 = lds_v2(lutv32 + k3 * 8u);
+  const int ca0 = 2 * lane - shift, ca1 = ca0 + 64;
+  if (lane < units) {
+    uint8_t* dst0 = outv + (ptrdiff_t)ca0 * 8;
+    if (ca0 >= 0 && ca0 + 1 < ohw) st_cs_128(dst0, q0, q1);
+    else if (ca0 >= 0) st_cs_64(dst0, q0);
+    else st_cs_64(dst0 + 8, q1);
+  }
+  if (lane + 32 < units) {
+    uint8_t* dst1 = outv + (ptrdiff_t)ca1 * 8;
+    if (ca1 + 1 < ohw) st_cs_128(dst1, q2, q3);
+    else st_cs_64(dst1, q2);
+  }
+}
+
+// Full-grid observation: the window IS the grid, so window cell c reads grid byte c.
+template <class SH>
+__device__ __forceinline__ void encode_viewer_direct(const SH& sh, uint32_t grid32, int v, uint8_t* outv, uint32_t lut32) {
+  const int lane = (int)lane_id();
+  const int ohw = sh.ohw();
+  const uint32_t lutv32 = lut32 + (uint32_t)(v * sh.lut_stride()) * 8u;
+  const int shift = (int)((reinterpret_cast<uintptr_t>(outv) >> 3) & 1);
+  const int units = (ohw + shift + 1) >> 1;
+  for (int u0 = lane; u0 < units; u0 += 64) {
+    const int u1 = u0 + 32;
+    const bool has1 = u1 < units;
+    const int ca0 = 2 * u0 - shift, ca1 = 2 * (has1 ? u1 : u0) - shift;
+    const uint32_t k0 = lds_u8(ca0 >= 0 ? grid32 + (uint32_t)ca0 : lutv32);
+    const uint32_t k1 = lds_u8(ca0 + 1 < ohw ? grid32 + (uint32_t)(ca0 + 1) : lutv32);
+    const uint32_t k2 = lds_u8(ca1 >= 0 ? grid32 + (uint32_t)ca1 : lutv32);
+    const uint32_t k3 = lds_u8(ca1 + 1 < ohw ? grid32 + (uint32_t)(ca1 + 1) : lutv32);
+    const uint2 q0 = lds_v2(lutv32 + k0 * 8u), q1 = lds_v2(lutv32 + k1 * 8u);
+    const uint2 q2 = lds_v2(lutv32 + k2 * 8u), q3 = lds_v2(lutv32 + k3 * 8u);
+    uint8_t* dst0 = outv + (ptrdiff_t)ca0 * 8;
+    if (ca0 >= 0 && ca0 + 1 < ohw) st_cs_128(dst0, q0, q1);
+    else if (ca0 >= 0) st_cs_64(dst0, q0);
+    else st_cs_64(dst0 + 8, q1);
+    if (has1) {
+      uint8_t* dst1 = outv + (ptrdiff_t)ca1 * 8;
+      if (ca1 + 1 < ohw) st_cs_128(dst1, q2, q3);
+      else st_cs_64(dst1, q2);
+    }
+  }
+}
+
 // frame_stack > 1: one warp encodes one environment.  Channel-bit bytes of all fs frames are staged in
 // output order ([viewer][cell][frame], oldest first) in the warp's staging area, then expanded to NHWC
 // with flat 128-bit stores.  The frame history lives in HBM as one byte per window cell per stored frame,
@@ -695,7 +798,7 @@ __device__ __forceinline__ void encode_env_stacked(const KParams& p, const SH& s
 // kCoop = true:  the CTA owns ONE tile; all threads move the records, warp 0 runs the rules, then the
 //                warps share the tile's viewers -- for small batches and large records, where one warp per
 //                tile leaves the GPU short of parallel work.
-template <int kNS, int kW, int kOH, int kOW, int kFS, bool kCoop>
+template <int kNS, int kW, int kOH, int kOW, int kFS, bool kCoop, int kEnc>
 __global__ void __launch_bounds__(kCoop ? SNK_MAX_THREADS_COOP : SNK_MAX_THREADS)
 snk_tile_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -717,8 +820,9 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   const int ntiles = kCoop ? 1 : nwarps;
   uint8_t* s_rec = smem + (size_t)(kCoop ? 0 : warp) * tile_bytes;
   uint8_t* s_stage = smem + (size_t)ntiles * tile_bytes + (size_t)warp * stage_bytes;
-  uint8_t* s_flag = smem + (size_t)ntiles * tile_bytes + (size_t)nwarps * stage_bytes + (size_t)(kCoop ? 0 : warp) * 48;
-  uint8_t* s_lut = smem + (size_t)ntiles * tile_bytes + (size_t)nwarps * stage_bytes + (size_t)ntiles * 48;
+  uint8_t* s_flag = smem + (size_t)ntiles * tile_bytes + (size_t)nwarps * stage_bytes + (size_t)(kCoop ? 0 : warp) * TILE_AUX_BYTES;
+  uint32_t* s_view = reinterpret_cast<uint32_t*>(s_flag + 48);         // one packed word per (environment, viewer) lane
+  uint8_t* s_lut = smem + (size_t)ntiles * tile_bytes + (size_t)nwarps * stage_bytes + (size_t)ntiles * TILE_AUX_BYTES;
 
   // ---- stage the tile's records: HBM -> shared.  One bulk asynchronous copy (TMA) issued by the tile's
   //      elected thread and awaited on an mbarrier, or 128-bit coalesced loads (p.use_tma == 0).
@@ -743,7 +847,7 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.enc_blob);
     uint4* dst = reinterpret_cast<uint4*>(s_lut);
-    for (int k = tid; k < (p.enc_blob_bytes >> 4); k += nt) dst[k] = __ldg(src + k);
+    for (int k = tid; k < (p.enc_copy_bytes >> 4); k += nt) dst[k] = __ldg(src + k);
   }
   // this lane's action (lane = environment lane/G of the tile, snake lane%G), fetched before the waits
   uint32_t action = 0;
@@ -757,6 +861,10 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
 
   if (!kCoop || warp == 0) {
     if (ne > 0) tile_rules(p, sh, s_rec, e0, ne, s_flag, action);
+    if (kEnc == ENC_REG && ne > 0) {           // crop origin + out-of-grid rows / columns of every viewer of the tile
+      const int g = (int)lane / G, i = (int)lane - g * G;
+      if (g < ne && i < ns) s_view[lane] = make_viewer_word(p, sh, s_rec + (size_t)g * d.rec_bytes, i);
+    }
     if (p.use_tma) fence_proxy_async();        // the rules' shared-memory writes -> visible to the bulk store
     __syncwarp();
   }
@@ -780,14 +888,19 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
       else { for (int k = (int)lane; k < n16; k += 32) dst[k] = src[k]; }
     }
     if (want_obs) {
+      CellWords cw;
+      if (kEnc == ENC_REG) cw = make_cell_words(sh, p.view_bits);
       if (kCoop) {
 #pragma unroll 1
         for (int pv = wfirst; pv < ne * ns; pv += wstep) {
           const int q = pv / ns, v = pv - q * ns;
           if (s_flag[q] & F_SKIP) continue;
           const uint8_t* base = s_rec + (size_t)q * d.rec_bytes;
+          const uint32_t grid32 = (uint32_t)__cvta_generic_to_shared(base);
           uint8_t* outv = p.obs + ((size_t)(e0 + q) * ns + v) * (size_t)ohw * 8;
-          encode_viewer_fs1(p, sh, base, (uint32_t)__cvta_generic_to_shared(base), v, outv, lut32);
+          if (kEnc == ENC_REG) encode_viewer_reg(p, sh, grid32, s_view[q * G + v], cw, v, outv, lut32);
+          else if (kEnc == ENC_DIRECT) encode_viewer_direct(sh, grid32, v, outv, lut32);
+          else encode_viewer_fs1(p, sh, base, grid32, v, outv, lut32);
         }
       } else {
 #pragma unroll 1
@@ -797,7 +910,12 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
           const uint32_t grid32 = (uint32_t)__cvta_generic_to_shared(base);
           uint8_t* outq = p.obs + (size_t)(e0 + q) * ns * (size_t)ohw * 8;
 #pragma unroll 1
-          for (int v = 0; v < ns; ++v) encode_viewer_fs1(p, sh, base, grid32, v, outq + (size_t)v * ohw * 8, lut32);
+          for (int v = 0; v < ns; ++v) {
+            uint8_t* outv = outq + (size_t)v * ohw * 8;
+            if (kEnc == ENC_REG) encode_viewer_reg(p, sh, grid32, s_view[q * G + v], cw, v, outv, lut32);
+            else if (kEnc == ENC_DIRECT) encode_viewer_direct(sh, grid32, v, outv, lut32);
+            else encode_viewer_fs1(p, sh, base, grid32, v, outv, lut32);
+          }
         }
       }
     }
@@ -985,19 +1103,30 @@ void encode_blob_fill(const Dims& d, uint8_t* out) {
   }
 }
 
+// Which frame_stack-1 encode a configuration runs (see ENC_* in snk_kernels.h).
+static int bits_for(int max_value) { int b = 0; while ((1 << b) <= max_value) ++b; return b; }
+int encode_flavour(const Dims& d) {
+  if (d.fs != 1) return ENC_LEGACY;
+  if (encode_lut_dual(d)) return ENC_LEGACY;
+  if (d.V == 0) return ENC_DIRECT;
+  const int B = d.oh + d.ow;
+  if (d.ohw <= 127 && B + bits_for((d.oh - 1) * d.W + d.ow - 1) <= 31 && B + bits_for(d.HW - 1) <= 32) return ENC_REG;
+  return ENC_LEGACY;
+}
+
 // Shared memory of one CTA of `warps` warps (must mirror the carve-up in snk_tile_kernel).
 size_t tile_smem_bytes(const Dims& d, int warps, bool coop, int EPW) {
   const size_t ntiles = coop ? 1 : (size_t)warps;
   size_t b = ntiles * (size_t)EPW * d.rec_bytes;
   if (d.fs > 1) b += (size_t)warps * (size_t)round_up(d.stage_env_bytes, 16);
-  b += ntiles * 48;
+  b += ntiles * TILE_AUX_BYTES;
   return b + encode_blob_bytes(d, nullptr) + 16;
 }
 
-template <int kNS, int kW, int kOH, int kOW, int kFS, bool kCoop>
+template <int kNS, int kW, int kOH, int kOW, int kFS, bool kCoop, int kEnc>
 static cudaError_t launch_instance(const KParams& p, int threads, size_t smem_bytes, cudaStream_t stream) {
   static size_t configured = 0;
-  auto kern = snk_tile_kernel<kNS, kW, kOH, kOW, kFS, kCoop>;
+  auto kern = snk_tile_kernel<kNS, kW, kOH, kOW, kFS, kCoop, kEnc>;
   if (smem_bytes > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
@@ -1009,25 +1138,30 @@ static cudaError_t launch_instance(const KParams& p, int threads, size_t smem_by
   return cudaGetLastError();
 }
 
-template <int kNS, int kW, int kOH, int kOW, int kFS>
+template <int kNS, int kW, int kOH, int kOW, int kFS, int kEnc>
 static cudaError_t launch_mode(const KParams& p, int threads, size_t smem_bytes, cudaStream_t stream) {
-  return p.coop ? launch_instance<kNS, kW, kOH, kOW, kFS, true>(p, threads, smem_bytes, stream)
-                : launch_instance<kNS, kW, kOH, kOW, kFS, false>(p, threads, smem_bytes, stream);
+  return p.coop ? launch_instance<kNS, kW, kOH, kOW, kFS, true, kEnc>(p, threads, smem_bytes, stream)
+                : launch_instance<kNS, kW, kOH, kOW, kFS, false, kEnc>(p, threads, smem_bytes, stream);
 }
 
-// Specialised instances for the BASELINE shapes; everything else runs the generic instance.
+// Specialised instances for the BASELINE shapes; everything else runs a generic instance of its flavour.
 cudaError_t launch_tile_kernel(const KParams& p, int threads, size_t smem_bytes, cudaStream_t stream) {
   const Dims& d = p.d;
   const bool generic = p.force_generic != 0;
-#define SNK_TRY(NS, W_, OH, OW, FS)                                                              \
-  if (!generic && d.ns == NS && d.W == W_ && d.oh == OH && d.ow == OW && d.fs == FS)             \
-    return launch_mode<NS, W_, OH, OW, FS>(p, threads, smem_bytes, stream);
-  SNK_TRY(4, 20, 11, 11, 1)      // cfg1 / cfg5: 20x20, 4 snakes, vision 5
-  SNK_TRY(4, 20, 20, 20, 1)      // cfg2: full-grid observation
-  SNK_TRY(4, 20, 11, 11, 4)      // cfg3: frame_stack 4
-  SNK_TRY(16, 64, 15, 15, 1)     // cfg4: 64x64, 16 snakes, vision 7
+#define SNK_TRY(NS, W_, OH, OW, FS, ENC)                                                                    \
+  if (!generic && d.ns == NS && d.W == W_ && d.oh == OH && d.ow == OW && d.fs == FS && p.enc_flavour == ENC) \
+    return launch_mode<NS, W_, OH, OW, FS, ENC>(p, threads, smem_bytes, stream);
+  SNK_TRY(4, 20, 11, 11, 1, ENC_REG)        // cfg1 / cfg5: 20x20, 4 snakes, vision 5
+  SNK_TRY(4, 20, 11, 11, 1, ENC_LEGACY)
+  SNK_TRY(4, 20, 20, 20, 1, ENC_DIRECT)     // cfg2: full-grid observation
+  SNK_TRY(4, 20, 11, 11, 4, ENC_LEGACY)     // cfg3: frame_stack 4
+  SNK_TRY(16, 64, 15, 15, 1, ENC_LEGACY)    // cfg4: 64x64, 16 snakes, vision 7
 #undef SNK_TRY
-  return launch_mode<0, 0, 0, 0, 0>(p, threads, smem_bytes, stream);
+  switch (p.enc_flavour) {
+    case ENC_REG: return launch_mode<0, 0, 0, 0, 0, ENC_REG>(p, threads, smem_bytes, stream);
+    case ENC_DIRECT: return launch_mode<0, 0, 0, 0, 0, ENC_DIRECT>(p, threads, smem_bytes, stream);
+    default: return launch_mode<0, 0, 0, 0, 0, ENC_LEGACY>(p, threads, smem_bytes, stream);
+  }
 }
 
 cudaError_t launch_get_state(const Dims& d, const uint8_t* recs, const StateView& sv, cudaStream_t s) {

@@ -12,6 +12,14 @@
 namespace snk {
 
 enum : int { MODE_STEP = 0, MODE_RESET = 1, MODE_ENCODE = 2 };
+// frame_stack 1 encode flavours (chosen per handle by encode_flavour):
+//   ENC_LEGACY  window-cell table in shared memory, or plain index arithmetic for windows wider than 16
+//   ENC_REG     egocentric window of at most 127 cells: the four window cells a lane owns live in registers
+//               as packed words, one packed word per viewer (crop origin + invalid rows/columns) is
+//               prepared by the rule warp -- no table loads, no per-viewer origin arithmetic
+//   ENC_DIRECT  full-grid observation: window cell == grid cell
+enum : int { ENC_LEGACY = 0, ENC_REG = 1, ENC_DIRECT = 2 };
+constexpr int TILE_AUX_BYTES = 48 + 128;   // per tile: flags (32 B), mbarrier (8 B), pad, viewer words (32 x 4 B)
 
 struct KParams {
   Dims d;
@@ -46,6 +54,10 @@ struct KParams {
   int32_t lut_dual;            // fs == 1: {as-other, as-own} LUT pair instead of one LUT per viewer
   int32_t coop;                // CTA-cooperative tile (small batches / large records)
   int32_t use_tma;             // move the record tile with cp.async.bulk (TMA) instead of LDG/STG
+  int32_t enc_flavour;         // ENC_* (fs == 1)
+  int32_t enc_copy_bytes;      // bytes of the blob the kernel stages (the table is skipped when unused)
+  int32_t view_bits;           // ENC_REG: oh + ow, the width of the row/column one-hot field
+  int32_t view_bias;           // ENC_REG: V*W + V, added to the crop origin so it packs as unsigned
 };
 
 struct StateView {
@@ -57,6 +69,7 @@ int tile_group(int ns);
 size_t tile_smem_bytes(const Dims& d, int warps, bool coop, int tile_envs);
 bool encode_lut_dual(const Dims& d);
 bool encode_uses_table(const Dims& d);
+int encode_flavour(const Dims& d);
 size_t encode_blob_bytes(const Dims& d, size_t* tab_off);
 void encode_blob_fill(const Dims& d, uint8_t* out);
 cudaError_t launch_tile_kernel(const KParams& p, int threads, size_t smem_bytes, cudaStream_t stream);

@@ -20,6 +20,8 @@ CONFIGS = {
     'cfg4': dict(num_envs=16384, height=64, width=64, num_snakes=16, snake_length=5, vision_range=7,
                  reward_dict=CFG4_REW),
     'cfg5_shard': dict(num_envs=131072, height=20, width=20, num_snakes=4, snake_length=3, vision_range=5),
+    'cfg5_256k': dict(num_envs=262144, height=20, width=20, num_snakes=4, snake_length=3, vision_range=5),
+    'cfg5_512k': dict(num_envs=524288, height=20, width=20, num_snakes=4, snake_length=3, vision_range=5),
     'cfg5_full': dict(num_envs=1048576, height=20, width=20, num_snakes=4, snake_length=3, vision_range=5),
 }
 
@@ -78,7 +80,7 @@ def run(name, kw, steps, graph=False):
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or list(CONFIGS)
+    which = sys.argv[1:] or ['cfg2', 'cfg3', 'cfg4', 'cfg5_shard', 'cfg5_full']
     for name in which:
         run(name, CONFIGS[name], int(os.environ.get('BENCH_STEPS', 400 if name != 'cfg2' else 2000)))
         if name == 'cfg2' and 'BENCH_STEPS' not in os.environ:
