@@ -262,6 +262,7 @@ extern "C" int snk_step(snk_env* h, const uint8_t* actions_dev, uint8_t* obs_dev
   if (!h->was_reset) return fail(SNK_E_STATE, "step before reset");
   if (obs_dev && ((uintptr_t)obs_dev & 7)) return fail(SNK_E_INVALID, "obs must be 8-byte aligned");
   if ((uintptr_t)rewards_dev & 7) return fail(SNK_E_INVALID, "rewards must be 8-byte aligned");
+  CU(cudaSetDevice(h->device));
   KParams p = base_params(h);
   p.mode = MODE_STEP;
   p.actions = actions_dev; p.obs = obs_dev; p.rew = rewards_dev; p.done = dones_dev;

@@ -200,8 +200,11 @@ __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+// One arrival that also announces `bytes` of bulk-copy traffic; the phase completes when they have landed.
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
@@ -830,10 +833,17 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   const uint32_t rec32 = (uint32_t)__cvta_generic_to_shared(s_rec);
   const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(s_flag) + 32u;     // flags: 32 B, mbarrier: 8 B
   const uint32_t tile_load_bytes = (uint32_t)ne * (uint32_t)d.rec_bytes;
+  // The encode tables ride on the same barrier when the tile's elected thread can speak for every reader
+  // of s_lut (coop CTA, or a single-warp CTA); otherwise the CTA copies them with 128-bit loads below.
+  const bool blob_by_tma = p.use_tma && (kCoop || nwarps == 1);
   if (p.use_tma) {
     if (elected) {
       mbar_init(mbar, 1);
-      if (ne > 0) bulk_load(rec32, p.recs + (size_t)e0 * d.rec_bytes, tile_load_bytes, mbar);
+      if (ne > 0) {
+        mbar_expect_tx(mbar, tile_load_bytes + (blob_by_tma ? (uint32_t)p.enc_copy_bytes : 0u));
+        bulk_load(rec32, p.recs + (size_t)e0 * d.rec_bytes, tile_load_bytes, mbar);
+        if (blob_by_tma) bulk_load((uint32_t)__cvta_generic_to_shared(s_lut), p.enc_blob, (uint32_t)p.enc_copy_bytes, mbar);
+      }
     }
   } else {
     const uint4* src = reinterpret_cast<const uint4*>(p.recs + (size_t)e0 * d.rec_bytes);
@@ -844,7 +854,7 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   }
   // ---- encode tables: host-built blob, L2-resident, copied with 128-bit loads.  fs == 1: {cell code ->
   //      8 output bytes, window-cell table}; fs > 1: {cell code -> channel-bit byte, table}.
-  {
+  if (!blob_by_tma) {
     const uint4* src = reinterpret_cast<const uint4*>(p.enc_blob);
     uint4* dst = reinterpret_cast<uint4*>(s_lut);
     for (int k = tid; k < (p.enc_copy_bytes >> 4); k += nt) dst[k] = __ldg(src + k);
@@ -1125,12 +1135,15 @@ size_t tile_smem_bytes(const Dims& d, int warps, bool coop, int EPW) {
 
 template <int kNS, int kW, int kOH, int kOW, int kFS, bool kCoop, int kEnc>
 static cudaError_t launch_instance(const KParams& p, int threads, size_t smem_bytes, cudaStream_t stream) {
-  static size_t configured = 0;
+  static size_t configured[64] = {};          // per device: function attributes belong to the device's context
   auto kern = snk_tile_kernel<kNS, kW, kOH, kOW, kFS, kCoop, kEnc>;
-  if (smem_bytes > configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || smem_bytes > configured[dev]) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
-    configured = smem_bytes;
+    if (dev >= 0 && dev < 64) configured[dev] = smem_bytes;
   }
   const int envs_per_cta = (kCoop ? 1 : threads / 32) * p.E;
   const int grid = (p.d.N + envs_per_cta - 1) / envs_per_cta;
