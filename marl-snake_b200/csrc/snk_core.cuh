@@ -162,7 +162,8 @@ SNK_HD uint32_t draw_word(const Dims& d, uint32_t env_local, uint32_t event, int
   uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32) ^ 0x534E4B31u, event,
                    ((uint32_t)purpose << 24) | (idx >> 2)};
   philox4x32_10(c, d.seed_lo, d.seed_hi);
-  return c[idx & 3];
+  const uint32_t k = idx & 3u;                 // select chain: a dynamic index would put c[] in local memory
+  return k == 0u ? c[0] : k == 1u ? c[1] : k == 2u ? c[2] : c[3];
 }
 
 SNK_HD uint32_t draw_below(const Dims& d, uint32_t env_local, uint32_t event, int purpose, uint32_t idx,
