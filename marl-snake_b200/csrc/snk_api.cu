@@ -149,7 +149,7 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
     return fail(SNK_E_INVALID, "SNK_TILE_ENVS must be a power of two <= %d", EPW_full);
   }
   // frame_stack > 1 encodes one environment per warp, so more warps than environments would idle
-  int threads = env_int("SNK_THREADS", !coop ? 32 : d.fs > 1 ? 32 * (EPW < 8 ? EPW : 8) : 128);
+  int threads = env_int("SNK_THREADS", !coop ? 32 : d.fs > 1 ? 32 * (EPW < 8 ? EPW : 8) : 96);
   const int max_threads = coop ? SNK_MAX_THREADS_COOP : SNK_MAX_THREADS;
   if (threads < 32 || threads > max_threads || (threads & 31)) { delete h; return fail(SNK_E_INVALID, "SNK_THREADS must be a multiple of 32 in 32..%d", max_threads); }
   while (threads > 32 && tile_smem_bytes(d, threads / 32, coop != 0, EPW) > 200 * 1024) threads -= 32;

@@ -631,78 +631,6 @@ __device__ __forceinline__ void encode_viewer_reg(const KParams& p, const SH& sh
   }
 }
 
-// ---- ENC_WIDE: windows of up to 16 rows x 15 columns, four units (eight cells) per lane ----------------
-// Unit u of a viewer block holds cells 2u and 2u+1 (no parity variants: a block that is only 8-byte aligned
-// is written with two 64-bit stores per unit).  Per unit three words: a / b = one-hot row (bits 0..15) and
-// column (bits 16..30) of the two cells, bit 31 = cell outside the block; g = grid offsets (16 bits each).
-// Per viewer two words: rows / columns of the window outside the grid (same bit layout, bit 31 set) and the
-// crop origin as a byte offset into the record's grid.
-struct WideCells { uint32_t a[4], b[4], g[4]; };
-
-template <class SH>
-__device__ __forceinline__ WideCells make_wide_cells(const SH& sh) {
-  const int lane = (int)lane_id(), ohw = sh.ohw(), ow = sh.ow(), W = sh.W();
-  WideCells wc;
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    const int ca = 2 * (lane + 32 * s), cb = ca + 1;
-    uint32_t a = 0x80000000u, b = 0x80000000u, g = 0;
-    if (ca < ohw) { const int ci = ca / ow, cj = ca - ci * ow; a = (1u << ci) | (1u << (16 + cj)); g = (uint32_t)(ci * W + cj); }
-    if (cb < ohw) { const int ci = cb / ow, cj = cb - ci * ow; b = (1u << ci) | (1u << (16 + cj)); g |= (uint32_t)(ci * W + cj) << 16; }
-    wc.a[s] = a; wc.b[s] = b; wc.g[s] = g;
-  }
-  return wc;
-}
-
-template <class SH>
-__device__ __forceinline__ void make_viewer_wide(const KParams& p, const SH& sh, const uint8_t* base, int v,
-                                                 uint32_t& bad, uint32_t& org) {
-  const Dims& d = p.d;
-  const int W = sh.W(), oh = sh.oh(), ow = sh.ow();
-  int r0, c0;
-  viewer_origin(d, base, sh.ns(), W, d.V, v, r0, c0);
-  const int rlo = max(0, -r0), rhi = min(oh, d.H - r0), clo = max(0, -c0), chi = min(ow, W - c0);
-  const uint32_t valid = (((1u << rhi) - 1u) & ~((1u << rlo) - 1u)) | ((((1u << chi) - 1u) & ~((1u << clo) - 1u)) << 16);
-  bad = ~valid;                                  // bit 31 is never a valid column (ow <= 15)
-  org = (uint32_t)(r0 * W + c0);                 // two's complement; added to the grid's shared address
-}
-
-template <class SH>
-__device__ __forceinline__ void encode_viewer_wide(const KParams& p, const SH& sh, uint32_t grid32, uint32_t bad,
-                                                   uint32_t org, const WideCells& wc, int v, uint8_t* outv, uint32_t lut32) {
-  const int lane = (int)lane_id();
-  const int ohw = sh.ohw(), LS = sh.lut_stride();
-  const bool dual = SH::kMayDual && p.lut_dual != 0;
-  const uint32_t lutv32 = dual ? lut32 : lut32 + (uint32_t)(v * LS) * 8u;        // entry 0 is all zero
-  const uint32_t lutown = lut32 + (uint32_t)LS * 8u;
-  const uint32_t gorg = grid32 + org;
-  const bool aligned = (reinterpret_cast<uintptr_t>(outv) & 15) == 0;
-  const int units = (ohw + 1) >> 1;
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    const int u = lane + 32 * s;
-    if (32 * s >= units) break;                                                   // warp-uniform
-    const uint32_t aa = (wc.a[s] & bad) ? lutv32 : gorg + (wc.g[s] & 0xffffu);
-    const uint32_t ab = (wc.b[s] & bad) ? lutv32 : gorg + (wc.g[s] >> 16);
-    const uint32_t ka = lds_u8(aa), kb = lds_u8(ab);
-    uint32_t la = lutv32, lb = lutv32;
-    if (dual) {
-      la = (((ka * 205u) >> 11) == (uint32_t)v) ? lutown : lut32;
-      lb = (((kb * 205u) >> 11) == (uint32_t)v) ? lutown : lut32;
-    }
-    const uint2 qa = lds_v2(la + ka * 8u), qb = lds_v2(lb + kb * 8u);
-    if (u < units) {
-      uint8_t* dst = outv + (size_t)u * 16;
-      if (2 * u + 1 < ohw) {
-        if (aligned) st_cs_128(dst, qa, qb);
-        else { st_cs_64(dst, qa); st_cs_64(dst + 8, qb); }
-      } else {
-        st_cs_64(dst, qa);
-      }
-    }
-  }
-}
-
 // Full-grid observation: the window IS the grid, so window cell c reads grid byte c.
 template <class SH>
 __device__ __forceinline__ void encode_viewer_direct(const SH& sh, uint32_t grid32, int v, uint8_t* outv, uint32_t lut32) {
@@ -951,10 +879,6 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
       const int g = (int)lane / G, i = (int)lane - g * G;
       if (g < ne && i < ns) s_view[lane] = make_viewer_word(p, sh, s_rec + (size_t)g * d.rec_bytes, i);
     }
-    if (kEnc == ENC_WIDE && ne > 0) {
-      const int g = (int)lane / G, i = (int)lane - g * G;
-      if (g < ne && i < ns) make_viewer_wide(p, sh, s_rec + (size_t)g * d.rec_bytes, i, s_view[lane], s_view[32 + lane]);
-    }
     if (p.use_tma) fence_proxy_async();        // the rules' shared-memory writes -> visible to the bulk store
     __syncwarp();
   }
@@ -979,9 +903,7 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
     }
     if (want_obs) {
       CellWords cw;
-      WideCells wc;
       if (kEnc == ENC_REG) cw = make_cell_words(sh, p.view_bits);
-      if (kEnc == ENC_WIDE) wc = make_wide_cells(sh);
       if (kCoop) {
 #pragma unroll 1
         for (int pv = wfirst; pv < ne * ns; pv += wstep) {
@@ -991,7 +913,6 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
           const uint32_t grid32 = (uint32_t)__cvta_generic_to_shared(base);
           uint8_t* outv = p.obs + ((size_t)(e0 + q) * ns + v) * (size_t)ohw * 8;
           if (kEnc == ENC_REG) encode_viewer_reg(p, sh, grid32, s_view[q * G + v], cw, v, outv, lut32);
-          else if (kEnc == ENC_WIDE) encode_viewer_wide(p, sh, grid32, s_view[q * G + v], s_view[32 + q * G + v], wc, v, outv, lut32);
           else if (kEnc == ENC_DIRECT) encode_viewer_direct(sh, grid32, v, outv, lut32);
           else encode_viewer_fs1(p, sh, base, grid32, v, outv, lut32);
         }
@@ -1006,8 +927,7 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
           for (int v = 0; v < ns; ++v) {
             uint8_t* outv = outq + (size_t)v * ohw * 8;
             if (kEnc == ENC_REG) encode_viewer_reg(p, sh, grid32, s_view[q * G + v], cw, v, outv, lut32);
-            else if (kEnc == ENC_WIDE) encode_viewer_wide(p, sh, grid32, s_view[q * G + v], s_view[32 + q * G + v], wc, v, outv, lut32);
-            else if (kEnc == ENC_DIRECT) encode_viewer_direct(sh, grid32, v, outv, lut32);
+              else if (kEnc == ENC_DIRECT) encode_viewer_direct(sh, grid32, v, outv, lut32);
             else encode_viewer_fs1(p, sh, base, grid32, v, outv, lut32);
           }
         }
@@ -1205,7 +1125,6 @@ int encode_flavour(const Dims& d) {
   if (d.V == 0) return dual ? ENC_LEGACY : ENC_DIRECT;
   const int B = d.oh + d.ow;
   if (!dual && d.ohw <= 127 && B + bits_for((d.oh - 1) * d.W + d.ow - 1) <= 31 && B + bits_for(d.HW - 1) <= 32) return ENC_REG;
-  if (d.oh <= 16 && d.ow <= 15 && d.ohw <= 255 && d.HW <= 65535) return ENC_WIDE;
   return ENC_LEGACY;
 }
 
@@ -1253,13 +1172,11 @@ cudaError_t launch_tile_kernel(const KParams& p, int threads, size_t smem_bytes,
   SNK_TRY(4, 20, 11, 11, 1, ENC_LEGACY)
   SNK_TRY(4, 20, 20, 20, 1, ENC_DIRECT)     // cfg2: full-grid observation
   SNK_TRY(4, 20, 11, 11, 4, ENC_LEGACY)     // cfg3: frame_stack 4
-  SNK_TRY(16, 64, 15, 15, 1, ENC_WIDE)      // cfg4: 64x64, 16 snakes, vision 7
-  SNK_TRY(16, 64, 15, 15, 1, ENC_LEGACY)
+  SNK_TRY(16, 64, 15, 15, 1, ENC_LEGACY)    // cfg4: 64x64, 16 snakes, vision 7
 #undef SNK_TRY
   switch (p.enc_flavour) {
     case ENC_REG: return launch_mode<0, 0, 0, 0, 0, ENC_REG>(p, threads, smem_bytes, stream);
     case ENC_DIRECT: return launch_mode<0, 0, 0, 0, 0, ENC_DIRECT>(p, threads, smem_bytes, stream);
-    case ENC_WIDE: return launch_mode<0, 0, 0, 0, 0, ENC_WIDE>(p, threads, smem_bytes, stream);
     default: return launch_mode<0, 0, 0, 0, 0, ENC_LEGACY>(p, threads, smem_bytes, stream);
   }
 }

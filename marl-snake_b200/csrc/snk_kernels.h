@@ -18,10 +18,8 @@ enum : int { MODE_STEP = 0, MODE_RESET = 1, MODE_ENCODE = 2 };
 //               as packed words, one packed word per viewer (crop origin + invalid rows/columns) is
 //               prepared by the rule warp -- no table loads, no per-viewer origin arithmetic
 //   ENC_DIRECT  full-grid observation: window cell == grid cell
-//   ENC_WIDE    egocentric window of up to 16 x 15 cells (at most 255): as ENC_REG with four units per lane
-//               and unpacked words (row / column one-hots, grid offsets, crop origin in separate registers)
-enum : int { ENC_LEGACY = 0, ENC_REG = 1, ENC_DIRECT = 2, ENC_WIDE = 3 };
-constexpr int TILE_AUX_BYTES = 48 + 256;   // per tile: flags (32 B), mbarrier (8 B), pad, viewer words (2 x 32 x 4 B)
+enum : int { ENC_LEGACY = 0, ENC_REG = 1, ENC_DIRECT = 2 };
+constexpr int TILE_AUX_BYTES = 48 + 128;   // per tile: flags (32 B), mbarrier (8 B), pad, viewer words (32 x 4 B)
 
 struct KParams {
   Dims d;

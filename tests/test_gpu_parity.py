@@ -251,7 +251,7 @@ def test_gpu_rollout_stats():
     assert float(t[0]) == eps
 
 
-@pytest.mark.parametrize('coop', ['0', '1'])
+@pytest.mark.parametrize('coop', ['0', '1', '1-small'])
 @pytest.mark.parametrize('kw,N', [
     (dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5), 2051),
     (dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5, frame_stack=4), 515),
@@ -264,10 +264,14 @@ def test_gpu_rollout_stats():
     (dict(height=9, width=9, num_snakes=1, snake_length=3, vision_range=2), 700),      # 32 envs per warp
 ])
 def test_gpu_tile_modes(monkeypatch, coop, kw, N):
-    """Both tile modes (warp-private tiles / CTA-cooperative tile) against the host build of the rule
-    source; by default the mode is chosen from the batch size, so each is forced here."""
+    """Both tile modes (warp-private tiles / CTA-cooperative tile; '1-small' = one environment per
+    cooperative tile with 64 threads) against the host build of the rule source; by default the mode and the
+    tile size are chosen from the batch size, so each is forced here."""
     from hostsim_util import HostSim
-    monkeypatch.setenv('SNK_COOP', coop)
+    monkeypatch.setenv('SNK_COOP', coop[0])
+    if coop == '1-small':
+        monkeypatch.setenv('SNK_THREADS', '64')
+        monkeypatch.setenv('SNK_TILE_ENVS', '1')
     ns = kw['num_snakes']
     hs = HostSim(N, kw, rng_mode=0, auto_reset=1, seed=21)
     be = GpuBackend(N, kw, rng_mode=0, auto_reset=1, seed=21)

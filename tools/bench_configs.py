@@ -19,6 +19,7 @@ CONFIGS = {
     'cfg3': dict(num_envs=65536, height=20, width=20, num_snakes=4, snake_length=3, vision_range=5, frame_stack=4),
     'cfg4': dict(num_envs=16384, height=64, width=64, num_snakes=16, snake_length=5, vision_range=7,
                  reward_dict=CFG4_REW),
+    'wide8': dict(num_envs=32768, height=32, width=32, num_snakes=8, snake_length=4, vision_range=7),
     'cfg5_shard': dict(num_envs=131072, height=20, width=20, num_snakes=4, snake_length=3, vision_range=5),
     'cfg5_256k': dict(num_envs=262144, height=20, width=20, num_snakes=4, snake_length=3, vision_range=5),
     'cfg5_512k': dict(num_envs=524288, height=20, width=20, num_snakes=4, snake_length=3, vision_range=5),
