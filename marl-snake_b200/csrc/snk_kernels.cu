@@ -667,7 +667,8 @@ __device__ __forceinline__ void encode_viewer_direct(const SH& sh, uint32_t grid
 // rows of a ring (hist layout); each step reads fs-1 rows and writes one.
 template <class SH, int kFS>
 __device__ __forceinline__ void encode_env_stacked(const KParams& p, const SH& sh, const uint8_t* base, int e,
-                                                   int qflag, uint8_t* s_stage, uint32_t lut32, const uint8_t* s_lut) {
+                                                   int qflag, uint8_t* s_stage, uint32_t lut32, const uint8_t* s_lut,
+                                                   const uint8_t* s_hist) {
   const Dims& d = p.d;
   const uint32_t lane = lane_id();
   const int ns = sh.ns(), W = sh.W(), ohw = sh.ohw(), ow = sh.ow(), oh = sh.oh(), LS = sh.lut_stride(), fs = sh.fs();
@@ -679,26 +680,15 @@ __device__ __forceinline__ void encode_env_stacked(const KParams& p, const SH& s
   const uint32_t grid32 = (uint32_t)__cvta_generic_to_shared(grid);
   const bool init = (qflag & (F_RESET | F_INIT)) != 0;
   const int hpos = (int)((const EnvHdr*)(base + d.off_hdr))->hpos;
-  // fs == 4, up to 4 viewers, window <= 128 cells: fetch the kept history words of ALL viewers first so the
-  // environment pays one HBM round trip instead of one per viewer
-  constexpr int kPre = (kFS == 4 && SH::kNSc >= 1 && SH::kNSc <= 4) ? SH::kNSc : 0;
-  uint32_t pre[kPre > 0 ? kPre : 1][3];
-  const bool prefetched = kPre > 0 && p.use_tab && ohw <= 128 && !init;
-  if (prefetched && (int)lane * 4 < ohw) {
-#pragma unroll
-    for (int v = 0; v < kPre; ++v) {
-      const uint8_t* hr = p.hist + (size_t)e * d.hist_env_bytes + (size_t)(v * 4) * d.ohw_p + lane * 4;
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        pre[v][k] = __ldcs(reinterpret_cast<const uint32_t*>(hr + (size_t)((hpos + 1 + k) & 3) * d.ohw_p));
-    }
-  }
-#pragma unroll
-  for (int v = 0; v < (kPre > 0 ? kPre : ns); ++v) {
+  // The environment's whole history block (ns x fs rows) was staged into shared memory by the same bulk copy
+  // barrier as its record, so the kept frames cost no HBM round trip here; only the new row goes out.
+#pragma unroll 1
+  for (int v = 0; v < ns; ++v) {
     int r0, c0;
     viewer_origin(d, base, ns, W, V, v, r0, c0);
     uint8_t* stg = s_stage + (size_t)v * ohw * fs;
     uint8_t* hrow = p.hist + (size_t)e * d.hist_env_bytes + (size_t)(v * fs) * d.ohw_p;
+    const uint8_t* srow = s_hist + (size_t)(v * fs) * d.ohw_p;                  // the same rows, staged
     if (kFS == 4 && p.use_tab) {
       // four consecutive window cells per lane: the new frame's bits as one word, the three kept history
       // rows as one word each, 4x4 byte transpose to per-cell words of four frames
@@ -715,13 +705,10 @@ __device__ __forceinline__ void encode_env_stacked(const KParams& p, const SH& s
           nw |= lds_u8(lutv32 + lds_u8(a)) << (8 * k);
         }
         uint32_t f0, f1, f2;
-        if (prefetched) {
-          f0 = pre[kPre > 0 ? v : 0][0]; f1 = pre[kPre > 0 ? v : 0][1]; f2 = pre[kPre > 0 ? v : 0][2];
-          *reinterpret_cast<uint32_t*>(hrow + (size_t)hpos * d.ohw_p + c4) = nw;
-        } else if (!init) {
-          f0 = __ldcs(reinterpret_cast<const uint32_t*>(hrow + (size_t)((hpos + 1) & 3) * d.ohw_p + c4));
-          f1 = __ldcs(reinterpret_cast<const uint32_t*>(hrow + (size_t)((hpos + 2) & 3) * d.ohw_p + c4));
-          f2 = __ldcs(reinterpret_cast<const uint32_t*>(hrow + (size_t)((hpos + 3) & 3) * d.ohw_p + c4));
+        if (!init) {
+          f0 = *reinterpret_cast<const uint32_t*>(srow + (size_t)((hpos + 1) & 3) * d.ohw_p + c4);
+          f1 = *reinterpret_cast<const uint32_t*>(srow + (size_t)((hpos + 2) & 3) * d.ohw_p + c4);
+          f2 = *reinterpret_cast<const uint32_t*>(srow + (size_t)((hpos + 3) & 3) * d.ohw_p + c4);
           *reinterpret_cast<uint32_t*>(hrow + (size_t)hpos * d.ohw_p + c4) = nw;
         } else {                                   // reset: every slot holds the first frame (:452-457)
           f0 = f1 = f2 = nw;
@@ -744,7 +731,7 @@ __device__ __forceinline__ void encode_env_stacked(const KParams& p, const SH& s
         for (int slot = 0; slot < fs; ++slot) {
           if (slot == hpos) continue;                // about to be overwritten by the new frame
           int f = slot - hpos - 1; if (f < 0) f += fs;
-          const uint8_t* src = hrow + (size_t)slot * d.ohw_p;
+          const uint8_t* src = srow + (size_t)slot * d.ohw_p;
           for (int c4 = (int)lane * 4; c4 < ohw; c4 += 128) {
             const uint32_t w = *reinterpret_cast<const uint32_t*>(src + c4);
 #pragma unroll
@@ -822,10 +809,12 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
 
   // shared memory (mirrored by tile_smem_bytes): tiles' records, per-warp staging (fs > 1), per-tile
   // flags, then the CTA-wide encode tables
-  const int tile_bytes = EPW * d.rec_bytes;
+  const int rec_tile_bytes = EPW * d.rec_bytes;
+  const int tile_bytes = rec_tile_bytes + EPW * d.hist_env_bytes;      // records, then (fs > 1) the frame histories
   const int stage_bytes = fs == 1 ? 0 : round_up(d.stage_env_bytes, 16);
   const int ntiles = kCoop ? 1 : nwarps;
   uint8_t* s_rec = smem + (size_t)(kCoop ? 0 : warp) * tile_bytes;
+  uint8_t* s_hist = s_rec + rec_tile_bytes;
   uint8_t* s_stage = smem + (size_t)ntiles * tile_bytes + (size_t)warp * stage_bytes;
   uint8_t* s_flag = smem + (size_t)ntiles * tile_bytes + (size_t)nwarps * stage_bytes + (size_t)(kCoop ? 0 : warp) * TILE_AUX_BYTES;
   uint32_t* s_view = reinterpret_cast<uint32_t*>(s_flag + 48);         // one packed word per (environment, viewer) lane
@@ -837,6 +826,7 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   const uint32_t rec32 = (uint32_t)__cvta_generic_to_shared(s_rec);
   const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(s_flag) + 32u;     // flags: 32 B, mbarrier: 8 B
   const uint32_t tile_load_bytes = (uint32_t)ne * (uint32_t)d.rec_bytes;
+  const uint32_t hist_load_bytes = (fs > 1 && p.mode == MODE_STEP) ? (uint32_t)ne * (uint32_t)d.hist_env_bytes : 0u;
   // The encode tables ride on the same barrier when the tile's elected thread can speak for every reader
   // of s_lut (coop CTA, or a single-warp CTA); otherwise the CTA copies them with 128-bit loads below.
   const bool blob_by_tma = p.use_tma && (kCoop || nwarps == 1);
@@ -844,8 +834,9 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
     if (elected) {
       mbar_init(mbar, 1);
       if (ne > 0) {
-        mbar_expect_tx(mbar, tile_load_bytes + (blob_by_tma ? (uint32_t)p.enc_copy_bytes : 0u));
+        mbar_expect_tx(mbar, tile_load_bytes + hist_load_bytes + (blob_by_tma ? (uint32_t)p.enc_copy_bytes : 0u));
         bulk_load(rec32, p.recs + (size_t)e0 * d.rec_bytes, tile_load_bytes, mbar);
+        if (hist_load_bytes) bulk_load((uint32_t)__cvta_generic_to_shared(s_hist), p.hist + (size_t)e0 * d.hist_env_bytes, hist_load_bytes, mbar);
         if (blob_by_tma) bulk_load((uint32_t)__cvta_generic_to_shared(s_lut), p.enc_blob, (uint32_t)p.enc_copy_bytes, mbar);
       }
     }
@@ -855,6 +846,11 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
     const int n16 = ne * (d.rec_bytes >> 4);
     if (kCoop) { for (int k = tid; k < n16; k += nt) dst[k] = __ldcs(src + k); }
     else { for (int k = (int)lane; k < n16; k += 32) dst[k] = __ldcs(src + k); }
+    const uint4* hsrc = reinterpret_cast<const uint4*>(p.hist + (size_t)e0 * d.hist_env_bytes);
+    uint4* hdst = reinterpret_cast<uint4*>(s_hist);
+    const int h16 = (int)(hist_load_bytes >> 4);
+    if (kCoop) { for (int k = tid; k < h16; k += nt) hdst[k] = __ldcs(hsrc + k); }
+    else { for (int k = (int)lane; k < h16; k += 32) hdst[k] = __ldcs(hsrc + k); }
   }
   // ---- encode tables: host-built blob, L2-resident, copied with 128-bit loads.  fs == 1: {cell code ->
   //      8 output bytes, window-cell table}; fs > 1: {cell code -> channel-bit byte, table}.
@@ -943,7 +939,7 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
     const int qflag = s_flag[q];
     if (qflag & F_SKIP) continue;
     encode_env_stacked<Shape<kNS, kW, kOH, kOW, kFS>, kFS>(p, sh, s_rec + (size_t)q * d.rec_bytes, e0 + q, qflag,
-                                                           s_stage, lut32, s_lut);
+                                                           s_stage, lut32, s_lut, s_hist + (size_t)q * d.hist_env_bytes);
   }
   if (kCoop) __syncthreads(); else __syncwarp();
   if (!kCoop || warp == 0) {
@@ -1131,7 +1127,7 @@ int encode_flavour(const Dims& d) {
 // Shared memory of one CTA of `warps` warps (must mirror the carve-up in snk_tile_kernel).
 size_t tile_smem_bytes(const Dims& d, int warps, bool coop, int EPW) {
   const size_t ntiles = coop ? 1 : (size_t)warps;
-  size_t b = ntiles * (size_t)EPW * d.rec_bytes;
+  size_t b = ntiles * (size_t)EPW * ((size_t)d.rec_bytes + (size_t)d.hist_env_bytes);
   if (d.fs > 1) b += (size_t)warps * (size_t)round_up(d.stage_env_bytes, 16);
   b += ntiles * TILE_AUX_BYTES;
   return b + encode_blob_bytes(d, nullptr) + 16;
