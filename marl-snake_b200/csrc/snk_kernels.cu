@@ -32,21 +32,49 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
 // ---- phase R helpers (warp-cooperative) -----------------------------------------------------------
 
+// 0x80 in every byte of x that is zero (exact, no carries between bytes).
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t x) {
+  const uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+  return ~(t | x | 0x7F7F7F7Fu);
+}
+__device__ __forceinline__ uint32_t warp_inclusive_sum(uint32_t v, uint32_t lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if ((int)lane >= o) v += t;
+  }
+  return v;
+}
+
 // Place k fruits on the k drawn ranks of the row-major empty-cell list (all ranks refer to the
 // grid as it is before any of them is placed; duplicates collapse)    core/grid_util.py:126-133
+// The grid is scanned as 32-bit words (four cells): lane l owns the contiguous word range
+// [l*cw, (l+1)*cw), so lane order is row-major order; one pass counts the empty cells per lane, a warp
+// prefix sum locates the lane range holding a drawn rank, and the warp then scans only that range.
 // (The record is passed as its base address, not as a Rec&: a Rec whose address escapes lives in local
 // memory, and every byte store into the grid would force its pointer fields to be reloaded from there.)
 __device__ __noinline__ void place_fruits_warp(const KParams& p, uint8_t* rec_base, uint32_t env_local, int k, int purpose) {
   const Dims& d = p.d;
   const Rec r = rec_view(rec_base, d);
+  const uint32_t FULL = 0xffffffffu;
   const uint32_t lane = lane_id();
   const int HW = d.HW;
-  int n_empty = 0;
-  for (int base = 0; base < HW; base += 32) {
-    const int c = base + (int)lane;
-    const bool emp = c < HW && r.grid[c] == EMPTY;
-    n_empty += __popc(__ballot_sync(0xffffffffu, emp));
+  const int nwords = (HW + 3) >> 2, cw = (nwords + 31) >> 5;
+  const uint32_t* gw = reinterpret_cast<const uint32_t*>(r.grid);        // record start is 16-byte aligned
+  auto load_zeros = [&](int w) -> uint32_t {                              // 0x80 per EMPTY cell of word w
+    if (w >= nwords) return 0u;
+    uint32_t x = gw[w];
+    if (4 * w + 4 > HW) x |= 0xFFFFFFFFu << (8 * (HW - 4 * w));           // bytes past the grid are not cells
+    return zero_bytes(x);
+  };
+  uint32_t cnt = 0;
+  for (int j = 0; j < cw; ++j) {
+    int jj = j + (int)lane;                                              // rotate: lanes start in different banks
+    jj -= (jj >= cw) ? ((jj >= 2 * cw) ? (jj / cw) * cw : cw) : 0;
+    cnt += (uint32_t)__popc(load_zeros((int)lane * cw + jj));
   }
+  const uint32_t incl = warp_inclusive_sum(cnt, lane);
+  const int n_empty = (int)__shfl_sync(FULL, incl, 31);
   if (n_empty == 0 || k <= 0) return;              // reference draws nothing when no cell is empty
   int rank = -1;
   if ((int)lane < k) {
@@ -64,14 +92,30 @@ __device__ __noinline__ void place_fruits_warp(const KParams& p, uint8_t* rec_ba
   }
   __syncwarp();
   if (lane == 0 && d.rng_mode == RNG_REPLAY) r.hdr->cursor += (uint32_t)k;
-  int run = 0, mycell = -1;
-  for (int base = 0; base < HW; base += 32) {
-    const int c = base + (int)lane;
-    const bool emp = c < HW && r.grid[c] == EMPTY;
-    const uint32_t b = __ballot_sync(0xffffffffu, emp);
-    const int pc = __popc(b);
-    if (rank >= run && rank < run + pc) mycell = base + (int)__fns(b, 0, rank - run + 1);
-    run += pc;
+  int mycell = -1;
+#pragma unroll 1
+  for (int j = 0; j < k; ++j) {
+    uint32_t rr = (uint32_t)__shfl_sync(FULL, rank, j);
+    const int owner = __popc(__ballot_sync(FULL, incl <= rr));            // first lane whose prefix exceeds the rank
+    rr -= __shfl_sync(FULL, incl - cnt, owner);                           // rank inside the owner's word range
+    int cell = -1;
+#pragma unroll 1
+    for (int t0 = 0; t0 < cw; t0 += 32) {
+      const int t = t0 + (int)lane;
+      const uint32_t z = t < cw ? load_zeros(owner * cw + t) : 0u;
+      const uint32_t c = (uint32_t)__popc(z);
+      const uint32_t in2 = warp_inclusive_sum(c, lane);
+      const uint32_t total = __shfl_sync(FULL, in2, 31);
+      if (rr < total) {
+        const int wl = __popc(__ballot_sync(FULL, in2 <= rr));
+        const uint32_t zsel = __shfl_sync(FULL, z, wl);
+        const uint32_t rin = rr - __shfl_sync(FULL, in2 - c, wl);
+        cell = 4 * (owner * cw + t0 + wl) + (int)(__fns(zsel, 0, (int)rin + 1) >> 3);
+        break;
+      }
+      rr -= total;
+    }
+    if ((int)lane == j) mycell = cell;
   }
   __syncwarp();
   if (mycell >= 0) r.grid[mycell] = (uint8_t)FRUIT;
@@ -84,7 +128,21 @@ __device__ __noinline__ void reset_env_warp(const KParams& p, uint8_t* rec_base,
   const Rec r = rec_view(rec_base, d);
   const uint32_t lane = lane_id();
   const int ns = d.ns, K = d.K, W = d.W;
-  for (int c = (int)lane; c < d.HW; c += 32) r.grid[c] = wall_or_empty(c, d.H, d.W);
+  // make_grid: walled empty box (core/grid_util.py:14-20), one grid row at a time so no division is needed
+  if ((W & 3) == 0) {
+    uint32_t* gw = reinterpret_cast<uint32_t*>(r.grid);
+    const int wpr = W >> 2;
+    for (int rr = 0; rr < d.H; ++rr) {
+      const bool edge = rr == 0 || rr == d.H - 1;
+      for (int x = (int)lane; x < wpr; x += 32)
+        gw[rr * wpr + x] = edge ? 0x01010101u : (x == 0 ? 0x00000001u : 0u) | (x == wpr - 1 ? 0x01000000u : 0u);
+    }
+  } else {
+    for (int rr = 0; rr < d.H; ++rr) {
+      const bool edge = rr == 0 || rr == d.H - 1;
+      for (int c = (int)lane; c < W; c += 32) r.grid[rr * W + c] = (uint8_t)((edge || c == 0 || c == W - 1) ? WALL : EMPTY);
+    }
+  }
   __syncwarp();
 
   uint64_t entry = 0;
