@@ -293,15 +293,17 @@ def ours(args):
                          'algorithmic_bytes_per_env_step': bytes_per_env, 'kernel': 'snk_tile_kernel',
                          'launch_ms': ms / args.steps},
             'e2e': {'value': N * world * ns * K2 / e2e_s, 'unit': 'agent-steps/s',
-                    'h2d_bytes_per_step': N * ns, 'd2h_bytes_per_step': N * (batch.obs_shape[0] * batch.obs_shape[1] *
-                                                                             batch.obs_shape[2] * batch.obs_shape[3]) + N * ns * 9,
+                    # bytes that cross PCIe per step per rank: actions in; channel-bit observations, float64
+                    # rewards and dones out.  The call delivers N*obs_bytes of uint8 NHWC into the host buffer.
+                    'h2d_bytes_per_step': N * ns, 'd2h_bytes_per_step': N * obs_bytes // 8 + N * ns * 9,
+                    'host_obs_bytes_delivered_per_step': N * obs_bytes,
                     'steps': K2, 'ms_per_step': 1e3 * e2e_s / K2,
                     'api': 'snk_step_host (C ABI, pinned host buffers), packed transport: device packs 8 channel '
                            'bytes -> 1, %d MB over PCIe in chunks, %d host threads per rank widen to uint8 NHWC'
                            % (obs_bytes * N // 8 // 1000000, host_threads),
-                    'pcie_obs_bytes_per_step': N * obs_bytes // 8, 'host_threads_per_rank': host_threads,
+                    'host_threads_per_rank': host_threads,
                     'raw_transport': {'value': N * world * ns * K2 / e2e_raw_s, 'ms_per_step': 1e3 * e2e_raw_s / K2,
-                                      'pcie_obs_bytes_per_step': N * obs_bytes}},
+                                      'd2h_bytes_per_step': N * obs_bytes + N * ns * 9}},
             'gpu_launches': args.steps * world,       # timed region of `value`: one snk_tile_kernel per step per rank
             'clocks': sampler.summary(),
             'rollout_stats': dict(zip(('episodes', 'return_sum', 'episode_steps_sum', 'fruits_sum', 'kills_sum',
