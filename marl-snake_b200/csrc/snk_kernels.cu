@@ -497,13 +497,16 @@ __device__ __forceinline__ void tile_rules(const KParams& p, const SH& sh, uint8
   if (!env_ok) flag = F_SKIP;
   __syncwarp();
 
-  // ---- rare events, whole warp per environment
+  // ---- rare events, whole warp per environment: only environments that owe a fruit draw or a reset
+  if (env_ok && i == 0) s_flag[g] = flag;
+  uint32_t ev = __ballot_sync(FULL, env_ok && i == 0 && (fruit != 0 || (flag & F_RESET)));
 #pragma unroll 1
-  for (int q = 0; q < ne; ++q) {
-    const int qf = __shfl_sync(FULL, fruit, q * G);
-    const int qflag = __shfl_sync(FULL, (int)flag, q * G);
-    if (lane == 0) s_flag[q] = (uint8_t)qflag;
-    if (!qf && !(qflag & F_RESET)) continue;
+  while (ev) {
+    const int src = __ffs(ev) - 1;                 // first lane of the environment's lane group
+    ev &= ev - 1;
+    const int q = src / G;
+    const int qf = __shfl_sync(FULL, fruit, src);
+    const int qflag = __shfl_sync(FULL, (int)flag, src);
     uint8_t* rq = s_rec + (size_t)q * d.rec_bytes;
     if (qf) place_fruits_warp(p, rq, (uint32_t)(e0 + q), qf, DRAW_STEP_FRUIT);
     if (qflag & F_RESET) reset_env_warp(p, rq, (uint32_t)(e0 + q));
