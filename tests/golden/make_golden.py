@@ -415,5 +415,7 @@ if __name__ == '__main__':
             vision_range=3, frame_stack=2, reward_dict=cfg4_rew)
     rollout('roll_crowd', 800, 4, 100, height=9, width=9, num_snakes=5, snake_length=3,
             vision_range=2, num_fruits=6, reward_dict=cfg4_rew)
+    rollout('roll_cfg4', 1100, 1, 90, height=64, width=64, num_snakes=16, snake_length=5, vision_range=7,
+            max_episode_steps=45, reward_dict=cfg4_rew)            # BASELINE cfg4 shape; the cap forces one auto-reset
     rollout('roll_human', 1000, 4, 150, height=12, width=12, num_snakes=3, snake_length=3,
             vision_range=4, observer='human', reward_dict=cfg4_rew)

@@ -6,7 +6,7 @@ import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 ROLLOUTS = ['roll_cfg1', 'roll_full', 'roll_fs4', 'roll_big', 'roll_single', 'roll_cap',
-            'roll_rect', 'roll_crowd', 'roll_coop', 'roll_human']
+            'roll_rect', 'roll_crowd', 'roll_coop', 'roll_human', 'roll_cfg4']
 
 
 def unpack_obs(packed):
