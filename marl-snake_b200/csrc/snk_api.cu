@@ -152,6 +152,9 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
   int threads = env_int("SNK_THREADS", !coop ? 32 : d.fs > 1 ? 32 * (EPW < 8 ? EPW : 8) : 96);
   const int max_threads = coop ? SNK_MAX_THREADS_COOP : SNK_MAX_THREADS;
   if (threads < 32 || threads > max_threads || (threads & 31)) { delete h; return fail(SNK_E_INVALID, "SNK_THREADS must be a multiple of 32 in 32..%d", max_threads); }
+  // large grids: fewer environments per tile until two CTAs fit an SM, then fewer warps if it still does not fit
+  if (env_int("SNK_TILE_ENVS", 0) <= 0)
+    while (EPW > 1 && tile_smem_bytes(d, coop ? threads / 32 : 1, coop != 0, EPW) > 100 * 1024) EPW >>= 1;
   while (threads > 32 && tile_smem_bytes(d, threads / 32, coop != 0, EPW) > 200 * 1024) threads -= 32;
   h->tile_envs = EPW; h->threads = threads; h->coop = coop;
   h->force_generic = env_int("SNK_FORCE_GENERIC", 0);

@@ -289,6 +289,34 @@ def test_gpu_tile_modes(monkeypatch, coop, kw, N):
     be.close()
 
 
+@pytest.mark.parametrize('kw,N,steps', [
+    (dict(height=80, width=90, num_snakes=2, snake_length=3, vision_range=3, num_fruits=20), 6, 60),
+    (dict(height=200, width=201, num_snakes=4, snake_length=4, vision_range=6, num_fruits=32), 3, 40),
+    (dict(height=255, width=257, num_snakes=3, snake_length=2, vision_range=2, num_fruits=9,
+          max_episode_steps=7), 2, 30),                                  # the largest grid the ABI accepts
+])
+def test_gpu_large_grids(kw, N, steps):
+    """Grids of thousands of cells: the fruit rank-select walks several 32-word groups per lane range, resets
+    repaint the walls row by row, and the tile shrinks to what fits in shared memory (one record is up to
+    80 KB).  Against the host build of the rule source, Philox mode, step cap forcing resets."""
+    from hostsim_util import HostSim
+    ns = kw['num_snakes']
+    hs = HostSim(N, kw, rng_mode=0, auto_reset=1, seed=77)
+    be = GpuBackend(N, kw, rng_mode=0, auto_reset=1, seed=77)
+    assert np.array_equal(hs.reset(), be.reset())
+    assert np.array_equal(hs.grid()[0], be.grid()[0])
+    rng = np.random.RandomState(3)
+    for t in range(steps):
+        a = rng.randint(0, 3, size=(N, ns)).astype(np.uint8)
+        o1, r1, d1, i1 = hs.step(a)
+        o2, r2, d2, i2 = be.step(a)
+        assert np.array_equal(r1, r2) and np.array_equal(d1, d2.astype(np.uint8)), t
+        assert np.array_equal(o1, o2), t
+        assert np.array_equal(hs.grid()[0], be.grid()[0]), t
+    assert be.errors() == 0
+    be.close()
+
+
 def test_render_export_and_gui_wrapper():
     """N3: one environment's state exported to the host renderers (render_fancy / rgb_array / RenderGUI)."""
     from marl_snake_b200 import RenderGUI, make_snake
