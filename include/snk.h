@@ -148,6 +148,10 @@ int snk_step(snk_env* env, const uint8_t* actions_dev, uint8_t* obs_dev, double*
  * SNK_HOST_THREADS override at create time). */
 int snk_step_host(snk_env* env, const uint8_t* actions_host, uint8_t* obs_host,
                   double* rewards_host, uint8_t* dones_host);
+/* snk_step_host plus the terminal info dict (snake_env.py:396-410): extra_host holds HOST pointers here
+ * (any may be NULL); entries of environments with finished[e] == 0 are unspecified. */
+int snk_step_host_info(snk_env* env, const uint8_t* actions_host, uint8_t* obs_host, double* rewards_host,
+                       uint8_t* dones_host, const snk_step_extra* extra_host);
 int snk_reset_host(snk_env* env, uint8_t* obs_host);
 
 enum { SNK_XFER_RAW = 0, SNK_XFER_PACKED = 1 };

@@ -50,6 +50,10 @@ struct snk_env {
   int enc_blob_bytes = 0, enc_tab_off = 0, use_tab = 0;
   // device mirrors used by the *_host entry points
   uint8_t* h_actions = nullptr; uint8_t* h_obs = nullptr; double* h_rew = nullptr; uint8_t* h_done = nullptr;
+  uint8_t* h_fin = nullptr; int32_t* h_rank = nullptr; double* h_scores = nullptr; int32_t* h_counts = nullptr;   // [3][N, ns]
+  // few environments: every output of a host-buffer step lives in ONE device block mirrored by ONE pinned host
+  // block, so the step costs one copy in, one launch, one copy out (the latency-bound drop-in mode)
+  uint8_t* small_dev = nullptr; uint8_t* small_host = nullptr;
   cudaStream_t own_stream = nullptr;
   // packed host transport (snk_hostxfer.cpp): device channel-bit mirror, pinned staging, widening pool
   int xfer_mode = XFER_RAW, xfer_threads = 0;
@@ -215,6 +219,9 @@ extern "C" int snk_destroy(snk_env* h) {
   cudaFree(h->recs); cudaFree(h->hist); cudaFree(h->spawn); cudaFree(h->replay); cudaFree(h->replay_off);
   cudaFree(h->err); cudaFree(h->stats); cudaFree(h->enc_blob);
   cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_rew); cudaFree(h->h_done);
+  cudaFree(h->h_fin); cudaFree(h->h_rank); cudaFree(h->h_scores); cudaFree(h->h_counts);
+  cudaFree(h->small_dev);
+  if (h->small_host) cudaFreeHost(h->small_host);
   cudaFree(h->d_bits);
   if (h->p_bits) cudaFreeHost(h->p_bits);
   delete h->pool;
@@ -332,23 +339,107 @@ static int obs_to_host(snk_env* h, uint8_t* obs_host, cudaStream_t s) {
   return SNK_OK;
 }
 
-extern "C" int snk_step_host(snk_env* h, const uint8_t* actions_host, uint8_t* obs_host,
-                             double* rewards_host, uint8_t* dones_host) {
+// Layout of the single output block used for small batches (all offsets 16-byte aligned).
+struct SmallLayout { size_t act, obs, rew, done, fin, rank, scores, counts, total; };
+static SmallLayout small_layout(const Dims& d) {
+  auto up = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t nn = (size_t)d.N * d.ns;
+  SmallLayout L;
+  L.act = 0;
+  L.obs = up(nn);
+  L.rew = L.obs + up((size_t)d.N * d.obs_env_bytes);
+  L.done = L.rew + up(nn * sizeof(double));
+  L.fin = L.done + up(nn);
+  L.rank = L.fin + up((size_t)d.N);
+  L.scores = L.rank + up(nn * sizeof(int32_t));
+  L.counts = L.scores + up(nn * sizeof(double));
+  L.total = L.counts + up(3 * nn * sizeof(int32_t));
+  return L;
+}
+
+static int step_host_small(snk_env* h, const SmallLayout& L, const uint8_t* actions_host, uint8_t* obs_host,
+                           double* rewards_host, uint8_t* dones_host, const snk_step_extra* xh) {
+  const Dims& d = h->d;
+  const size_t nn = (size_t)d.N * d.ns;
+  cudaStream_t s = h->own_stream;
+  if (!h->small_dev) CU(cudaMalloc(&h->small_dev, L.total));
+  if (!h->small_host) CU(cudaMallocHost(&h->small_host, L.total));
+  uint8_t* dv = h->small_dev;
+  uint8_t* hv = h->small_host;
+  memcpy(hv + L.act, actions_host, nn);
+  CU(cudaMemcpyAsync(dv + L.act, hv + L.act, nn, cudaMemcpyHostToDevice, s));
+  snk_step_extra xd;
+  memset(&xd, 0, sizeof xd);
+  if (xh) {
+    xd.finished = dv + L.fin; xd.rank = (int32_t*)(dv + L.rank); xd.episode_scores = (double*)(dv + L.scores);
+    xd.episode_steps = (int32_t*)(dv + L.counts); xd.episode_fruits = xd.episode_steps + nn; xd.episode_kills = xd.episode_fruits + nn;
+  }
+  int rc = snk_step(h, dv + L.act, obs_host ? dv + L.obs : nullptr, (double*)(dv + L.rew), dv + L.done, xh ? &xd : nullptr, s);
+  if (rc) return rc;
+  const size_t lo = obs_host ? L.obs : L.rew, hi = xh ? L.total : L.fin;
+  CU(cudaMemcpyAsync(hv + lo, dv + lo, hi - lo, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (obs_host) memcpy(obs_host, hv + L.obs, (size_t)d.N * d.obs_env_bytes);
+  memcpy(rewards_host, hv + L.rew, nn * sizeof(double));
+  memcpy(dones_host, hv + L.done, nn);
+  if (xh) {
+    if (xh->finished) memcpy(xh->finished, hv + L.fin, (size_t)d.N);
+    if (xh->rank) memcpy(xh->rank, hv + L.rank, nn * sizeof(int32_t));
+    if (xh->episode_scores) memcpy(xh->episode_scores, hv + L.scores, nn * sizeof(double));
+    if (xh->episode_steps) memcpy(xh->episode_steps, hv + L.counts, nn * sizeof(int32_t));
+    if (xh->episode_fruits) memcpy(xh->episode_fruits, hv + L.counts + nn * sizeof(int32_t), nn * sizeof(int32_t));
+    if (xh->episode_kills) memcpy(xh->episode_kills, hv + L.counts + 2 * nn * sizeof(int32_t), nn * sizeof(int32_t));
+  }
+  return SNK_OK;
+}
+
+extern "C" int snk_step_host_info(snk_env* h, const uint8_t* actions_host, uint8_t* obs_host,
+                                  double* rewards_host, uint8_t* dones_host, const snk_step_extra* xh) {
   if (!h) return fail(SNK_E_INVALID, "null handle");
   if (!actions_host || !rewards_host || !dones_host) return fail(SNK_E_INVALID, "actions, rewards and dones are required");
   CU(cudaSetDevice(h->device));
+  {
+    const SmallLayout L = small_layout(h->d);
+    if (L.total <= 64 * 1024) return step_host_small(h, L, actions_host, obs_host, rewards_host, dones_host, xh);
+  }
   int rc = ensure_mirrors(h);
   if (rc) return rc;
   const Dims& d = h->d;
+  const size_t nn = (size_t)d.N * d.ns;
   cudaStream_t s = h->own_stream;
-  CU(cudaMemcpyAsync(h->h_actions, actions_host, (size_t)d.N * d.ns, cudaMemcpyHostToDevice, s));
-  rc = snk_step(h, h->h_actions, obs_host ? h->h_obs : nullptr, h->h_rew, h->h_done, nullptr, s);
+  snk_step_extra xd;
+  memset(&xd, 0, sizeof xd);
+  if (xh) {                                    // device mirrors of the terminal-info outputs the caller asked for
+    if (!h->h_fin) CU(cudaMalloc(&h->h_fin, (size_t)d.N));
+    if (!h->h_rank) CU(cudaMalloc(&h->h_rank, nn * sizeof(int32_t)));
+    if (!h->h_scores) CU(cudaMalloc(&h->h_scores, nn * sizeof(double)));
+    if (!h->h_counts) CU(cudaMalloc(&h->h_counts, 3 * nn * sizeof(int32_t)));
+    if (xh->finished) xd.finished = h->h_fin;
+    if (xh->rank) xd.rank = h->h_rank;
+    if (xh->episode_scores) xd.episode_scores = h->h_scores;
+    if (xh->episode_steps) xd.episode_steps = h->h_counts;
+    if (xh->episode_fruits) xd.episode_fruits = h->h_counts + nn;
+    if (xh->episode_kills) xd.episode_kills = h->h_counts + 2 * nn;
+  }
+  CU(cudaMemcpyAsync(h->h_actions, actions_host, nn, cudaMemcpyHostToDevice, s));
+  rc = snk_step(h, h->h_actions, obs_host ? h->h_obs : nullptr, h->h_rew, h->h_done, xh ? &xd : nullptr, s);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(rewards_host, h->h_rew, (size_t)d.N * d.ns * sizeof(double), cudaMemcpyDeviceToHost, s));
-  CU(cudaMemcpyAsync(dones_host, h->h_done, (size_t)d.N * d.ns, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(rewards_host, h->h_rew, nn * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(dones_host, h->h_done, nn, cudaMemcpyDeviceToHost, s));
+  if (xd.finished) CU(cudaMemcpyAsync(xh->finished, xd.finished, (size_t)d.N, cudaMemcpyDeviceToHost, s));
+  if (xd.rank) CU(cudaMemcpyAsync(xh->rank, xd.rank, nn * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (xd.episode_scores) CU(cudaMemcpyAsync(xh->episode_scores, xd.episode_scores, nn * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (xd.episode_steps) CU(cudaMemcpyAsync(xh->episode_steps, xd.episode_steps, nn * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (xd.episode_fruits) CU(cudaMemcpyAsync(xh->episode_fruits, xd.episode_fruits, nn * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (xd.episode_kills) CU(cudaMemcpyAsync(xh->episode_kills, xd.episode_kills, nn * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   if (obs_host) return obs_to_host(h, obs_host, s);
   CU(cudaStreamSynchronize(s));
   return SNK_OK;
+}
+
+extern "C" int snk_step_host(snk_env* h, const uint8_t* actions_host, uint8_t* obs_host,
+                             double* rewards_host, uint8_t* dones_host) {
+  return snk_step_host_info(h, actions_host, obs_host, rewards_host, dones_host, nullptr);
 }
 
 extern "C" int snk_reset_host(snk_env* h, uint8_t* obs_host) {

@@ -296,8 +296,20 @@ class SnakeEnv:
         self.obs_ch = b.obs_ch
         self.action_space = Discrete(len(self.action_dict) * self.num_snakes)             # snake_env.py:107-109
         self.observation_space = Box(self.low, self.high, b.obs_shape, np.uint8)          # snake_env.py:115-129
-        self._actions = torch.zeros((1, self.num_snakes), dtype=torch.uint8, device=b.device)
-        self._alive = np.zeros(self.num_snakes, dtype=bool)
+        # host buffers of the single-environment call: one C-ABI call per step (snk_step_host_info: actions
+        # in, step, observation / rewards / dones / terminal info out, one synchronisation)
+        ns = self.num_snakes
+        self._h_act = np.zeros((1, ns), dtype=np.uint8)
+        self._h_obs = np.empty((1,) + b.obs_shape, dtype=np.uint8)
+        self._h_rew = np.empty((1, ns), dtype=np.float64)
+        self._h_done = np.empty((1, ns), dtype=np.uint8)
+        self._h_fin = np.zeros(1, dtype=np.uint8)
+        self._h_rank = np.zeros((1, ns), dtype=np.int32)
+        self._h_scores = np.zeros((1, ns), dtype=np.float64)
+        self._h_counts = np.zeros((3, 1, ns), dtype=np.int32)
+        self._xh = SnkStepExtra(self._h_fin.ctypes.data, self._h_rank.ctypes.data, self._h_scores.ctypes.data,
+                                self._h_counts[0].ctypes.data, self._h_counts[1].ctypes.data,
+                                self._h_counts[2].ctypes.data)
 
     @property
     def unwrapped(self):
@@ -310,36 +322,39 @@ class SnakeEnv:
         self._batch.close()
 
     def reset(self):
-        obs = self._batch.reset()[0].cpu().numpy()
-        self._alive[:] = True
-        return obs
+        check(lib.snk_reset_host(self._batch._h, self._h_obs.ctypes.data_as(C.c_void_p)))
+        return self._h_obs[0].copy()
+
+    def _alive_now(self):
+        return self._batch.get_state()['alive'][0].cpu().numpy().astype(bool)
 
     def step(self, actions):
         if isinstance(actions, int):
             actions = [actions]
         assert len(actions) == self.num_snakes                                            # snake_env.py:313
-        acts = []
+        alive = None
         for i, ac in enumerate(actions):
             if isinstance(ac, np.ndarray):
                 ac = ac.item()
             if self.observer == 'human':              # unknown actions keep the direction (:610-632)
-                acts.append(int(ac) if ac in (0, 1, 2, 3, 4) else 0)
+                self._h_act[0, i] = int(ac) if ac in (0, 1, 2, 3, 4) else 0
                 continue
-            if self._alive[i] and ac not in self.action_dict:
-                raise KeyError(ac)                                                        # snake_env.py:606
-            acts.append(int(ac) if ac in self.action_dict else 0)
-        self._actions.copy_(torch.tensor([acts], dtype=torch.uint8))
-        obs, rew, done, info = self._batch.step(self._actions)
-        st = self._batch.get_state()
-        self._alive[:] = st['alive'][0].cpu().numpy().astype(bool)
-        out_info = {}
-        if bool(info['finished'][0]):
-            out_info['rank'] = [int(r) for r in info['rank'][0].cpu().numpy()]
-            out_info['episode_scores'] = info['episode_scores'][0].cpu().numpy().copy()
-            for k in ('episode_steps', 'episode_fruits', 'episode_kills'):
-                out_info[k] = info[k][0].cpu().numpy().astype(np.float64)
-        return (obs[0].cpu().numpy(), [float(r) for r in rew[0].cpu().numpy()],
-                [bool(d) for d in done[0].cpu().numpy()], out_info)
+            if ac not in self.action_dict:            # the reference looks the action up only for live snakes
+                alive = self._alive_now() if alive is None else alive
+                if alive[i]:
+                    raise KeyError(ac)                                                    # snake_env.py:606
+                ac = 0
+            self._h_act[0, i] = int(ac)
+        p = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
+        check(lib.snk_step_host_info(self._batch._h, p(self._h_act), p(self._h_obs), p(self._h_rew), p(self._h_done),
+                                     C.byref(self._xh)))
+        info = {}
+        if self._h_fin[0]:
+            info['rank'] = [int(r) for r in self._h_rank[0]]
+            info['episode_scores'] = self._h_scores[0].copy()
+            for k, name in enumerate(('episode_steps', 'episode_fruits', 'episode_kills')):
+                info[name] = self._h_counts[k, 0].astype(np.float64)
+        return (self._h_obs[0].copy(), [float(r) for r in self._h_rew[0]], [bool(d) for d in self._h_done[0]], info)
 
     @property
     def grid(self):

@@ -475,6 +475,43 @@ def test_gpu_pack_obs_roundtrip():
         b.pack_obs(obs[..., :4])
 
 
+@pytest.mark.parametrize('N', [3, 700])
+def test_gpu_step_host_info_matches_device_path(N):
+    """snk_step_host_info: host buffers incl. the terminal info arrays (one output block for a few
+    environments, separate copies for many) against the device-pointer call."""
+    import ctypes as C
+    from marl_snake_b200 import SnakeBatch
+    from marl_snake_b200._lib import SnkStepExtra, check, lib
+    ns = 3
+    kw = dict(num_snakes=ns, height=9, width=11, vision_range=2, frame_stack=2, max_episode_steps=6, seed=13)
+    dev, host = SnakeBatch(N, **kw), SnakeBatch(N, **kw)
+    obs = np.empty((N,) + host.obs_shape, np.uint8)
+    rew, done = np.empty((N, ns), np.float64), np.empty((N, ns), np.uint8)
+    fin, rank = np.zeros(N, np.uint8), np.zeros((N, ns), np.int32)
+    sc, cnt = np.zeros((N, ns), np.float64), np.zeros((3, N, ns), np.int32)
+    xh = SnkStepExtra(fin.ctypes.data, rank.ctypes.data, sc.ctypes.data, cnt[0].ctypes.data, cnt[1].ctypes.data,
+                      cnt[2].ctypes.data)
+    p = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
+    check(lib.snk_reset_host(host._h, p(obs)))
+    assert np.array_equal(dev.reset().cpu().numpy(), obs)
+    rng = np.random.RandomState(2)
+    seen = 0
+    for t in range(20):
+        a = rng.randint(0, 3, size=(N, ns)).astype(np.uint8)
+        check(lib.snk_step_host_info(host._h, p(a), p(obs), p(rew), p(done), C.byref(xh)))
+        o, r, d, info = dev.step(torch.as_tensor(a).cuda())
+        assert np.array_equal(o.cpu().numpy(), obs) and np.array_equal(r.cpu().numpy(), rew)
+        assert np.array_equal(d.cpu().numpy(), done.astype(bool))
+        f = info['finished'].cpu().numpy()
+        assert np.array_equal(f, fin.astype(bool))
+        seen += int(f.sum())
+        assert np.array_equal(info['rank'].cpu().numpy()[f], rank[f])
+        assert np.array_equal(info['episode_scores'].cpu().numpy()[f], sc[f])
+        for k, name in enumerate(('episode_steps', 'episode_fruits', 'episode_kills')):
+            assert np.array_equal(info[name].cpu().numpy()[f], cnt[k][f])
+    assert seen >= N * 2                                   # the step cap ended every env at least twice
+
+
 def test_gpu_state_roundtrip():
     """get_state -> set_state on a second batch reproduces the trajectory (checkpoint / restore)."""
     from marl_snake_b200 import SnakeBatch
