@@ -4,10 +4,13 @@ marlenv/wrappers.py (make_snake :203-223, SingleAgent :84-105, SingleMultiAgent 
 The reference vectorises with one OS process per environment (gym AsyncVectorEnv, :211-212); here
 `num_envs > 1` is one `SnakeBatch` on the GPU with the reference worker's auto-reset rule (:138-146).
 """
+import ctypes as C
+
 import numpy as np
 import torch
 
-from .env import ACTION_ANGLE_DICT, SnakeBatch
+from ._lib import SnkStepExtra, check, lib
+from .env import SnakeBatch
 from .registration import make
 from .spaces import Box, Discrete
 
@@ -110,12 +113,14 @@ class RenderGUI(_Wrapper):
 
 class VectorSnakeEnv:
     """`num_envs` environments stepped by one kernel launch.  By default returns host arrays shaped like
-    gym's vector API (obs [N, ns, h, w, c], rewards [N, ns], dones [N, ns], tuple of info dicts);
+    gym's vector API (obs [N, ns, h, w, c], rewards [N, ns], dones [N, ns], tuple of info dicts) through the
+    host-buffer C-ABI call (`snk_step_host_info`: pinned buffers, packed PCIe transport for large batches);
+    `copy=False` hands out the env's own buffers instead of copies (gym's `AsyncVectorEnv(copy=...)`).
     `output='torch'` returns the batch's CUDA tensors and a dict of info tensors instead."""
 
-    def __init__(self, num_envs, num_snakes, output='numpy', **kwargs):
+    def __init__(self, num_envs, num_snakes, output='numpy', copy=True, **kwargs):
         self.batch = SnakeBatch(num_envs, num_snakes=num_snakes, auto_reset=True, **kwargs)
-        self.num_envs, self.num_snakes, self.output = num_envs, num_snakes, output
+        self.num_envs, self.num_snakes, self.output, self.copy = num_envs, num_snakes, output, copy
         b = self.batch
         self.action_dict = b.action_dict
         self.vision_range, self.obs_ch, self.grid_shape = b.vision_range, b.obs_ch, b.grid_shape
@@ -124,36 +129,65 @@ class VectorSnakeEnv:
         self.observation_space = Box(0, 255, (num_envs, *single), np.uint8)
         self.single_action_space = self.action_space = Discrete(len(self.action_dict))
         self._act = torch.zeros((num_envs, num_snakes), dtype=torch.uint8, device=b.device)
+        if output != 'torch':
+            N, ns = num_envs, num_snakes
+
+            def host(shape, dtype):
+                return torch.zeros(shape, dtype=dtype).pin_memory().numpy()
+            self._h_act = host((N, ns), torch.uint8)
+            self._h_obs = host((N,) + b.obs_shape, torch.uint8)
+            self._h_rew, self._h_done = host((N, ns), torch.float64), host((N, ns), torch.uint8)
+            self._h_fin, self._h_rank = host((N,), torch.uint8), host((N, ns), torch.int32)
+            self._h_scores, self._h_counts = host((N, ns), torch.float64), host((3, N, ns), torch.int32)
+            self._xh = SnkStepExtra(self._h_fin.ctypes.data, self._h_rank.ctypes.data, self._h_scores.ctypes.data,
+                                    self._h_counts[0].ctypes.data, self._h_counts[1].ctypes.data,
+                                    self._h_counts[2].ctypes.data)
 
     def _squeeze(self, x):
         return x[:, 0] if self.num_snakes == 1 else x
 
+    def _out(self, x):
+        x = self._squeeze(x)
+        return x.copy() if self.copy else x
+
     def reset(self):
-        obs = self._squeeze(self.batch.reset())
-        return obs if self.output == 'torch' else obs.cpu().numpy()
+        if self.output == 'torch':
+            return self._squeeze(self.batch.reset())
+        check(lib.snk_reset_host(self.batch._h, self._h_obs.ctypes.data_as(C.c_void_p)))
+        return self._out(self._h_obs)
 
     def step(self, actions):
-        if isinstance(actions, torch.Tensor) and actions.is_cuda:
-            self._act.copy_(actions.reshape(self.num_envs, self.num_snakes))
-        else:
-            self._act.copy_(torch.as_tensor(np.asarray(actions, dtype=np.uint8).reshape(self.num_envs, self.num_snakes)))
-        obs, rew, done, info = self.batch.step(self._act)
-        obs, rew, done = self._squeeze(obs), self._squeeze(rew), self._squeeze(done)
         if self.output == 'torch':
-            return obs, rew, done, info
-        self.batch.raise_on_device_errors()
-        fin = info['finished'].cpu().numpy()
+            if isinstance(actions, torch.Tensor) and actions.is_cuda:
+                self._act.copy_(actions.reshape(self.num_envs, self.num_snakes))
+            else:
+                self._act.copy_(torch.as_tensor(np.asarray(actions, dtype=np.uint8).reshape(self.num_envs, self.num_snakes)))
+            obs, rew, done, info = self.batch.step(self._act)
+            return self._squeeze(obs), self._squeeze(rew), self._squeeze(done), info
+        if isinstance(actions, torch.Tensor):
+            actions = actions.cpu().numpy()
+        a = np.asarray(actions).reshape(self.num_envs, self.num_snakes)
+        if self.batch.observer == 'snake' and ((a < 0) | (a > 2)).any():
+            # the reference looks an action up only for live snakes (snake_env.py:321, 606)
+            alive = self.batch.get_state()['alive'].cpu().numpy().astype(bool)
+            bad = ((a < 0) | (a > 2)) & alive
+            if bad.any():
+                raise KeyError(int(a[bad][0]))
+            a = np.where((a < 0) | (a > 2), 0, a)
+        elif self.batch.observer == 'human':
+            a = np.where((a < 0) | (a > 4), 0, a)
+        self._h_act[...] = a
+        p = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
+        check(lib.snk_step_host_info(self.batch._h, p(self._h_act), p(self._h_obs), p(self._h_rew), p(self._h_done),
+                                     C.byref(self._xh)))
         infos = [{} for _ in range(self.num_envs)]
-        if fin.any() and self.num_snakes > 1:
-            host = {k: info[k].cpu().numpy() for k in ('rank', 'episode_scores', 'episode_steps',
-                                                       'episode_fruits', 'episode_kills')}
-            for e in np.nonzero(fin)[0]:
-                infos[e] = dict(rank=[int(r) for r in host['rank'][e]],
-                                episode_scores=host['episode_scores'][e].copy(),
-                                episode_steps=host['episode_steps'][e].astype(np.float64),
-                                episode_fruits=host['episode_fruits'][e].astype(np.float64),
-                                episode_kills=host['episode_kills'][e].astype(np.float64))
-        return obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy(), tuple(infos)
+        if self.num_snakes > 1 and self._h_fin.any():
+            for e in np.nonzero(self._h_fin)[0]:
+                infos[e] = dict(rank=[int(r) for r in self._h_rank[e]], episode_scores=self._h_scores[e].copy(),
+                                episode_steps=self._h_counts[0, e].astype(np.float64),
+                                episode_fruits=self._h_counts[1, e].astype(np.float64),
+                                episode_kills=self._h_counts[2, e].astype(np.float64))
+        return self._out(self._h_obs), self._out(self._h_rew), self._out(self._h_done.view(np.bool_)), tuple(infos)
 
     def close(self):
         self.batch.close()
@@ -168,7 +202,7 @@ def make_snake(num_envs=1, num_snakes=4, env_id="Snake-v1", **kwargs):
         action_n = env.action_space.n
     else:
         wrapper = SingleMultiAgent if num_snakes > 1 else SingleAgent
-        for k in ('output',):
+        for k in ('output', 'copy'):
             kwargs.pop(k, None)
         env = wrapper(make(env_id, num_snakes=num_snakes, **kwargs))
         action_n = env.action_space.n

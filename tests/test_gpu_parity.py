@@ -155,6 +155,35 @@ def test_dropin_api():
     assert r.shape == (16, 4) and d.shape == (16, 4) and len(infos) == 16
 
 
+def test_vector_env_numpy_equals_torch_output():
+    """make_snake(num_envs > 1): the host-array mode (snk_step_host_info, pinned buffers) and the CUDA-tensor
+    mode step the same trajectories; infos carry the terminal dict of finished envs (wrappers.py:138-146)."""
+    from marl_snake_b200 import make_snake
+    kw = dict(num_snakes=3, height=10, width=10, vision_range=3, max_episode_steps=9, seed=5)
+    a_env, _, _, _ = make_snake(num_envs=40, **kw)
+    b_env, _, _, _ = make_snake(num_envs=40, output='torch', **kw)
+    assert np.array_equal(a_env.reset(), b_env.reset().cpu().numpy())
+    rng = np.random.RandomState(1)
+    ended = 0
+    for t in range(30):
+        act = rng.randint(0, 3, size=(40, 3))
+        o1, r1, d1, infos = a_env.step(act)
+        o2, r2, d2, info2 = b_env.step(act)
+        assert np.array_equal(o1, o2.cpu().numpy()) and np.array_equal(r1, r2.cpu().numpy())
+        assert d1.dtype == np.bool_ and np.array_equal(d1, d2.cpu().numpy())
+        fin = info2['finished'].cpu().numpy()
+        for e in range(40):
+            assert bool(infos[e]) == bool(fin[e])
+            if fin[e]:
+                ended += 1
+                assert infos[e]['rank'] == [int(x) for x in info2['rank'][e].cpu().numpy()]
+                assert np.array_equal(infos[e]['episode_scores'], info2['episode_scores'][e].cpu().numpy())
+    assert ended >= 80
+    with pytest.raises(KeyError):
+        a_env.step(np.full((40, 3), 3))
+    a_env.close(); b_env.close()
+
+
 def test_dropin_human_observer():
     """observer='human': five absolute actions, Discrete(5*ns) on the env, Discrete(5) behind the wrapper
     (snake_env.py:101-109, wrappers.py:111), unknown actions are no-ops instead of KeyError (:610-632)."""
