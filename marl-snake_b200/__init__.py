@@ -9,8 +9,8 @@ from .registration import make, register_with_gym                # noqa: F401
 from .wrappers import (RenderGUI, SingleAgent, SingleMultiAgent,  # noqa: F401
                        VectorSnakeEnv, make_snake)
 from .dist import shard_range, allreduce_stats                    # noqa: F401
-from .rollout import DeviceReplayBuffer, collect, epsilon_greedy   # noqa: F401
+from .rollout import DeviceReplayBuffer, GraphedSteps, collect, epsilon_greedy, unpack_obs   # noqa: F401
 
 __all__ = ['SnakeBatch', 'SnakeEnv', 'CoopSnakeEnv', 'make', 'make_snake', 'SingleAgent', 'SingleMultiAgent',
            'VectorSnakeEnv', 'RenderGUI', 'shard_range', 'allreduce_stats', 'DeviceReplayBuffer', 'collect',
-           'epsilon_greedy', 'lib', 'LIB_PATH', 'SnkError']
+           'epsilon_greedy', 'GraphedSteps', 'unpack_obs', 'lib', 'LIB_PATH', 'SnkError']

@@ -19,12 +19,21 @@ def epsilon_greedy(q_values, epsilon, generator=None):
     return torch.where(explore, rand, greedy).to(torch.uint8)
 
 
-class DeviceReplayBuffer:
-    """Fixed-capacity ring of transitions in device memory; observations stay uint8 (NHWC)."""
+def unpack_obs(bits):
+    """Inverse of SnakeBatch.pack_obs on the device: uint8 [..., F] channel-bit bytes -> uint8 0/1 [..., 8*F]."""
+    shifts = torch.arange(8, device=bits.device, dtype=torch.uint8)
+    return ((bits.unsqueeze(-1) >> shifts) & 1).reshape(*bits.shape[:-1], bits.shape[-1] * 8)
 
-    def __init__(self, capacity, obs_shape, device):
-        self.capacity, self.size, self.pos = int(capacity), 0, 0
-        self.obs = torch.empty((capacity, *obs_shape), dtype=torch.uint8, device=device)
+
+class DeviceReplayBuffer:
+    """Fixed-capacity ring of transitions in device memory; observations stay uint8 (NHWC).  With
+    `pack=batch` (a SnakeBatch) observations are stored as channel bits -- one byte per (cell, frame), an
+    eighth of the memory -- packed by the library's kernel on push and widened again on sample."""
+
+    def __init__(self, capacity, obs_shape, device, pack=None):
+        self.capacity, self.size, self.pos, self.pack = int(capacity), 0, 0, pack
+        stored = (*obs_shape[:-1], obs_shape[-1] // 8) if pack is not None else tuple(obs_shape)
+        self.obs = torch.empty((capacity, *stored), dtype=torch.uint8, device=device)
         self.next_obs = torch.empty_like(self.obs)
         self.action = torch.empty(capacity, dtype=torch.uint8, device=device)
         self.reward = torch.empty(capacity, dtype=torch.float32, device=device)
@@ -38,6 +47,8 @@ class DeviceReplayBuffer:
         if n > self.capacity:
             obs, action, reward, next_obs, done = (t[-self.capacity:] for t in (obs, action, reward, next_obs, done))
             n = self.capacity
+        if self.pack is not None:
+            obs, next_obs = self.pack.pack_obs(obs.contiguous()), self.pack.pack_obs(next_obs.contiguous())
         idx = (self.pos + torch.arange(n, device=obs.device)) % self.capacity
         self.obs[idx], self.next_obs[idx] = obs, next_obs
         self.action[idx], self.reward[idx], self.done[idx] = action, reward.to(torch.float32), done
@@ -46,7 +57,44 @@ class DeviceReplayBuffer:
 
     def sample(self, batch_size, generator=None):
         idx = torch.randint(0, self.size, (batch_size,), device=self.obs.device, generator=generator)
-        return self.obs[idx], self.action[idx], self.reward[idx], self.next_obs[idx], self.done[idx]
+        obs, next_obs = self.obs[idx], self.next_obs[idx]
+        if self.pack is not None:
+            obs, next_obs = unpack_obs(obs), unpack_obs(next_obs)
+        return obs, self.action[idx], self.reward[idx], next_obs, self.done[idx]
+
+
+class GraphedSteps:
+    """T environment steps captured once in a CUDA graph and replayed with a single launch call.
+
+    A step is one kernel with no host synchronisation, so a short batch (BASELINE cfg2: 4 096 envs, ~20 us of
+    work per step) is bound by launch latency; replaying a captured sequence removes the per-step launch
+    overhead (profiles/README.md: 21 -> 19 us per step).  `actions` is a uint8 CUDA tensor [T, N, ns] that
+    the caller refills between replays; after a replay the batch's own obs / reward / done buffers hold the
+    last step's outputs and, when `keep` is true, `rewards[T, N, ns]` / `dones[T, N, ns]` hold every step's."""
+
+    def __init__(self, batch, actions, keep=True):
+        if actions.dtype != torch.uint8 or actions.dim() != 3 or tuple(actions.shape[1:]) != (batch.num_envs, batch.num_snakes):
+            raise ValueError('actions must be a uint8 CUDA tensor of shape [T, num_envs, num_snakes]')
+        self.batch, self.actions, self.T = batch, actions, actions.shape[0]
+        self.rewards = torch.empty((self.T, batch.num_envs, batch.num_snakes), dtype=torch.float64, device=actions.device) if keep else None
+        self.dones = torch.empty((self.T, batch.num_envs, batch.num_snakes), dtype=torch.bool, device=actions.device) if keep else None
+        stream = torch.cuda.Stream(device=actions.device)
+        stream.wait_stream(torch.cuda.current_stream(actions.device))
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(stream):
+            with torch.cuda.graph(self.graph, stream=stream):
+                for t in range(self.T):
+                    obs, rew, done, _ = batch.step(actions[t], want_info=False)
+                    if keep:
+                        self.rewards[t].copy_(rew)
+                        self.dones[t].copy_(done)
+        torch.cuda.current_stream(actions.device).wait_stream(stream)
+        self.obs = obs
+
+    def replay(self):
+        """Run the T captured steps (asynchronous; outputs are valid on the current stream afterwards)."""
+        self.graph.replay()
+        return self.obs, self.rewards, self.dones
 
 
 @torch.no_grad()

@@ -377,6 +377,45 @@ def test_device_rollout_with_q_network():
     assert b.device_errors() == 0
 
 
+def test_packed_replay_buffer_and_graphed_steps():
+    """N1 plumbing: a replay buffer that stores channel bits (packed by the library, an eighth of the memory)
+    returns the same transitions as the unpacked one; T steps captured in a CUDA graph equal T eager steps."""
+    from marl_snake_b200 import DeviceReplayBuffer, GraphedSteps, SnakeBatch, unpack_obs
+    N, ns, T = 300, 4, 12
+    kw = dict(num_snakes=ns, vision_range=5, frame_stack=2, seed=6)
+    b = SnakeBatch(N, **kw)
+    plain = DeviceReplayBuffer(5000, b.obs_shape[1:], b.device)
+    packed = DeviceReplayBuffer(5000, b.obs_shape[1:], b.device, pack=b)
+    assert packed.obs.numel() * 8 == plain.obs.numel()
+    g = torch.Generator(device='cuda').manual_seed(3)
+    obs = b.reset().clone()
+    for t in range(6):
+        act = torch.randint(0, 3, (N, ns), dtype=torch.uint8, device='cuda', generator=g)
+        nxt, rew, done, _ = b.step(act, copy=True)
+        flat = lambda x: x.reshape(N * ns, *x.shape[2:])  # noqa: E731
+        for buf in (plain, packed):
+            buf.push(flat(obs), act.reshape(-1), rew.reshape(-1), flat(nxt), done.reshape(-1))
+        obs = nxt
+    assert torch.equal(unpack_obs(packed.obs[:packed.size]), plain.obs[:plain.size])
+    s1 = plain.sample(64, generator=torch.Generator(device='cuda').manual_seed(1))
+    s2 = packed.sample(64, generator=torch.Generator(device='cuda').manual_seed(1))
+    assert all(torch.equal(x, y) for x, y in zip(s1, s2))
+
+    eager, graphed = SnakeBatch(N, **kw), SnakeBatch(N, **kw)
+    eager.reset(); graphed.reset()
+    actions = torch.randint(0, 3, (T, N, ns), dtype=torch.uint8, device='cuda', generator=g)
+    gs = GraphedSteps(graphed, actions)                     # capture runs nothing
+    for rep in range(2):
+        want_r, want_d = [], []
+        for t in range(T):
+            o, r, d, _ = eager.step(actions[t], copy=True)
+            want_r.append(r); want_d.append(d)
+        got_o, got_r, got_d = gs.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(got_o, o) and torch.equal(got_r, torch.stack(want_r)) and torch.equal(got_d, torch.stack(want_d))
+        actions.copy_(torch.randint(0, 3, (T, N, ns), dtype=torch.uint8, device='cuda', generator=g))
+
+
 def test_gpu_long_spawn_pose_matches_oracle():
     """snake_length 6 on a 7x9 grid: bent spawn poses and the head-boxed pruning of the DFS table."""
     kw = dict(height=7, width=9, num_snakes=2, snake_length=6, vision_range=2, num_fruits=3)
