@@ -13,6 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from marl_snake_b200 import SnakeBatch  # noqa: E402
 
+WANT_OBS = os.environ.get('BENCH_NO_OBS', '0') != '1'      # BENCH_NO_OBS=1: rules + record traffic only
 CFG4_REW = {'fruit': 10.0, 'kill': 1.0, 'lose': -1.0, 'win': 0.1, 'time': -0.001}
 CONFIGS = {
     'cfg2': dict(num_envs=4096, height=20, width=20, num_snakes=4, snake_length=3),
@@ -60,7 +61,7 @@ def run(name, kw, steps, graph=False):
     else:
         e0.record()
         for t in range(steps):
-            b.step(pool[(300 + t) % npool], want_info=False)
+            b.step(pool[(300 + t) % npool], want_info=False, want_obs=WANT_OBS)
         e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
