@@ -318,6 +318,36 @@ def test_gpu_tile_modes(monkeypatch, coop, kw, N):
     be.close()
 
 
+@pytest.mark.parametrize('knob', ['SNK_TMA=0', 'SNK_ENC_LEGACY=1', 'SNK_NO_TABLE=1', 'SNK_TMA=0,SNK_COOP=0'])
+@pytest.mark.parametrize('kw,N', [
+    (dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5), 1500),
+    (dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5, frame_stack=4), 300),
+    (dict(height=14, width=12, num_snakes=3, snake_length=3), 200),
+])
+def test_gpu_alternative_code_paths(monkeypatch, knob, kw, N):
+    """The A/B switches of INTEGRATION.md section 6 select real code paths (plain loads / stores instead of
+    TMA bulk copies, the table-driven or index-arithmetic encode instead of the register / direct ones);
+    each must give the same bytes as the default."""
+    from hostsim_util import HostSim
+    for kv in knob.split(','):
+        k, v = kv.split('=')
+        monkeypatch.setenv(k, v)
+    ns = kw['num_snakes']
+    hs = HostSim(N, kw, rng_mode=0, auto_reset=1, seed=8)
+    be = GpuBackend(N, kw, rng_mode=0, auto_reset=1, seed=8)
+    assert np.array_equal(hs.reset(), be.reset())
+    rng = np.random.RandomState(4)
+    for t in range(60):
+        a = rng.randint(0, 3, size=(N, ns)).astype(np.uint8)
+        o1, r1, d1, _ = hs.step(a)
+        o2, r2, d2, _ = be.step(a)
+        assert np.array_equal(r1, r2) and np.array_equal(d1, d2.astype(np.uint8)), t
+        assert np.array_equal(o1, o2), t
+    assert np.array_equal(hs.grid()[0], be.grid()[0])
+    assert be.errors() == 0
+    be.close()
+
+
 @pytest.mark.parametrize('kw,N,steps', [
     (dict(height=80, width=90, num_snakes=2, snake_length=3, vision_range=3, num_fruits=20), 6, 60),
     (dict(height=200, width=201, num_snakes=4, snake_length=4, vision_range=6, num_fruits=32), 3, 40),
