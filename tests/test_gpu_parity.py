@@ -376,6 +376,58 @@ def test_gpu_large_grids(kw, N, steps):
     be.close()
 
 
+def _fuzz_configs(n, seed):
+    rng = np.random.RandomState(seed)
+    out = []
+    while len(out) < n:
+        H, W = int(rng.randint(6, 41)), int(rng.randint(6, 41))
+        ns, K = int(rng.randint(1, 13)), int(rng.randint(2, 7))
+        if ns * K * 6 > (H - 2) * (W - 2):
+            continue                                          # keep spawn rejection sampling cheap
+        V = [None, 1, 2, 3, 4, 5, 6, 8][rng.randint(0, 8)]
+        kw = dict(height=H, width=W, num_snakes=ns, snake_length=K, vision_range=V,
+                  frame_stack=int([1, 1, 1, 2, 3, 4, 5][rng.randint(0, 7)]),
+                  num_fruits=int(rng.randint(0, min(32, (H - 2) * (W - 2) // 4) + 1)),
+                  max_episode_steps=int([10000, 10000, 12, 5][rng.randint(0, 4)]),
+                  observer=['snake', 'snake', 'human'][rng.randint(0, 3)],
+                  reward_dict={'fruit': float(rng.randint(1, 9)), 'kill': 0.25 * rng.randint(0, 9), 'lose': -0.125 * rng.randint(0, 9),
+                               'win': 0.5 * rng.randint(0, 5), 'time': -0.001 * rng.randint(0, 5)})
+        out.append((kw, int(rng.randint(0, 2)), int([1, 7, 40, 130][rng.randint(0, 4)])))
+    return out
+
+
+FUZZ_CASES = int(__import__('os').environ.get('SNK_FUZZ_CASES', 48))      # soak runs: SNK_FUZZ_CASES=400 SNK_FUZZ_SEED=7
+FUZZ_SEED = int(__import__('os').environ.get('SNK_FUZZ_SEED', 20240611))
+
+
+@pytest.mark.parametrize('case', range(FUZZ_CASES))
+def test_gpu_fuzz_shapes(case):
+    """Seeded random shapes (grid 6..40, 1..12 snakes, length 2..6, vision None..8, frame_stack 1..5, fruit
+    counts 0..32, step caps, both done rules and observers, odd batch sizes) against the host build of the rule
+    source in Philox mode: every output of every step bit-exact."""
+    from hostsim_util import HostSim
+    kw, done_mode, N = _fuzz_configs(FUZZ_CASES, FUZZ_SEED)[case]
+    ns = kw['num_snakes']
+    hs = HostSim(N, kw, rng_mode=0, auto_reset=1, seed=1000 + case, done_mode=done_mode)
+    be = GpuBackend(N, kw, rng_mode=0, auto_reset=1, seed=1000 + case, done_mode=done_mode)
+    assert np.array_equal(hs.reset(), be.reset()), kw
+    rng = np.random.RandomState(case)
+    n_act = 5 if kw['observer'] == 'human' else 3
+    for t in range(50):
+        a = rng.randint(0, n_act, size=(N, ns)).astype(np.uint8)
+        o1, r1, d1, i1 = hs.step(a)
+        o2, r2, d2, i2 = be.step(a)
+        assert np.array_equal(r1, r2) and np.array_equal(d1, d2.astype(np.uint8)), (t, kw)
+        assert np.array_equal(o1, o2), (t, kw)
+        f = i1['finished'].astype(bool)
+        assert np.array_equal(f, i2['finished']), (t, kw)
+        for k in ('rank', 'episode_scores', 'episode_steps', 'episode_fruits', 'episode_kills'):
+            assert np.array_equal(i1[k][f], i2[k][f]), (k, t, kw)
+        assert np.array_equal(hs.grid()[0], be.grid()[0]), (t, kw)
+    assert hs.errors() == 0 and be.errors() == 0
+    hs.close(); be.close()
+
+
 def test_render_export_and_gui_wrapper():
     """N3: one environment's state exported to the host renderers (render_fancy / rgb_array / RenderGUI)."""
     from marl_snake_b200 import RenderGUI, make_snake
