@@ -37,6 +37,19 @@ def test_hostsim_philox_matches_oracle(kw):
     hs.close()
 
 
+@pytest.mark.parametrize('case', range(24))
+def test_hostsim_fuzz_matches_oracle(case):
+    """Seeded random small shapes, Philox mode: the device rule source (host build) against the oracle.  The
+    GPU suite fuzzes libsnk.so against the same host build on larger shapes, closing the chain
+    reference -> oracle -> rule source -> kernels."""
+    from test_oracle_vs_golden import small_fuzz_configs
+    kw, _ = small_fuzz_configs(24, 4242)[case]
+    hs = check_against_oracle_philox(HostSim, kw, num_envs=5, steps=60, seed=31337 + case, env_id_offset=case,
+                                     action_seed=case)
+    assert hs.errors() == 0
+    hs.close()
+
+
 def test_bad_action_flag():
     hs = HostSim(1, dict(num_snakes=2), rng_mode=0, auto_reset=1)
     hs.reset()

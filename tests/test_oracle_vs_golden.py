@@ -87,14 +87,7 @@ def test_reward_dict_keys_and_action_errors():
 
 
 # ------------------------------------------------------------------ live reference (container only)
-@pytest.mark.needs_reference
-@pytest.mark.parametrize('kw', [
-    dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5),
-    dict(height=12, width=9, num_snakes=3, snake_length=4, vision_range=2, frame_stack=3,
-         reward_dict={'fruit': 1.5, 'kill': 2.0, 'lose': -3.0, 'win': 4.0, 'time': 0.1}),
-    dict(height=8, width=8, num_snakes=5, snake_length=2, num_fruits=7, max_episode_steps=25),
-])
-def test_same_seed_as_live_reference(kw):
+def _compare_with_live_reference(kw, env_id='Snake-v1', steps=400, n_actions=3):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, os.path.join(root, 'oracle', 'gym_stub'))
     sys.path.insert(1, '/root/reference/marlenv')
@@ -102,7 +95,7 @@ def test_same_seed_as_live_reference(kw):
         import gym
         import marlenv  # noqa: F401
         ns = kw['num_snakes']
-        acts = np.random.RandomState(5).randint(0, 3, size=(400, ns))
+        acts = np.random.RandomState(5).randint(0, n_actions, size=(steps, ns))
 
         def run(make):
             np.random.seed(42)
@@ -117,19 +110,63 @@ def test_same_seed_as_live_reference(kw):
                             np.asarray(env.grid).copy()))
             return out
 
-        ref = run(lambda: gym.make('Snake-v1', **kw))
-        mine = run(lambda: OracleSnakeEnv(**kw))
+        cls = CoopOracleSnakeEnv if env_id == 'SnakeCoop-v1' else OracleSnakeEnv
+        ref = run(lambda: gym.make(env_id, **kw))
+        mine = run(lambda: cls(**kw))
         assert np.array_equal(ref[0], mine[0])
         for t, (a, b) in enumerate(zip(ref[1:], mine[1:])):
-            assert np.array_equal(a[0], b[0]), t
-            assert a[1] == b[1] and a[2] == b[2] and a[3] == b[3] and a[4] == b[4], t
-            assert np.array_equal(a[5], b[5]), t
+            assert np.array_equal(a[0], b[0]), (t, kw)
+            assert a[1] == b[1] and a[2] == b[2] and a[3] == b[3] and a[4] == b[4], (t, kw)
+            assert np.array_equal(a[5], b[5]), (t, kw)
     finally:
         sys.path.remove(os.path.join(root, 'oracle', 'gym_stub'))
         sys.path.remove('/root/reference/marlenv')
         for m in [m for m in sys.modules if m == 'gym' or m.startswith('gym.') or m == 'marlenv'
                   or m.startswith('marlenv.')]:
             del sys.modules[m]
+
+
+@pytest.mark.needs_reference
+@pytest.mark.parametrize('kw', [
+    dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5),
+    dict(height=12, width=9, num_snakes=3, snake_length=4, vision_range=2, frame_stack=3,
+         reward_dict={'fruit': 1.5, 'kill': 2.0, 'lose': -3.0, 'win': 4.0, 'time': 0.1}),
+    dict(height=8, width=8, num_snakes=5, snake_length=2, num_fruits=7, max_episode_steps=25),
+])
+def test_same_seed_as_live_reference(kw):
+    _compare_with_live_reference(kw)
+
+
+def small_fuzz_configs(n, seed):
+    """Seeded random small shapes (the reference re-enumerates every spawn pose on each reset, so grids stay
+    <= 13 cells wide); shared with the host-simulation fuzz.  num_fruits >= 1: with 0 the reference's reset
+    executes `grid[None, None] = FRUIT` (snake_env.py:147-148 has no None guard), which paints the WHOLE grid,
+    walls included, and the snakes then walk out of the array -- a crash path, not a behaviour to match."""
+    rng = np.random.RandomState(seed)
+    out = []
+    while len(out) < n:
+        H, W = int(rng.randint(6, 14)), int(rng.randint(6, 14))
+        ns, K = int(rng.randint(1, 7)), int(rng.randint(2, 5))
+        if ns * K * 5 > (H - 2) * (W - 2):
+            continue
+        kw = dict(height=H, width=W, num_snakes=ns, snake_length=K,
+                  vision_range=[None, 1, 2, 3, 4][rng.randint(0, 5)], frame_stack=int([1, 1, 2, 3][rng.randint(0, 4)]),
+                  num_fruits=int(rng.randint(1, 9)), max_episode_steps=int([10000, 15, 6][rng.randint(0, 3)]),
+                  observer=['snake', 'snake', 'human'][rng.randint(0, 3)],
+                  reward_dict={'fruit': float(rng.randint(1, 9)), 'kill': 0.25 * rng.randint(0, 9),
+                               'lose': -0.125 * rng.randint(0, 9), 'win': 0.5 * rng.randint(0, 5),
+                               'time': -0.001 * rng.randint(0, 5)})
+        out.append((kw, ['Snake-v1', 'Snake-v1', 'SnakeCoop-v1'][rng.randint(0, 3)]))
+    return out
+
+
+@pytest.mark.needs_reference
+@pytest.mark.parametrize('case', range(24))
+def test_oracle_fuzz_vs_live_reference(case):
+    """The oracle against the unmodified reference under the same np.random seed on seeded random shapes,
+    both env ids and both observers."""
+    kw, env_id = small_fuzz_configs(24, 777)[case]
+    _compare_with_live_reference(kw, env_id, steps=150, n_actions=5 if kw['observer'] == 'human' else 3)
 
 
 def test_recording_roundtrip():
