@@ -984,7 +984,7 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
           for (int v = 0; v < ns; ++v) {
             uint8_t* outv = outq + (size_t)v * ohw * 8;
             if (kEnc == ENC_REG) encode_viewer_reg(p, sh, grid32, s_view[q * G + v], cw, v, outv, lut32);
-              else if (kEnc == ENC_DIRECT) encode_viewer_direct(sh, grid32, v, outv, lut32);
+            else if (kEnc == ENC_DIRECT) encode_viewer_direct(sh, grid32, v, outv, lut32);
             else encode_viewer_fs1(p, sh, base, grid32, v, outv, lut32);
           }
         }
