@@ -111,6 +111,8 @@ class SnakeBatch:
     def reset(self, mask=None, copy=False):
         """SnakeEnv.reset for all envs (or those with mask != 0). Returns uint8 [N, ns, oh, ow, 8*fs]."""
         if mask is not None:
+            if mask.numel() != self.num_envs:
+                raise ValueError('mask must have one entry per environment')
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
         check(lib.snk_reset(self._h, _ptr(mask), _ptr(self._obs), self._stream()))
         return self._obs.clone() if copy else self._obs
@@ -194,6 +196,12 @@ class SnakeBatch:
         def t(x, dtype, shape):
             return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).reshape(shape).to(dev).contiguous()
         cells = t(cells, torch.int32, (N, ns, -1))
+        H, W = self.grid_shape
+        length_h = np.asarray(length).reshape(N, ns)
+        if cells.shape[-1] < 2 or int(length_h.max(initial=0)) > cells.shape[-1] or int(length_h.min(initial=0)) < 0:
+            raise ValueError('length must be within 0..cells.shape[-1] (and cells hold at least two columns)')
+        if int(cells.min()) < 0 or int(cells.max()) >= H * W:
+            raise ValueError('cells must be flat indices into the H x W grid (pad unused entries with 0)')
         if episode_length is None:
             episode_length = np.zeros(N, dtype=np.int32)
         keep = dict(grid=t(grid, torch.uint8, (N, -1)), alive=t(alive, torch.uint8, (N, ns)),
