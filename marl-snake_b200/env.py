@@ -331,6 +331,7 @@ class SnakeEnv:
 
     def reset(self):
         check(lib.snk_reset_host(self._batch._h, self._h_obs.ctypes.data_as(C.c_void_p)))
+        self.frame_buffer = []                                                            # snake_env.py:151
         return self._h_obs[0].copy()
 
     def _alive_now(self):
@@ -380,6 +381,25 @@ class SnakeEnv:
         elif mode == 'rgb_array':
             from .render import rgb_from_grid
             return rgb_from_grid(self.grid)
+        elif mode == 'gif':                       # append a frame; save_gif() writes them out (snake_env.py:283-288)
+            from .render import image_from_grid
+            self.frame_buffer.append(image_from_grid(self.grid))
+
+    def save_gif(self, fp=None):
+        """Write the frames collected by render('gif') as an animated GIF (snake_env.py:419-436): to `fp`
+        (path or file object), or to ./tmp/<timestamp>.gif.  Returns fp."""
+        import datetime
+        import os
+        import warnings
+        if fp is None:
+            save_dir = os.path.join(os.getcwd(), 'tmp')
+            os.makedirs(save_dir, exist_ok=True)
+            fp = os.path.join(save_dir, '{}.gif'.format(datetime.datetime.now().strftime('%Y%m%d%H%M%S')))
+        if not getattr(self, 'frame_buffer', None):
+            warnings.warn("You must call render('gif') first. No images to save.")
+        else:
+            self.frame_buffer[0].save(fp, save_all=True, append_images=self.frame_buffer[1:], format='GIF', loop=0)
+        return fp
 
     def render_fancy(self, cell_size=40, save_path=None):
         """RGB frame of the current state (host-side visualisation; see render.py)."""

@@ -27,6 +27,16 @@ def rgb_from_grid(grid):
     return out
 
 
+def image_from_grid(grid, max_size=300):
+    """PIL image of the grid, each cell scaled so that the longer side is about max_size pixels (one frame of
+    render('gif'), grid_util.py:177-185)."""
+    from PIL import Image
+    grid = np.asarray(grid)
+    scale = max(max_size // max(grid.shape), 1)
+    rgb = np.repeat(np.repeat(rgb_from_grid(grid), scale, axis=0), scale, axis=1)
+    return Image.fromarray(rgb, 'RGB')
+
+
 def render_fancy(grid, heads=None, dirs=None, cell_size=40):
     """Upscaled frame: walls, round fruit, snake bodies, round heads with two eyes along the heading."""
     grid = np.asarray(grid)

@@ -442,6 +442,32 @@ def test_render_export_and_gui_wrapper():
     env.close()
 
 
+def test_gif_rendering_like_the_reference_tests(tmp_path, monkeypatch):
+    """marlenv/tests/test_snake.py:85-111: 100 random steps with render('gif'), then save_gif() to the default
+    ./tmp/<timestamp>.gif and to a file object."""
+    import io
+    import os
+    from PIL import Image
+    from marl_snake_b200 import make
+    monkeypatch.chdir(tmp_path)
+    env = make('Snake-v1', num_snakes=1, num_fruits=4, disable_env_checker=True,
+               reward_dict={'fruit': 1.0, 'kill': 0.0, 'lose': -10.0, 'win': 0.0, 'time': 0.0})
+    env.reset()
+    with pytest.warns(UserWarning):
+        env.save_gif(io.BytesIO())                       # nothing rendered yet
+    for _ in range(100):                                   # the reference's rollout keeps stepping a finished env too
+        env.render('gif')
+        env.step(int(np.random.randint(3)))
+    path = env.save_gif()
+    assert os.path.exists(path) and os.path.dirname(path) == os.path.join(str(tmp_path), 'tmp')
+    gif = Image.open(path)
+    gif.seek(1)
+    assert gif.size == (300, 300)
+    with io.BytesIO() as f:
+        env.save_gif(f)
+        assert f.tell() > 0
+
+
 def test_device_rollout_with_q_network():
     """N1: epsilon-greedy from the device observation + device replay buffer, no host sync per step."""
     from marl_snake_b200 import DeviceReplayBuffer, SnakeBatch, collect
