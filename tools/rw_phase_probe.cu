@@ -44,6 +44,31 @@ __global__ void tile_pattern(uint8_t* __restrict__ recs, uint8_t* __restrict__ o
   for (int i = lane; i < OBS_TILE / 16; i += 32) __stcs(o + i, acc);
 }
 
+// variant E: like tile_pattern, but only a pseudo-random `keep_of_41` of every 41 record sectors (32 B) are
+// written back -- what a dirty-sector write-back of the records would cost
+__global__ void tile_pattern_sparse(uint8_t* __restrict__ recs, uint8_t* __restrict__ obs, int ntiles, int keep_of_41) {
+  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tile >= ntiles) return;
+  const int lane = threadIdx.x & 31;
+  uint4* r = reinterpret_cast<uint4*>(recs + (size_t)tile * REC_TILE);
+  uint4 acc = make_uint4(0, 0, 0, 0);
+  uint4 keep[11];
+#pragma unroll
+  for (int k = 0; k < 11; ++k) {
+    const int i = lane + 32 * k;
+    keep[k] = make_uint4(0, 0, 0, 0);
+    if (i < REC_TILE / 16) { keep[k] = __ldcs(r + i); acc.x ^= keep[k].x; }
+  }
+#pragma unroll
+  for (int k = 0; k < 11; ++k) {
+    const int i = lane + 32 * k;                       // 16-byte unit; sector = i / 2
+    const unsigned sector = (unsigned)(i >> 1) + (unsigned)tile * 164u;
+    if (i < REC_TILE / 16 && (int)((sector * 2654435761u >> 16) % 41u) < keep_of_41) { keep[k].y += 1; r[i] = keep[k]; }
+  }
+  uint4* o = reinterpret_cast<uint4*>(obs + (size_t)tile * OBS_TILE);
+  for (int i = lane; i < OBS_TILE / 16; i += 32) __stcs(o + i, acc);
+}
+
 __global__ void prefetch_l2(const uint8_t* __restrict__ recs, size_t bytes) {
   // one 128-byte line per thread: prefetch.global.L2 brings the line into L2 without a register destination
   size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 128;
@@ -73,7 +98,13 @@ int main(int argc, char** argv) {
   for (int wpb : {1, 4})
     time_it(wpb == 1 ? "B interleaved tiles, 1 warp/CTA" : "B interleaved tiles, 4 warps/CTA", total,
             [&] { tile_pattern<false><<<(ntiles + wpb - 1) / wpb, 32 * wpb>>>(recs, obs, 0, ntiles); });
-  for (int chunk : {4096, 8192, 16384, 32768})
+  for (int keep : {41, 24, 16, 12, 8}) {
+    char name[128];
+    snprintf(name, sizeof name, "E interleaved tiles, %d of 41 record sectors written back", keep);
+    time_it(name, (double)rec_bytes * (1.0 + keep / 41.0) + obs_bytes,
+            [&] { tile_pattern_sparse<<<ntiles, 32>>>(recs, obs, ntiles, keep); });
+  }
+  for (int chunk : {16384})
     for (int wpb : {1, 4}) {
       char name[128];
       snprintf(name, sizeof name, "C prefetch launch + tiles, chunk %d tiles (%.0f MB rec), %d w/CTA", chunk, chunk * REC_TILE / 1e6, wpb);
