@@ -121,9 +121,13 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
   h->device = c->device;
 
   // spawn table (host) -- core/grid_util.py:73-115
-  const int64_t n_cand = spawn_enumerate(d.H, d.W, d.K, nullptr, nullptr, 0);
+  const int64_t n_cand = spawn_enumerate(d.H, d.W, d.K, nullptr, nullptr, 0, SPAWN_TABLE_LIMIT);
   if (n_cand < d.ns) { delete h; return fail(SNK_E_INVALID, "only %lld spawn poses for %d snakes", (long long)n_cand, c->num_snakes); }
-  if (n_cand > 0x7fffffff) { delete h; return fail(SNK_E_INVALID, "spawn table too large"); }
+  if (n_cand > SPAWN_TABLE_LIMIT) {
+    delete h;
+    return fail(SNK_E_INVALID, "more than %lld spawn poses for a %dx%d grid and snake_length %d (the reference enumerates "
+                "them on every reset; here the table would not fit)", (long long)SPAWN_TABLE_LIMIT, c->height, c->width, c->snake_length);
+  }
   std::vector<uint64_t> table((size_t)n_cand);
   spawn_enumerate(d.H, d.W, d.K, table.data(), nullptr, n_cand);
   d.n_cand = (uint32_t)n_cand;
@@ -575,7 +579,9 @@ extern "C" int snk_stats(snk_env* h, double* out_host, int clear) {
 
 extern "C" int64_t snk_spawn_count(int32_t H, int32_t W, int32_t K) {
   if (H < 3 || W < 3 || K < 1 || K > MAX_SNAKE_LENGTH) { fail(SNK_E_INVALID, "bad spawn table shape"); return -1; }
-  return spawn_enumerate(H, W, K, nullptr, nullptr, 0);
+  const int64_t n = spawn_enumerate(H, W, K, nullptr, nullptr, 0, SPAWN_TABLE_LIMIT);
+  if (n > SPAWN_TABLE_LIMIT) { fail(SNK_E_INVALID, "more than %lld spawn poses", (long long)SPAWN_TABLE_LIMIT); return -1; }
+  return n;
 }
 
 extern "C" int snk_spawn_cells(int32_t H, int32_t W, int32_t K, int32_t* out, int64_t count) {

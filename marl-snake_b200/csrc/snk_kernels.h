@@ -80,6 +80,7 @@ cudaError_t launch_init_records(const Dims& d, uint8_t* recs, cudaStream_t s);
 cudaError_t launch_pack_obs(const uint8_t* obs, uint8_t* bits, size_t n_units, cudaStream_t s);
 
 // host-side spawn table (snk_spawn.cpp)
-int64_t spawn_enumerate(int H, int W, int K, uint64_t* packed_out, int32_t* cells_out, int64_t cap);
+int64_t spawn_enumerate(int H, int W, int K, uint64_t* packed_out, int32_t* cells_out, int64_t cap, int64_t limit = 0);
+constexpr int64_t SPAWN_TABLE_LIMIT = (int64_t)64 << 20;     // poses (512 MB of table); more is refused
 
 }  // namespace snk

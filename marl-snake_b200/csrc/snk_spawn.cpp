@@ -20,6 +20,7 @@ struct Walker {
   std::vector<int> path;       // flat cells
   std::vector<int> links;      // direction codes (0 UP 1 RIGHT 2 DOWN 3 LEFT) between consecutive cells
   uint64_t* packed; int32_t* cells; int64_t cap; int64_t n = 0;
+  int64_t limit = 0;           // > 0: stop enumerating once this many poses were seen (the count explodes with length)
 
   bool free_cell(int r, int c) const { return r > 0 && r < H - 1 && c > 0 && c < W - 1; }
   bool on_path(int cell) const {
@@ -47,6 +48,7 @@ struct Walker {
     ++n;
   }
   void grow() {
+    if (limit > 0 && n > limit) return;
     if ((int)path.size() == K) { emit(); return; }
     // DFS shift order (0,1),(1,0),(0,-1),(-1,0) expressed as direction codes RIGHT, DOWN, LEFT, UP
     static const int DR[4] = {0, 1, 0, -1}, DC[4] = {1, 0, -1, 0}, CODE[4] = {1, 2, 3, 0};
@@ -64,9 +66,11 @@ struct Walker {
 
 }  // namespace
 
-// Returns the number of poses; fills up to `cap` entries of whichever outputs are non-null.
-int64_t spawn_enumerate(int H, int W, int K, uint64_t* packed_out, int32_t* cells_out, int64_t cap) {
+// Returns the number of poses; fills up to `cap` entries of whichever outputs are non-null.  With limit > 0
+// the walk stops soon after `limit` poses (the return value is then > limit, not the true count).
+int64_t spawn_enumerate(int H, int W, int K, uint64_t* packed_out, int32_t* cells_out, int64_t cap, int64_t limit) {
   Walker w{H, W, K, {}, {}, packed_out, cells_out, cap};
+  w.limit = limit;
   for (int r = 0; r < H; ++r)
     for (int c = 0; c < W; ++c)
       if (w.free_cell(r, c)) { w.path.assign(1, r * W + c); w.links.clear(); w.grow(); }

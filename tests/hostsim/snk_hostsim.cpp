@@ -11,7 +11,7 @@
 #include "../../include/snk.h"
 #include "../../marl-snake_b200/csrc/snk_core.cuh"
 
-namespace snk { int64_t spawn_enumerate(int H, int W, int K, uint64_t* packed_out, int32_t* cells_out, int64_t cap); }
+namespace snk { int64_t spawn_enumerate(int H, int W, int K, uint64_t* packed_out, int32_t* cells_out, int64_t cap, int64_t limit = 0); }
 using namespace snk;
 
 struct HostSim {

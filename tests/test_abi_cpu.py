@@ -58,6 +58,11 @@ def test_spawn_table_matches_reference_enumeration():
         want = ref[..., 0].astype(np.int32) * W + ref[..., 1]
         assert np.array_equal(out, want), (H, W, k)
     assert m.lib.snk_spawn_count(64, 64, 5) == 362344          # SURVEY probe for the cfg4 shape
+    # the pose count explodes with the length; the enumeration gives up instead of running for hours
+    assert m.lib.snk_spawn_count(40, 40, 25) == -1 and b'spawn poses' in m.lib.snk_last_error()
+    from hostsim_util import make_config
+    h = C.c_void_p()
+    assert m.lib.snk_create(C.byref(make_config(4, dict(height=40, width=40, snake_length=25))), C.byref(h)) == -1
 
 
 @pytest.mark.parametrize('n,threads,misalign', [(0, 1, 0), (1, 1, 0), (7, 1, 0), (121 * 4, 1, 0), (100003, 1, 0),
