@@ -248,6 +248,16 @@ def ours(args):
         return sec
 
     e2e_raw_s = time_host_steps('raw')
+    # context only: a host caller that consumes channel bits as they are (snk_step_host_bits, no widening)
+    h_bits = torch.empty((N,) + batch.obs_shape[:-1] + (batch.obs_shape[-1] // 8,), dtype=torch.uint8).pin_memory()
+    for t in range(2):
+        batch.step_host_bits(h_act[t % 4], h_bits, h_rew, h_done)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for t in range(K2):
+        batch.step_host_bits(h_act[t % 4], h_bits, h_rew, h_done)
+    e2e_bits_s = time.perf_counter() - t0
+    del h_bits
     e2e_s = time_host_steps('packed')
     # the delivered block against the device state of the same step: the window centre of a live snake is
     # its own head (channel 5), a dead snake's window sits on wall cell (0,0)  (byte parity: tests/)
@@ -302,6 +312,9 @@ def ours(args):
                            'bytes -> 1, %d MB over PCIe in chunks, %d host threads per rank widen to uint8 NHWC'
                            % (obs_bytes * N // 8 // 1000000, host_threads),
                     'host_threads_per_rank': host_threads,
+                    'bits_to_host_rank0': {'agent_steps_per_sec_per_gpu': N * ns * K2 / e2e_bits_s, 'ms_per_step': 1e3 * e2e_bits_s / K2,
+                                           'note': 'snk_step_host_bits: channel bits delivered as they are (not the '
+                                                   'reference format; context only)'},
                     'raw_transport': {'value': N * world * ns * K2 / e2e_raw_s, 'ms_per_step': 1e3 * e2e_raw_s / K2,
                                       'd2h_bytes_per_step': N * obs_bytes + N * ns * 9}},
             'gpu_launches': args.steps * world,       # timed region of `value`: one snk_tile_kernel per step per rank

@@ -153,6 +153,11 @@ int snk_step_host(snk_env* env, const uint8_t* actions_host, uint8_t* obs_host,
 int snk_step_host_info(snk_env* env, const uint8_t* actions_host, uint8_t* obs_host, double* rewards_host,
                        uint8_t* dones_host, const snk_step_extra* extra_host);
 int snk_reset_host(snk_env* env, uint8_t* obs_host);
+/* For host callers that can consume channel bits directly: as snk_step_host, but delivers the observation as
+ * one byte per (cell, frame) -- bits_host[u] bit c = channel c, N * prod(obs shape) / 8 bytes, the layout of
+ * snk_pack_obs -- so nothing is widened on the host and an eighth of the bytes crosses the PCIe link. */
+int snk_step_host_bits(snk_env* env, const uint8_t* actions_host, uint8_t* bits_host,
+                       double* rewards_host, uint8_t* dones_host);
 
 enum { SNK_XFER_RAW = 0, SNK_XFER_PACKED = 1 };
 /* threads: widening threads of the packed transport, 0 = one per core this process may run on (<= 32) */

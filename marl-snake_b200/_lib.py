@@ -58,6 +58,7 @@ PROTOTYPES = {
     'snk_step_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'snk_step_host_info': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.POINTER(SnkStepExtra)]),
+    'snk_step_host_bits': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'snk_reset_host': (C.c_int, [C.c_void_p, C.c_void_p]),
     'snk_set_host_transport': (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     'snk_get_host_transport': (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

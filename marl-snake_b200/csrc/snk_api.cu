@@ -441,6 +441,28 @@ extern "C" int snk_step_host_info(snk_env* h, const uint8_t* actions_host, uint8
   return SNK_OK;
 }
 
+extern "C" int snk_step_host_bits(snk_env* h, const uint8_t* actions_host, uint8_t* bits_host,
+                                  double* rewards_host, uint8_t* dones_host) {
+  if (!h) return fail(SNK_E_INVALID, "null handle");
+  if (!actions_host || !bits_host || !rewards_host || !dones_host) return fail(SNK_E_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  int rc = ensure_mirrors(h);
+  if (rc) return rc;
+  const Dims& d = h->d;
+  const size_t nn = (size_t)d.N * d.ns, units = (size_t)d.N * d.obs_env_bytes / 8;
+  cudaStream_t s = h->own_stream;
+  if (!h->d_bits) CU(cudaMalloc(&h->d_bits, units));
+  CU(cudaMemcpyAsync(h->h_actions, actions_host, nn, cudaMemcpyHostToDevice, s));
+  rc = snk_step(h, h->h_actions, h->h_obs, h->h_rew, h->h_done, nullptr, s);
+  if (rc) return rc;
+  CU(launch_pack_obs(h->h_obs, h->d_bits, units, s));
+  CU(cudaMemcpyAsync(rewards_host, h->h_rew, nn * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(dones_host, h->h_done, nn, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(bits_host, h->d_bits, units, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return SNK_OK;
+}
+
 extern "C" int snk_step_host(snk_env* h, const uint8_t* actions_host, uint8_t* obs_host,
                              double* rewards_host, uint8_t* dones_host) {
   return snk_step_host_info(h, actions_host, obs_host, rewards_host, dones_host, nullptr);

@@ -145,6 +145,12 @@ class SnakeBatch:
                                 C.c_void_p(obs.data_ptr()) if obs is not None else C.c_void_p(0),
                                 C.c_void_p(rewards.data_ptr()), C.c_void_p(dones.data_ptr())))
 
+    def step_host_bits(self, actions, bits, rewards, dones):
+        """As step_host, but `bits` (uint8, obs shape with the last dimension divided by 8) receives channel
+        bits -- one byte per (cell, frame) -- and nothing is widened on the host."""
+        check(lib.snk_step_host_bits(self._h, C.c_void_p(actions.data_ptr()), C.c_void_p(bits.data_ptr()),
+                                     C.c_void_p(rewards.data_ptr()), C.c_void_p(dones.data_ptr())))
+
     def reset_host(self, obs):
         check(lib.snk_reset_host(self._h, C.c_void_p(obs.data_ptr()) if obs is not None else C.c_void_p(0)))
         self._host_reset_done = True

@@ -631,6 +631,27 @@ def test_gpu_packed_host_transport_equals_raw(kw, N):
         assert torch.equal(o.cpu(), o2) and torch.equal(r.cpu(), r2)
 
 
+def test_gpu_step_host_bits():
+    """snk_step_host_bits delivers np.packbits(obs, little) of what snk_step_host delivers."""
+    from marl_snake_b200 import SnakeBatch
+    N, ns = 333, 4
+    kw = dict(num_snakes=ns, vision_range=5, frame_stack=2, seed=21)
+    a, b = SnakeBatch(N, **kw), SnakeBatch(N, **kw)
+    a.reset(); b.reset()
+    obs = torch.empty((N,) + a.obs_shape, dtype=torch.uint8).pin_memory()
+    bits = torch.empty((N,) + a.obs_shape[:-1] + (a.obs_shape[-1] // 8,), dtype=torch.uint8).pin_memory()
+    r1, r2 = (torch.empty((N, ns), dtype=torch.float64).pin_memory() for _ in range(2))
+    d1, d2 = (torch.empty((N, ns), dtype=torch.uint8).pin_memory() for _ in range(2))
+    g = torch.Generator().manual_seed(2)
+    for t in range(12):
+        act = torch.randint(0, 3, (N, ns), dtype=torch.uint8, generator=g)
+        a.step_host(act, obs, r1, d1)
+        b.step_host_bits(act, bits, r2, d2)
+        assert torch.equal(r1, r2) and torch.equal(d1, d2)
+        want = np.packbits(obs.numpy().reshape(-1, 8), axis=1, bitorder='little').reshape(bits.shape)
+        assert np.array_equal(bits.numpy(), want), t
+
+
 def test_gpu_pack_obs_roundtrip():
     """snk_pack_obs (device) and snk_widen_bits_host (host) are inverse; the packed form is np.packbits."""
     import ctypes as C
