@@ -113,6 +113,7 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
   d.V = c->vision_range; d.fs = c->frame_stack; d.nfruits = nfruits;
   d.auto_reset = c->auto_reset ? 1 : 0; d.done_mode = c->done_mode ? 1 : 0; d.rng_mode = c->rng_mode;
   d.observer = c->observer;
+  d.dig = default_dig(d.ns);
   d.seed_lo = (uint32_t)c->seed; d.seed_hi = (uint32_t)(c->seed >> 32);
   d.env_off_lo = (uint32_t)c->env_id_offset; d.env_off_hi = (uint32_t)(c->env_id_offset >> 32);
   d.r_fruit = c->reward_fruit; d.r_kill = c->reward_kill; d.r_lose = c->reward_lose;

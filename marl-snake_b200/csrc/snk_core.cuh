@@ -9,6 +9,7 @@
 // Reference lines (relative to /root/reference/marlenv/marlenv/) are cited at each rule.
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 
 #if defined(__CUDACC__)
 #define SNK_HD __host__ __device__ __forceinline__
@@ -51,12 +52,15 @@ struct Dims {
   int32_t ohw_p;                  // history row stride (ohw rounded up to 16)
   int32_t auto_reset, done_mode, rng_mode;
   int32_t observer;               // 0 'snake': three relative actions; 1 'human': five absolute actions
+  int32_t dig;                    // 1: body directions live in bits 6..7 of the grid byte (cell codes < 64, i.e.
+                                  //    at most 6 snakes) and the record has no direction plane
+  int32_t code_mask;              // 63 when dig, else 255: grid byte -> cell code
   // record layout (bytes from record start; grid is at 0)
   int32_t off_dirp, off_snk, off_hdr, off_stats, rec_bytes;
   int32_t hist_env_bytes;         // ns*fs*ohw_p, 0 when fs == 1
   int32_t stage_env_bytes;        // ns*ohw*fs  (staging area per env, output order)
   int32_t obs_env_bytes;          // ns*ohw*fs*8
-  int32_t scr_bytes;              // per-env scratch: tgt u16[ns], st u8[ns], kl u8[ns], padded to 8
+  int32_t scr_bytes;              // per-env scratch: tgt u16[ns], st u8[ns], kl u8[ns], tdir u8[ns], padded to 8
   uint32_t n_cand;
   uint32_t seed_lo, seed_hi, env_off_lo, env_off_hi;
   double r_fruit, r_kill, r_lose, r_win, r_time, max_steps;
@@ -69,15 +73,16 @@ inline void finalize_layout(Dims& d) {
   if (d.V > 0) { d.oh = d.ow = 2 * d.V + 1; } else { d.oh = d.H; d.ow = d.W; }
   d.ohw = d.oh * d.ow;
   d.ohw_p = round_up(d.ohw, 16);
+  d.code_mask = d.dig ? 63 : 255;
   d.off_dirp = round_up(d.HW, 16);
-  d.off_snk = d.off_dirp + round_up((d.HW + 3) / 4, 16);
+  d.off_snk = d.off_dirp + (d.dig ? 0 : round_up((d.HW + 3) / 4, 16));
   d.off_hdr = d.off_snk + round_up(8 * d.ns, 16);
   d.off_stats = d.off_hdr + (int)sizeof(EnvHdr);
   d.rec_bytes = d.off_stats + round_up(20 * d.ns, 16);
   d.hist_env_bytes = d.fs > 1 ? d.ns * d.fs * d.ohw_p : 0;
   d.stage_env_bytes = d.ns * d.ohw * d.fs;
   d.obs_env_bytes = d.stage_env_bytes * 8;
-  d.scr_bytes = round_up(4 * d.ns, 8);
+  d.scr_bytes = round_up(5 * d.ns, 8);
 }
 
 // ---- record field accessors ---------------------------------------------------------------------
@@ -121,6 +126,21 @@ SNK_HD void dirp_set(uint8_t* dirp, int c, int v) {
   dirp[c >> 2] = (uint8_t)((dirp[c >> 2] & ~(3 << sh)) | (v << sh));
 }
 SNK_HD int dir_delta(int dir, int W) { return dir == 0 ? -W : dir == 1 ? 1 : dir == 2 ? W : -1; }
+
+// With at most 6 snakes every cell code (type + 10*owner <= 55) fits 6 bits, so the 2-bit direction of a
+// BODY / TAIL cell rides in bits 6..7 of its grid byte and the plane is dropped from the record ("dig").
+// EMPTY / WALL / FRUIT / HEAD bytes carry no direction bits, so an empty cell is still exactly 0.
+inline int default_dig(int ns) {
+  const char* off = getenv("SNK_NO_DIG");
+  return (10 * (ns - 1) + 5 < 64 && !(off && *off == '1')) ? 1 : 0;
+}
+SNK_HD uint32_t cell_code(const Dims& d, uint32_t grid_byte) { return grid_byte & (uint32_t)d.code_mask; }
+SNK_HD int body_dir(const Dims& d, const Rec& r, int c) { return d.dig ? (r.grid[c] >> 6) : dirp_get(r.dirp, c); }
+// single-writer contexts only (host simulation, thread-per-environment kernels)
+SNK_HD void set_body_dir(const Dims& d, const Rec& r, int c, int v) {
+  if (d.dig) r.grid[c] = (uint8_t)((r.grid[c] & 63) | (v << 6));
+  else dirp_set(r.dirp, c, v);
+}
 
 // observer='snake': 0 keep, 1 turn left, 2 turn right (the exact table of the reference's trigonometric
 // _next_direction, snake_env.py:598-608; a > 2 is the reference's KeyError, reported by the caller).
@@ -198,7 +218,7 @@ struct StepResult {
   uint8_t deaths;
 };
 
-// scr: tgt u16[ns] | st u8[ns] | kl u8[ns]
+// scr: tgt u16[ns] | st u8[ns] | kl u8[ns] | tdir u8[ns]
 // act: ns actions; rew/done: ns outputs.
 SNK_HD StepResult env_step_logic(const Dims& d, uint8_t* rec_base, uint8_t* scr, const uint8_t* act,
                                  double* rew, uint8_t* done, uint32_t* err_bits) {
@@ -207,6 +227,7 @@ SNK_HD StepResult env_step_logic(const Dims& d, uint8_t* rec_base, uint8_t* scr,
   uint16_t* tgt = (uint16_t*)scr;
   uint8_t* st = scr + 2 * ns;
   uint8_t* kl = st + ns;
+  uint8_t* tdir = kl + ns;
   StepResult out;
   out.fruit_taken = 0; out.finished = 0; out.deaths = 0;
 
@@ -228,7 +249,7 @@ SNK_HD StepResult env_step_logic(const Dims& d, uint8_t* rec_base, uint8_t* scr,
   int fruit_taken = 0, ndead = 0;
   for (int i = 0; i < ns; ++i) {
     if (!(st[i] & ST_WAS_ALIVE)) continue;
-    const uint32_t code = r.grid[tgt[i]];
+    const uint32_t code = cell_code(d, r.grid[tgt[i]]);
     const uint32_t owner = (code * 205u) >> 11;
     const uint32_t kind = code - owner * 10u;
     int n = 0; bool first = true;
@@ -262,6 +283,11 @@ SNK_HD StepResult env_step_logic(const Dims& d, uint8_t* rec_base, uint8_t* scr,
     for (int i = 0; i < ns; ++i) if (r.alive[i]) { st[i] |= ST_WON; break; }
   r.hdr->alive_counter = counter;
 
+  // The direction stored with a tail cell is read before any snake moves: in this sequential walk an
+  // earlier snake's head may already sit in a later snake's vacated tail cell (:555) and, when directions
+  // ride in the grid byte, would have overwritten it.
+  for (int i = 0; i < ns; ++i) tdir[i] = (st[i] & ST_WAS_ALIVE) ? (uint8_t)body_dir(d, r, r.tail[i]) : 0;
+
   // 4. rewards (float64, fixed order, no FMA) and sequential grid update              :358-374, :546-566
   int n_alive = 0, n_done = 0;
   for (int i = 0; i < ns; ++i) {
@@ -287,18 +313,18 @@ SNK_HD StepResult env_step_logic(const Dims& d, uint8_t* rec_base, uint8_t* scr,
       if (alive) {                                         // _update_grid, live branch      :548-559
         const int oh = r.head[i];
         r.grid[oh] = (uint8_t)(BODY + tag);
-        dirp_set(r.dirp, oh, r.dir[i]);
+        set_body_dir(d, r, oh, r.dir[i]);
         if (!ate) {
           const int ot = r.tail[i];
-          const int nt = ot + dir_delta(dirp_get(r.dirp, ot), W);
-          if (r.grid[ot] == TAIL + tag) r.grid[ot] = EMPTY;   // may already hold another head (:555)
+          const int nt = ot + dir_delta(tdir[i], W);
+          if (cell_code(d, r.grid[ot]) == (uint32_t)(TAIL + tag)) r.grid[ot] = EMPTY;   // may already hold another head (:555)
           r.tail[i] = (uint16_t)nt;
         } else {
           r.len[i] = (uint16_t)(r.len[i] + 1);
         }
         r.head[i] = tgt[i];
         r.grid[tgt[i]] = (uint8_t)(HEAD + tag);
-        r.grid[r.tail[i]] = (uint8_t)(TAIL + tag);
+        r.grid[r.tail[i]] = (uint8_t)((TAIL + tag) | (d.dig ? (r.grid[r.tail[i]] & 0xC0) : 0));   // keeps the cell's direction
         // episode statistics gate on this step's done flags                                 :385-389
 #if defined(__CUDA_ARCH__)
         r.score[i] = __dadd_rn(r.score[i], rw);
@@ -312,8 +338,8 @@ SNK_HD StepResult env_step_logic(const Dims& d, uint8_t* rec_base, uint8_t* scr,
         const int hd = r.head[i];
         bool is_tail = true;
         for (int guard = 0; guard < d.HW; ++guard) {
-          const int nxt = c + dir_delta(dirp_get(r.dirp, c), W);
-          if (!(is_tail && (int)(((uint32_t)r.grid[c] * 205u) >> 11) != i)) r.grid[c] = EMPTY;
+          const int nxt = c + dir_delta(is_tail ? (int)tdir[i] : body_dir(d, r, c), W);
+          if (!(is_tail && (int)((cell_code(d, r.grid[c]) * 205u) >> 11) != i)) r.grid[c] = EMPTY;
           if (c == hd) break;
           c = nxt; is_tail = false;
         }

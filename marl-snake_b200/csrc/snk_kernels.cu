@@ -192,7 +192,7 @@ __device__ __noinline__ void reset_env_warp(const KParams& p, uint8_t* rec_base,
     __syncwarp();
   }
   __syncwarp();
-  // snake table + body-direction plane; serialised per snake because plane bytes hold 4 cells
+  // snake table + body directions (toward the head); serialised per snake because plane bytes hold 4 cells
   for (int s = 0; s < ns; ++s) {
     if ((int)lane == s) {
       int c = spawn_head(entry);
@@ -201,10 +201,10 @@ __device__ __noinline__ void reset_env_warp(const KParams& p, uint8_t* rec_base,
       for (int j = 1; j < K; ++j) {
         const int l = spawn_link(entry, j);
         c += dir_delta(l, W);
-        dirp_set(r.dirp, c, (l + 2) & 3);            // toward the head
+        r.grid[c] = (uint8_t)((j == K - 1 ? TAIL : BODY) + 10 * s);
+        set_body_dir(d, r, c, (l + 2) & 3);            // toward the head
       }
       r.tail[s] = (uint16_t)c;
-      r.grid[c] = (uint8_t)(TAIL + 10 * s);
       r.len[s] = (uint16_t)K;
       r.dir[s] = (uint8_t)((spawn_link(entry, 1) + 2) & 3);   // coords[0] - coords[1]  core/snake.py:58-61
       r.alive[s] = 1;
@@ -325,7 +325,7 @@ __device__ __forceinline__ GroupOut step_group(const KParams& p, const SH& sh, R
   const uint32_t same = __match_any_sync(FULL, tgt) & gmask;     // snakes of my env entering my cell
   const int n = __popc(same);
   const bool first = (__ffs(same) - 1) == (int)lane;             // lowest-index arrival speaks for the cell
-  const uint32_t code = was_alive ? r.grid[tgt] : 0u;
+  const uint32_t code = was_alive ? cell_code(d, r.grid[tgt]) : 0u;
   const uint32_t owner = (code * 205u) >> 11;
   const uint32_t kind = code - owner * 10u;
   const bool lethal = (kind == WALL) | (kind == BODY) | (kind == HEAD);
@@ -376,14 +376,14 @@ __device__ __forceinline__ GroupOut step_group(const KParams& p, const SH& sh, R
       const int hd = r.head[i];
 #pragma unroll 1
       for (int guard = 0; guard < d.HW; ++guard) {
-        const int nxt = c + dir_delta(dirp_get(r.dirp, c), W);
+        const int nxt = c + dir_delta(body_dir(d, r, c), W);
         r.grid[c] = (uint8_t)EMPTY;
         if (c == hd) break;
         c = nxt;
       }
     } else if (!eater) {
       const int ot = r.tail[i];
-      new_tail = ot + dir_delta(dirp_get(r.dirp, ot), W);
+      new_tail = ot + dir_delta(body_dir(d, r, ot), W);
       r.grid[ot] = (uint8_t)EMPTY;
     } else {
       new_tail = r.tail[i];
@@ -393,12 +393,13 @@ __device__ __forceinline__ GroupOut step_group(const KParams& p, const SH& sh, R
   if (active) {
     if (alive_now) {
       const int oh = r.head[i];
-      r.grid[oh] = (uint8_t)(BODY + tag);
-      dirp_set_atomic(r.dirp, oh, dirv);
+      r.grid[oh] = (uint8_t)((BODY + tag) | (d.dig ? dirv << 6 : 0));
+      if (!d.dig) dirp_set_atomic(r.dirp, oh, dirv);
       r.dir[i] = (uint8_t)dirv;
       r.tail[i] = (uint16_t)new_tail;
       if (eater) r.len[i] = (uint16_t)(r.len[i] + 1);
-      r.grid[new_tail] = (uint8_t)(TAIL + tag);        // length 2: overwrites the BODY just written
+      // length 2: overwrites the BODY just written; the cell keeps its direction bits
+      r.grid[new_tail] = (uint8_t)((TAIL + tag) | (d.dig ? (r.grid[new_tail] & 0xC0) : 0));
       r.head[i] = (uint16_t)tgt;
       r.grid[tgt] = (uint8_t)(HEAD + tag);
       r.score[i] = __dadd_rn(r.score[i], rw);          // statistics gate on this step's dones  :385-389
@@ -569,7 +570,8 @@ __device__ __forceinline__ void encode_viewer_fs1(const KParams& p, const SH& sh
       const uint32_t ab0 = ((eb0.x & maskpk) == eb0.x) ? gorg + eb0.y : lutv32;
       const uint32_t aa1 = ((ea1.x & maskpk) == ea1.x) ? gorg + ea1.y : lutv32;
       const uint32_t ab1 = ((eb1.x & maskpk) == eb1.x) ? gorg + eb1.y : lutv32;
-      const uint32_t ka0 = lds_u8(aa0), kb0 = lds_u8(ab0), ka1 = lds_u8(aa1), kb1 = lds_u8(ab1);
+      const uint32_t cm = (uint32_t)d.code_mask;
+      const uint32_t ka0 = lds_u8(aa0) & cm, kb0 = lds_u8(ab0) & cm, ka1 = lds_u8(aa1) & cm, kb1 = lds_u8(ab1) & cm;
       uint32_t la0 = lutv32, lb0 = lutv32, la1 = lutv32, lb1 = lutv32;
       if (dual) {
         la0 = (((ka0 * 205u) >> 11) == (uint32_t)v) ? lutown : lut32;
@@ -600,7 +602,7 @@ __device__ __forceinline__ void encode_viewer_fs1(const KParams& p, const SH& sh
         const int ci = c / ow, cj = c - ci * ow;
         const int rr = r0 + ci, cc = c0 + cj;
         uint32_t code = 0;
-        if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
+        if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = cell_code(d, grid[rr * W + cc]);
         qa = lut[code];
       }
       {
@@ -608,7 +610,7 @@ __device__ __forceinline__ void encode_viewer_fs1(const KParams& p, const SH& sh
         const int ci = c / ow, cj = c - ci * ow;
         const int rr = r0 + ci, cc = c0 + cj;
         uint32_t code = 0;
-        if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
+        if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = cell_code(d, grid[rr * W + cc]);
         qb = lut[code];
       }
       uint8_t* dst = outv + (ptrdiff_t)ca * 8;
@@ -675,7 +677,8 @@ __device__ __forceinline__ void encode_viewer_reg(const KParams& p, const SH& sh
   const uint32_t a1 = (e1 & bad) ? lutv32 : gorg + ((e1 & 0x7fffffffu) >> B);
   const uint32_t a2 = (e2 & bad) ? lutv32 : gorg + ((e2 & 0x7fffffffu) >> B);
   const uint32_t a3 = (e3 & bad) ? lutv32 : gorg + ((e3 & 0x7fffffffu) >> B);
-  const uint32_t k0 = lds_u8(a0), k1 = lds_u8(a1), k2 = lds_u8(a2), k3 = lds_u8(a3);
+  const uint32_t cm = (uint32_t)p.d.code_mask;
+  const uint32_t k0 = lds_u8(a0) & cm, k1 = lds_u8(a1) & cm, k2 = lds_u8(a2) & cm, k3 = lds_u8(a3) & cm;
   const uint2 q0 = lds_v2(lutv32 + k0 * 8u), q1 = lds_v2(lutv32 + k1 * 8u);
   const uint2 q2 = lds_v2(lutv32 + k2 * 8u), q3 = lds_v2(lutv32 + k3 * 8u);
   const int ca0 = 2 * lane - shift, ca1 = ca0 + 64;
@@ -694,7 +697,8 @@ __device__ __forceinline__ void encode_viewer_reg(const KParams& p, const SH& sh
 
 // Full-grid observation: the window IS the grid, so window cell c reads grid byte c.
 template <class SH>
-__device__ __forceinline__ void encode_viewer_direct(const SH& sh, uint32_t grid32, int v, uint8_t* outv, uint32_t lut32) {
+__device__ __forceinline__ void encode_viewer_direct(const SH& sh, uint32_t grid32, int v, uint8_t* outv, uint32_t lut32,
+                                                     uint32_t cm) {
   const int lane = (int)lane_id();
   const int ohw = sh.ohw();
   const uint32_t lutv32 = lut32 + (uint32_t)(v * sh.lut_stride()) * 8u;
@@ -704,10 +708,10 @@ __device__ __forceinline__ void encode_viewer_direct(const SH& sh, uint32_t grid
     const int u1 = u0 + 32;
     const bool has1 = u1 < units;
     const int ca0 = 2 * u0 - shift, ca1 = 2 * (has1 ? u1 : u0) - shift;
-    const uint32_t k0 = lds_u8(ca0 >= 0 ? grid32 + (uint32_t)ca0 : lutv32);
-    const uint32_t k1 = lds_u8(ca0 + 1 < ohw ? grid32 + (uint32_t)(ca0 + 1) : lutv32);
-    const uint32_t k2 = lds_u8(ca1 >= 0 ? grid32 + (uint32_t)ca1 : lutv32);
-    const uint32_t k3 = lds_u8(ca1 + 1 < ohw ? grid32 + (uint32_t)(ca1 + 1) : lutv32);
+    const uint32_t k0 = lds_u8(ca0 >= 0 ? grid32 + (uint32_t)ca0 : lutv32) & cm;     // cm: grid byte -> cell code
+    const uint32_t k1 = lds_u8(ca0 + 1 < ohw ? grid32 + (uint32_t)(ca0 + 1) : lutv32) & cm;
+    const uint32_t k2 = lds_u8(ca1 >= 0 ? grid32 + (uint32_t)ca1 : lutv32) & cm;
+    const uint32_t k3 = lds_u8(ca1 + 1 < ohw ? grid32 + (uint32_t)(ca1 + 1) : lutv32) & cm;
     const uint2 q0 = lds_v2(lutv32 + k0 * 8u), q1 = lds_v2(lutv32 + k1 * 8u);
     const uint2 q2 = lds_v2(lutv32 + k2 * 8u), q3 = lds_v2(lutv32 + k3 * 8u);
     uint8_t* dst0 = outv + (ptrdiff_t)ca0 * 8;
@@ -763,7 +767,7 @@ __device__ __forceinline__ void encode_env_stacked(const KParams& p, const SH& s
           const int c = min(c4 + k, ohw);                                 // c == ohw: sentinel entry
           const uint2 en = lds_v2(tab32 + (uint32_t)(c * 8));
           const uint32_t a = ((en.x & maskpk) == en.x) ? gorg + en.y : lutv32;
-          nw |= lds_u8(lutv32 + lds_u8(a)) << (8 * k);
+          nw |= lds_u8(lutv32 + (lds_u8(a) & (uint32_t)d.code_mask)) << (8 * k);
         }
         uint32_t f0, f1, f2;
         if (!init) {
@@ -806,7 +810,7 @@ __device__ __forceinline__ void encode_env_stacked(const KParams& p, const SH& s
         const int ci = cell / ow, cj = cell - ci * ow;
         const int rr = r0 + ci, cc = c0 + cj;
         uint32_t code = 0;
-        if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = grid[rr * W + cc];
+        if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = cell_code(d, grid[rr * W + cc]);
         const uint8_t bits = lut[code];
         if (!init) {
           if (want_obs) stg[(size_t)cell * fs + (fs - 1)] = bits;
@@ -970,7 +974,7 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
           const uint32_t grid32 = (uint32_t)__cvta_generic_to_shared(base);
           uint8_t* outv = p.obs + ((size_t)(e0 + q) * ns + v) * (size_t)ohw * 8;
           if (kEnc == ENC_REG) encode_viewer_reg(p, sh, grid32, s_view[q * G + v], cw, v, outv, lut32);
-          else if (kEnc == ENC_DIRECT) encode_viewer_direct(sh, grid32, v, outv, lut32);
+          else if (kEnc == ENC_DIRECT) encode_viewer_direct(sh, grid32, v, outv, lut32, (uint32_t)d.code_mask);
           else encode_viewer_fs1(p, sh, base, grid32, v, outv, lut32);
         }
       } else {
@@ -984,7 +988,7 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
           for (int v = 0; v < ns; ++v) {
             uint8_t* outv = outq + (size_t)v * ohw * 8;
             if (kEnc == ENC_REG) encode_viewer_reg(p, sh, grid32, s_view[q * G + v], cw, v, outv, lut32);
-            else if (kEnc == ENC_DIRECT) encode_viewer_direct(sh, grid32, v, outv, lut32);
+            else if (kEnc == ENC_DIRECT) encode_viewer_direct(sh, grid32, v, outv, lut32, (uint32_t)d.code_mask);
             else encode_viewer_fs1(p, sh, base, grid32, v, outv, lut32);
           }
         }
@@ -1031,7 +1035,7 @@ __global__ void snk_get_state_kernel(const Dims d, const uint8_t* __restrict__ r
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.N) return;
   Rec r = rec_view(const_cast<uint8_t*>(recs) + (size_t)e * d.rec_bytes, d);
-  if (sv.grid) for (int c = 0; c < d.HW; ++c) sv.grid[(size_t)e * d.HW + c] = r.grid[c];
+  if (sv.grid) for (int c = 0; c < d.HW; ++c) sv.grid[(size_t)e * d.HW + c] = (uint8_t)cell_code(d, r.grid[c]);
   if (sv.alive_counter) sv.alive_counter[e] = r.hdr->alive_counter;
   if (sv.episode_length) sv.episode_length[e] = (int32_t)r.hdr->episode_length;
   for (int i = 0; i < d.ns; ++i) {
@@ -1049,7 +1053,7 @@ __global__ void snk_get_state_kernel(const Dims d, const uint8_t* __restrict__ r
         int c = r.tail[i];
         for (int k = (int)r.len[i] - 1; k >= 0; --k) {
           if (k < sv.max_cells) cl[k] = c;
-          c += dir_delta(dirp_get(r.dirp, c), d.W);
+          c += dir_delta(body_dir(d, r, c), d.W);
         }
       }
     }
@@ -1075,7 +1079,7 @@ __global__ void snk_set_state_kernel(const Dims d, uint8_t* __restrict__ recs, S
       for (int k = 1; k < len; ++k) {
         const int diff = cl[k - 1] - cl[k];
         const int dd = diff == -d.W ? 0 : diff == 1 ? 1 : diff == d.W ? 2 : 3;
-        dirp_set(r.dirp, cl[k], dd);
+        set_body_dir(d, r, cl[k], dd);
       }
     }
     r.score[i] = 0.0; r.steps[i] = 0; r.fruits[i] = 0; r.kills[i] = 0;

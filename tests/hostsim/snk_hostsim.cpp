@@ -85,10 +85,10 @@ static void reset_env(HostSim& h, Rec& r, uint32_t env) {
     for (int j = 1; j < K; ++j) {
       const int l = spawn_link(entry[s], j);
       c += dir_delta(l, W);
-      dirp_set(r.dirp, c, (l + 2) & 3);
+      r.grid[c] = (uint8_t)((j == K - 1 ? TAIL : BODY) + 10 * s);
+      set_body_dir(d, r, c, (l + 2) & 3);
     }
     r.tail[s] = (uint16_t)c;
-    r.grid[c] = (uint8_t)(TAIL + 10 * s);
     r.len[s] = (uint16_t)K;
     r.dir[s] = (uint8_t)((spawn_link(entry[s], 1) + 2) & 3);
     r.alive[s] = 1;
@@ -120,7 +120,7 @@ static void encode_env(HostSim& h, Rec& r, uint32_t env, bool init, uint8_t* obs
     for (int cell = 0; cell < ohw; ++cell) {
       const int rr = r0 + cell / d.ow, cc = c0 + cell % d.ow;
       uint32_t bits = 0;
-      if (rr >= 0 && rr < d.H && cc >= 0 && cc < d.W) bits = cell_bits(r.grid[rr * d.W + cc], (uint32_t)v);
+      if (rr >= 0 && rr < d.H && cc >= 0 && cc < d.W) bits = cell_bits(cell_code(d, r.grid[rr * d.W + cc]), (uint32_t)v);
       if (fs == 1) stg[cell] = (uint8_t)bits;
       else if (!init) { stg[(size_t)cell * fs + fs - 1] = (uint8_t)bits; hrow[(size_t)hpos * d.ohw_p + cell] = (uint8_t)bits; }
       else for (int f = 0; f < fs; ++f) { stg[(size_t)cell * fs + f] = (uint8_t)bits; hrow[(size_t)f * d.ohw_p + cell] = (uint8_t)bits; }
@@ -146,6 +146,7 @@ void* hs_create(const snk_config* c) {
   d.V = c->vision_range; d.fs = c->frame_stack;
   d.nfruits = c->num_fruits < 0 ? (int)(c->num_snakes * 0.8 + 0.5) : c->num_fruits;
   d.auto_reset = c->auto_reset; d.done_mode = c->done_mode; d.rng_mode = c->rng_mode; d.observer = c->observer;
+  d.dig = default_dig(d.ns);
   d.seed_lo = (uint32_t)c->seed; d.seed_hi = (uint32_t)(c->seed >> 32);
   d.env_off_lo = (uint32_t)c->env_id_offset; d.env_off_hi = (uint32_t)(c->env_id_offset >> 32);
   d.r_fruit = c->reward_fruit; d.r_kill = c->reward_kill; d.r_lose = c->reward_lose;
@@ -219,7 +220,7 @@ void hs_get_grid(void* p, uint8_t* grid, int32_t* counter, int32_t* cursor) {
   const Dims& d = h->d;
   for (int e = 0; e < d.N; ++e) {
     Rec r = rec_view(h->recs.data() + (size_t)e * d.rec_bytes, d);
-    memcpy(grid + (size_t)e * d.HW, r.grid, (size_t)d.HW);
+    for (int c = 0; c < d.HW; ++c) grid[(size_t)e * d.HW + c] = (uint8_t)cell_code(d, r.grid[c]);
     if (counter) counter[e] = r.hdr->alive_counter;
     if (cursor) cursor[e] = (int32_t)r.hdr->cursor;
   }
@@ -243,7 +244,7 @@ void hs_set_state(void* p, const uint8_t* grid, const uint8_t* alive, const uint
         r.head[i] = (uint16_t)cl[0]; r.tail[i] = (uint16_t)cl[len - 1];
         for (int k = 1; k < len; ++k) {
           const int diff = cl[k - 1] - cl[k];
-          dirp_set(r.dirp, cl[k], diff == -d.W ? 0 : diff == 1 ? 1 : diff == d.W ? 2 : 3);
+          set_body_dir(d, r, cl[k], diff == -d.W ? 0 : diff == 1 ? 1 : diff == d.W ? 2 : 3);
         }
       }
       r.score[i] = 0.0; r.steps[i] = 0; r.fruits[i] = 0; r.kills[i] = 0;
