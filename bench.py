@@ -111,7 +111,7 @@ def reference_arm(args):
         'cpu_baseline': {'value': val, 'unit': 'agent-steps/s', 'cores': pool.procs, 'kind': 'port',
                          'sample': sample},
         'e2e': {'value': val, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0}))
+        'gpu_launches': 0}), file=RESULT_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------ clocks
@@ -325,12 +325,18 @@ def ours(args):
         if cpu:
             out['cpu_baseline'] = cpu
             out['cpu_native_1thread'] = cpu_native
-        print(json.dumps(out))
+        print(json.dumps(out), file=RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == '__main__':
+    # stdout must carry exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner to
+    # stdout when NCCL_DEBUG is set), so file descriptor 1 is pointed at stderr for the whole run and the
+    # result line goes to a private duplicate of the original stdout.
+    RESULT_OUT = os.fdopen(os.dup(1), 'w')
+    sys.stdout.flush()
+    os.dup2(2, 1)
     a = parse()
     if a.impl == 'reference':
         reference_arm(a)
