@@ -8,7 +8,19 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def _ensure_native_builds():
+    """The suite needs libsnk.so (and, for the host simulation, g++): build what is missing so that a fresh
+    checkout can run `pytest` directly.  On the GPU box the built files travel with the snapshot."""
+    import shutil
+    import subprocess
+    lib = os.path.join(ROOT, 'marl-snake_b200', 'libsnk.so')
+    if not os.path.exists(lib) and shutil.which('nvcc'):
+        subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'marl-snake_b200', 'csrc')],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+
 def pytest_configure(config):
+    _ensure_native_builds()
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     config.addinivalue_line("markers", "needs_reference: needs /root/reference (build container only)")
 
