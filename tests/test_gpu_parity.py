@@ -525,6 +525,41 @@ def test_packed_replay_buffer_and_graphed_steps():
         actions.copy_(torch.randint(0, 3, (T, N, ns), dtype=torch.uint8, device='cuda', generator=g))
 
 
+def test_gpu_stepping_a_finished_env_matches_oracle():
+    """Without auto-reset the reference keeps accepting steps after the episode ended (probe g3):
+    dead snakes return 0 / True, a capped episode keeps moving its live snakes, and the terminal info dict is
+    emitted again on every such step with the statistics accumulated since the previous emission."""
+    from oracle.snake_oracle import OracleSnakeEnv, PhiloxDraws
+    kw = dict(height=9, width=9, num_snakes=3, snake_length=3, vision_range=2, max_episode_steps=6)
+    N, seed = 6, 77
+    be = GpuBackend(N, kw, rng_mode=0, auto_reset=0, seed=seed)
+    draws = [PhiloxDraws(seed, e) for e in range(N)]
+    envs = [OracleSnakeEnv(draws=draws[e], **kw) for e in range(N)]
+    for dr in draws:
+        dr.tick()
+    assert np.array_equal(be.reset(), np.stack([e.reset() for e in envs]))
+    rng = np.random.RandomState(3)
+    emitted = 0
+    for t in range(25):
+        acts = rng.randint(0, 3, size=(N, 3)).astype(np.uint8)
+        obs, rew, done, info = be.step(acts)
+        for e, env in enumerate(envs):
+            draws[e].tick()
+            o, r, d, inf = env.step([int(a) for a in acts[e]])
+            assert np.array_equal(obs[e], o) and np.array_equal(rew[e], np.asarray(r)), (t, e)
+            assert np.array_equal(done[e].astype(bool), np.asarray(d)), (t, e)
+            assert bool(info['finished'][e]) == bool(inf), (t, e)
+            if inf:
+                emitted += 1
+                assert list(info['rank'][e]) == list(inf['rank'])
+                assert np.array_equal(info['episode_scores'][e], inf['episode_scores'])
+                assert np.array_equal(info['episode_steps'][e], inf['episode_steps'])
+        assert np.array_equal(be.grid()[0].reshape(N, 9, 9), np.stack([e.grid for e in envs])), t
+    assert emitted >= N * 15                               # every step from the cap on emits info again
+    assert be.errors() == 0
+    be.close()
+
+
 def test_gpu_long_spawn_pose_matches_oracle():
     """snake_length 6 on a 7x9 grid: bent spawn poses and the head-boxed pruning of the DFS table."""
     kw = dict(height=7, width=9, num_snakes=2, snake_length=6, vision_range=2, num_fruits=3)
