@@ -87,7 +87,7 @@ def test_reward_dict_keys_and_action_errors():
 
 
 # ------------------------------------------------------------------ live reference (container only)
-def _compare_with_live_reference(kw, env_id='Snake-v1', steps=400, n_actions=3):
+def _compare_with_live_reference(kw, env_id='Snake-v1', steps=400, n_actions=3, reset_on_done=True):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, os.path.join(root, 'oracle', 'gym_stub'))
     sys.path.insert(1, '/root/reference/marlenv')
@@ -103,7 +103,7 @@ def _compare_with_live_reference(kw, env_id='Snake-v1', steps=400, n_actions=3):
             out = [env.reset()]
             for a in acts:
                 o, r, d, info = env.step([int(x) for x in a])
-                if all(d):
+                if all(d) and reset_on_done:
                     o = env.reset()
                 out.append((o, list(r), list(d), sorted(info.keys()),
                             [list(np.asarray(info[k], dtype=np.float64)) for k in sorted(info.keys())],
@@ -135,6 +135,17 @@ def _compare_with_live_reference(kw, env_id='Snake-v1', steps=400, n_actions=3):
 ])
 def test_same_seed_as_live_reference(kw):
     _compare_with_live_reference(kw)
+
+
+@pytest.mark.needs_reference
+@pytest.mark.parametrize('kw', [
+    dict(height=9, width=9, num_snakes=3, snake_length=3, vision_range=2, max_episode_steps=6, num_fruits=2),
+    dict(height=8, width=10, num_snakes=2, snake_length=2, frame_stack=2, num_fruits=1),
+])
+def test_stepping_a_finished_env_like_the_live_reference(kw):
+    """No reset after the episode ends (probe g3): the reference keeps stepping -- capped episodes
+    move on, dead snakes return 0 / True, info is emitted again every step."""
+    _compare_with_live_reference(kw, steps=60, reset_on_done=False)
 
 
 def small_fuzz_configs(n, seed):
