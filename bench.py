@@ -37,6 +37,9 @@ def parse():
     ap.add_argument('--warmup', type=int, default=100)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--envs-per-gpu', type=int, default=1 << 20)
+    ap.add_argument('--envs-total', type=int, default=0,
+                    help='strong scaling: this many environments in total, sharded over the ranks '
+                         '(BASELINE cfg5 read literally: 1048576); default 0 = weak scaling, --envs-per-gpu each')
     ap.add_argument('--e2e-steps', type=int, default=8)
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -177,7 +180,13 @@ def ours(args):
         cpu = {'value': v, 'unit': 'agent-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample}
         cpu_native = cpu_native_leg()
 
-    N, ns = args.envs_per_gpu, ENV_KW['num_snakes']
+    ns = ENV_KW['num_snakes']
+    if args.envs_total:
+        if args.envs_total % world:
+            raise SystemExit('--envs-total must be a multiple of the number of GPUs')
+        N = args.envs_total // world
+    else:
+        N = args.envs_per_gpu
     batch = SnakeBatch(N, device=local, seed=0, rng='philox', auto_reset=True, env_id_offset=rank * N, **ENV_KW)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     # A short action cycle would trap snakes in closed orbits (net turn of the cycle != 0 closes the
@@ -289,7 +298,8 @@ def ours(args):
         out = {
             'metric': 'agent_steps_per_sec', 'value': value, 'unit': 'agent-steps/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+            'higher_is_better': True, 'scaling': 'strong' if args.envs_total else 'weak', 'vs_baseline': None,
+            'dtype': 'u8', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'envs_per_gpu': N, 'global_envs': N * world, 'burn_in_steps': BURN_IN,
                        'l2': 'no flush: per-step working set (records %.0f MB read + written, obs %.0f MB written) '
                              'exceeds the 126 MB L2' % (N * rec_bytes / 1e6, N * obs_bytes / 1e6),
