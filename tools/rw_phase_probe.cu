@@ -11,7 +11,10 @@
 #include <cstdlib>
 #include <cuda_runtime.h>
 
-constexpr int REC_TILE = 5248, OBS_TILE = 30976;     // bytes per tile (8 envs x 656 B, 8 x 3872 B)
+#ifndef REC_ENV_BYTES
+#define REC_ENV_BYTES 544                            // 656 with the separate direction plane
+#endif
+constexpr int REC_TILE = 8 * REC_ENV_BYTES, OBS_TILE = 30976;     // bytes per tile (8 envs x record, 8 x 3872 B)
 
 __global__ void pure_write(uint4* __restrict__ dst, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -28,7 +31,7 @@ __global__ void tile_pattern(uint8_t* __restrict__ recs, uint8_t* __restrict__ o
   const int lane = threadIdx.x & 31;
   uint4* r = reinterpret_cast<uint4*>(recs + (size_t)tile * REC_TILE);
   uint4 acc = make_uint4(0, 0, 0, 0);
-  uint4 keep[11];
+  uint4 keep[11];   // up to 11 x 512 B per warp
 #pragma unroll
   for (int k = 0; k < 11; ++k) {
     const int i = lane + 32 * k;
@@ -52,7 +55,7 @@ __global__ void tile_pattern_sparse(uint8_t* __restrict__ recs, uint8_t* __restr
   const int lane = threadIdx.x & 31;
   uint4* r = reinterpret_cast<uint4*>(recs + (size_t)tile * REC_TILE);
   uint4 acc = make_uint4(0, 0, 0, 0);
-  uint4 keep[11];
+  uint4 keep[11];   // up to 11 x 512 B per warp
 #pragma unroll
   for (int k = 0; k < 11; ++k) {
     const int i = lane + 32 * k;
