@@ -85,10 +85,12 @@ def test_gpu_shard_invariance():
         assert np.array_equal(o, np.concatenate([o1, o2])) and np.array_equal(r, np.concatenate([r1, r2]))
 
 
-def test_gpu_invariants_full_size():
-    """BASELINE cfg5 shard (131072 envs): size-independent properties after 64 steps."""
+@pytest.mark.parametrize('N', [131072, 1048576])
+def test_gpu_invariants_full_size(N):
+    """BASELINE cfg5 at its full size (1,048,576 envs, warp-private tiles) and one 8-GPU shard of it (131,072
+    envs, cooperative tiles): size-independent properties after 64 steps."""
     from marl_snake_b200 import SnakeBatch
-    N, ns = 131072, 4
+    ns = 4
     b = SnakeBatch(N, num_snakes=ns, vision_range=5, seed=1)
     b.reset()
     g = torch.Generator(device='cuda').manual_seed(0)
@@ -121,6 +123,31 @@ def test_gpu_invariants_full_size():
     assert int(obs.max()) == 1
     live_env = ~info['finished']            # envs reset this step return the terminal dones (A1)
     assert torch.equal(done[live_env], ~alive[live_env])
+    assert b.device_errors() == 0
+
+
+def test_gpu_full_size_prefix_matches_rule_source():
+    """The first 2,500 and the last 1,500 environments of a 1,048,576-env batch (BASELINE cfg5, the bench's
+    own configuration) against the host build of the rule source stepping only those environments: Philox
+    streams are keyed by global env id, so every output of those environments must be bit-identical."""
+    from hostsim_util import HostSim
+    from marl_snake_b200 import SnakeBatch
+    N, ns, head, tail = 1 << 20, 4, 2500, 1500
+    kw = dict(height=20, width=20, num_snakes=ns, snake_length=3, vision_range=5)
+    b = SnakeBatch(N, seed=9, **kw)
+    lo = HostSim(head, kw, rng_mode=0, auto_reset=1, seed=9)
+    hi = HostSim(tail, kw, rng_mode=0, auto_reset=1, seed=9, env_id_offset=N - tail)
+    obs = b.reset()
+    assert np.array_equal(obs[:head].cpu().numpy(), lo.reset()) and np.array_equal(obs[N - tail:].cpu().numpy(), hi.reset())
+    g = torch.Generator(device='cuda').manual_seed(4)
+    for t in range(40):
+        a = torch.randint(0, 3, (N, ns), dtype=torch.uint8, device='cuda', generator=g)
+        obs, rew, done, info = b.step(a)
+        for sim, sl in ((lo, slice(0, head)), (hi, slice(N - tail, N))):
+            o, r, d, i = sim.step(a[sl].cpu().numpy())
+            assert np.array_equal(obs[sl].cpu().numpy(), o), t
+            assert np.array_equal(rew[sl].cpu().numpy(), r) and np.array_equal(done[sl].cpu().numpy(), d.astype(bool)), t
+            assert np.array_equal(info['finished'][sl].cpu().numpy(), i['finished'].astype(bool)), t
     assert b.device_errors() == 0
 
 
