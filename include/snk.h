@@ -180,6 +180,14 @@ int snk_get_state(snk_env* env, const snk_state_view* out, void* stream);
  * of the given grid.  obs_dev (may be NULL) receives that stacked observation. */
 int snk_set_state(snk_env* env, const snk_state_view* in, uint8_t* obs_dev, void* stream);
 
+/* Exact checkpoint / resume of a shard (the reference never saves env state; its trainers checkpoint only
+ * their networks, train_dqn.py:356-383): the raw records, frame histories and rollout statistics as one host
+ * blob.  A handle created with the same configuration (same seed and env_id_offset for the same Philox
+ * stream; replay streams are set separately) continues bit for bit after snk_checkpoint_load. */
+size_t snk_checkpoint_bytes(const snk_env* env);
+int snk_checkpoint_save(snk_env* env, void* blob_host, size_t bytes);
+int snk_checkpoint_load(snk_env* env, const void* blob_host, size_t bytes);
+
 /* Replay mode: per-env streams of recorded draw OUTPUTS in consumption order -- per reset the ns
  * accepted spawn-candidate indices (np.random.permutation, snake_env.py:581) then the fruit ranks
  * (np.random.randint, grid_util.py:130); per step its fruit ranks.  draws_host holds all streams

@@ -66,6 +66,9 @@ PROTOTYPES = {
     'snk_widen_bits_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     'snk_get_state': (C.c_int, [C.c_void_p, C.POINTER(SnkStateView), C.c_void_p]),
     'snk_set_state': (C.c_int, [C.c_void_p, C.POINTER(SnkStateView), C.c_void_p, C.c_void_p]),
+    'snk_checkpoint_bytes': (C.c_size_t, [C.c_void_p]),
+    'snk_checkpoint_save': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    'snk_checkpoint_load': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     'snk_set_replay': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'snk_replay_cursors': (C.c_int, [C.c_void_p, C.c_void_p]),
     'snk_device_errors': (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.c_int]),

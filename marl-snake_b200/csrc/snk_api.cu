@@ -545,6 +545,51 @@ extern "C" int snk_set_state(snk_env* h, const snk_state_view* in, uint8_t* obs_
   return SNK_OK;
 }
 
+// ---- exact checkpoint: the raw records (grid, snakes, counters, Philox event, replay cursor, statistics),
+// the frame histories and the rollout statistics vector, byte for byte
+static const uint64_t CKPT_MAGIC = 0x0031544B434B4E53ull;     // "SNKCKT1"
+struct CkptHeader { uint64_t magic; int32_t N, H, W, ns, K, V, fs, dig, rec_bytes, hist_env_bytes; double env_steps; };
+
+extern "C" size_t snk_checkpoint_bytes(const snk_env* h) {
+  if (!h) return 0;
+  return sizeof(CkptHeader) + (size_t)h->d.N * ((size_t)h->d.rec_bytes + (size_t)h->d.hist_env_bytes) + STAT_COUNT * sizeof(double);
+}
+
+extern "C" int snk_checkpoint_save(snk_env* h, void* blob_host, size_t bytes) {
+  if (!h || !blob_host) return fail(SNK_E_INVALID, "null argument");
+  if (bytes < snk_checkpoint_bytes(h)) return fail(SNK_E_INVALID, "checkpoint buffer too small: %zu < %zu", bytes, snk_checkpoint_bytes(h));
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  const Dims& d = h->d;
+  uint8_t* out = (uint8_t*)blob_host;
+  CkptHeader hd = {CKPT_MAGIC, d.N, d.H, d.W, d.ns, d.K, d.V, d.fs, d.dig, d.rec_bytes, d.hist_env_bytes, h->env_steps};
+  memcpy(out, &hd, sizeof hd); out += sizeof hd;
+  CU(cudaMemcpy(out, h->recs, (size_t)d.N * d.rec_bytes, cudaMemcpyDeviceToHost)); out += (size_t)d.N * d.rec_bytes;
+  if (d.hist_env_bytes) { CU(cudaMemcpy(out, h->hist, (size_t)d.N * d.hist_env_bytes, cudaMemcpyDeviceToHost)); out += (size_t)d.N * d.hist_env_bytes; }
+  CU(cudaMemcpy(out, h->stats, STAT_COUNT * sizeof(double), cudaMemcpyDeviceToHost));
+  return SNK_OK;
+}
+
+extern "C" int snk_checkpoint_load(snk_env* h, const void* blob_host, size_t bytes) {
+  if (!h || !blob_host) return fail(SNK_E_INVALID, "null argument");
+  if (bytes < snk_checkpoint_bytes(h)) return fail(SNK_E_INVALID, "checkpoint too small for this handle");
+  const Dims& d = h->d;
+  const uint8_t* in = (const uint8_t*)blob_host;
+  CkptHeader hd;
+  memcpy(&hd, in, sizeof hd); in += sizeof hd;
+  if (hd.magic != CKPT_MAGIC || hd.N != d.N || hd.H != d.H || hd.W != d.W || hd.ns != d.ns || hd.K != d.K || hd.V != d.V ||
+      hd.fs != d.fs || hd.dig != d.dig || hd.rec_bytes != d.rec_bytes || hd.hist_env_bytes != d.hist_env_bytes)
+    return fail(SNK_E_INVALID, "checkpoint was written by a handle of a different shape");
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(h->recs, in, (size_t)d.N * d.rec_bytes, cudaMemcpyHostToDevice)); in += (size_t)d.N * d.rec_bytes;
+  if (d.hist_env_bytes) { CU(cudaMemcpy(h->hist, in, (size_t)d.N * d.hist_env_bytes, cudaMemcpyHostToDevice)); in += (size_t)d.N * d.hist_env_bytes; }
+  CU(cudaMemcpy(h->stats, in, STAT_COUNT * sizeof(double), cudaMemcpyHostToDevice));
+  h->env_steps = hd.env_steps;
+  h->was_reset = true;
+  return SNK_OK;
+}
+
 extern "C" int snk_set_replay(snk_env* h, const int32_t* draws_host, const int64_t* offsets_host) {
   if (!h || !offsets_host) return fail(SNK_E_INVALID, "null argument");
   if (h->d.rng_mode != RNG_REPLAY) return fail(SNK_E_STATE, "handle was not created with SNK_RNG_REPLAY");

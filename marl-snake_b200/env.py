@@ -219,6 +219,18 @@ class SnakeBatch:
         torch.cuda.current_stream(self.device).synchronize()      # `keep` must outlive the kernels
         return self._obs
 
+    def save_checkpoint(self):
+        """Exact state of the shard as a NumPy byte array (records, frame histories, statistics); a batch
+        created with the same arguments continues bit for bit after load_checkpoint()."""
+        n = int(lib.snk_checkpoint_bytes(self._h))
+        blob = np.empty(n, dtype=np.uint8)
+        check(lib.snk_checkpoint_save(self._h, blob.ctypes.data_as(C.c_void_p), n))
+        return blob
+
+    def load_checkpoint(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        check(lib.snk_checkpoint_load(self._h, blob.ctypes.data_as(C.c_void_p), blob.size))
+
     def set_replay(self, draws_per_env):
         """draws_per_env: sequence of N int arrays -- recorded draw outputs in consumption order."""
         assert len(draws_per_env) == self.num_envs

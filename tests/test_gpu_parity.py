@@ -772,6 +772,40 @@ def test_gpu_step_host_info_matches_device_path(N):
     assert seen >= N * 2                                   # the step cap ended every env at least twice
 
 
+@pytest.mark.parametrize('kw', [dict(num_snakes=4, vision_range=5), dict(num_snakes=3, vision_range=3, frame_stack=4),
+                                dict(num_snakes=9, height=16, width=16, vision_range=2, max_episode_steps=15)])
+def test_gpu_exact_checkpoint_resume(kw):
+    """snk_checkpoint_save / _load: a second batch continues bit for bit -- grid, frame history, episode
+    statistics, Philox position and rollout statistics included."""
+    from marl_snake_b200 import SnakeBatch, SnkError
+    N, ns = 700, kw['num_snakes']
+    a, b = SnakeBatch(N, seed=44, **kw), SnakeBatch(N, seed=44, **kw)
+    a.reset()
+    g = torch.Generator(device='cuda').manual_seed(1)
+    for _ in range(25):
+        a.step(torch.randint(0, 3, (N, ns), dtype=torch.uint8, device='cuda', generator=g))
+    blob = a.save_checkpoint()
+    b.load_checkpoint(blob)
+    for t in range(40):
+        act = torch.randint(0, 3, (N, ns), dtype=torch.uint8, device='cuda', generator=g)
+        oa, ra, da, ia = a.step(act)
+        ob, rb, db, ib = b.step(act)
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db), t
+        fin = ia['finished']
+        assert torch.equal(fin, ib['finished']), t
+        for k in ia:                              # terminal arrays are only defined for finished envs
+            assert torch.equal(ia[k][fin], ib[k][fin]), (k, t)
+    sa, sb = a.stats(), b.stats()
+    for k in sa:                                  # counters are exact; the return sum is a float64 atomicAdd
+        if k == 'return_sum':                     # reduction whose order differs from launch to launch
+            assert abs(sa[k] - sb[k]) <= 1e-9 * max(1.0, abs(sa[k])), k
+        else:
+            assert sa[k] == sb[k], k
+    other = SnakeBatch(N + 1, seed=44, **kw)
+    with pytest.raises(SnkError):
+        other.load_checkpoint(blob)
+
+
 def test_gpu_state_roundtrip():
     """get_state -> set_state on a second batch reproduces the trajectory (checkpoint / restore)."""
     from marl_snake_b200 import SnakeBatch
