@@ -47,7 +47,8 @@ enum {
                                     snake_env.py:606); 'human' ignores unknown actions as the reference does */
   SNK_DEV_REPLAY_UNDERRUN = 2,   /* replay stream exhausted                                         */
   SNK_DEV_REPLAY_RANGE = 4,      /* replayed draw out of range / replayed spawn overlaps            */
-  SNK_DEV_SPAWN_GIVEUP = 8       /* no overlap-free spawn found within the attempt cap               */
+  SNK_DEV_SPAWN_GIVEUP = 8,      /* no overlap-free spawn found within the attempt cap               */
+  SNK_DEV_INTERNAL = 16          /* a bounds / alignment check failed (debug build, -DSNK_DEBUG_CHECKS) */
 };
 
 enum { SNK_RNG_PHILOX = 0, SNK_RNG_REPLAY = 1 };

@@ -14,7 +14,8 @@ SNK_ABI_VERSION = 1
 SNK_RNG_PHILOX, SNK_RNG_REPLAY = 0, 1
 SNK_XFER_RAW, SNK_XFER_PACKED = 0, 1
 DEV_ERRORS = {1: 'action outside {0,1,2}', 2: 'replay stream exhausted',
-              4: 'replayed draw out of range / replayed spawn overlaps', 8: 'spawn sampling gave up'}
+              4: 'replayed draw out of range / replayed spawn overlaps', 8: 'spawn sampling gave up',
+              16: 'internal bounds check failed (debug build)'}
 STAT_NAMES = ('episodes', 'return_sum', 'episode_steps_sum', 'fruits_sum', 'kills_sum', 'deaths',
               'env_steps', 'reserved')
 

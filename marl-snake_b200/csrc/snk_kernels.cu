@@ -30,6 +30,32 @@ enum : uint8_t { F_RESET = 1, F_INIT = 2, F_SKIP = 4 };
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+// ---- debug build (-DSNK_DEBUG_CHECKS -> libsnk_dbg.so): compute-sanitizer is not available on the GPU pool, so
+// this build checks every observation / history store against the caller's buffers and every grid index against
+// the record, and raises the sticky ERR_INTERNAL bit.  The test suite runs against it via SNK_LIB_PATH.
+#ifdef SNK_DEBUG_CHECKS
+__device__ const uint8_t* dbg_obs_lo; __device__ const uint8_t* dbg_obs_hi;
+__device__ const uint8_t* dbg_hist_lo; __device__ const uint8_t* dbg_hist_hi;
+__device__ uint32_t* dbg_err;
+__device__ __forceinline__ void dbg_arm(const KParams& p) {        // every thread writes the same values
+  dbg_obs_lo = p.obs; dbg_obs_hi = p.obs ? p.obs + (size_t)p.d.N * p.d.obs_env_bytes : nullptr;
+  dbg_hist_lo = p.hist; dbg_hist_hi = p.hist ? p.hist + (size_t)p.d.N * p.d.hist_env_bytes : nullptr;
+  dbg_err = p.err;
+}
+__device__ __forceinline__ void dbg_store(const void* q, size_t n, const uint8_t* lo, const uint8_t* hi) {
+  const uint8_t* a = reinterpret_cast<const uint8_t*>(q);
+  if (a < lo || a + n > hi || (reinterpret_cast<uintptr_t>(a) & (n - 1))) atomicOr(dbg_err, ERR_INTERNAL);
+}
+#define SNK_CHECK_OBS(q, n) dbg_store((q), (n), dbg_obs_lo, dbg_obs_hi)
+#define SNK_CHECK_HIST(q, n) dbg_store((q), (n), dbg_hist_lo, dbg_hist_hi)
+#define SNK_ASSERT(p, cond) do { if (!(cond)) atomicOr((p).err, ERR_INTERNAL); } while (0)
+#else
+#define SNK_CHECK_OBS(q, n) ((void)0)
+#define SNK_CHECK_HIST(q, n) ((void)0)
+#define SNK_ASSERT(p, cond) ((void)0)
+#endif
+
+
 // ---- phase R helpers (warp-cooperative) -----------------------------------------------------------
 
 // 0x80 in every byte of x that is zero (exact, no carries between bytes).
@@ -118,6 +144,7 @@ __device__ __noinline__ void place_fruits_warp(const KParams& p, uint8_t* rec_ba
     if ((int)lane == j) mycell = cell;
   }
   __syncwarp();
+  SNK_ASSERT(p, mycell < HW);
   if (mycell >= 0) r.grid[mycell] = (uint8_t)FRUIT;
   __syncwarp();
 }
@@ -241,8 +268,14 @@ struct Shape {
   }
 };
 
-__device__ __forceinline__ void st_cs_128(void* p, uint2 a, uint2 b) { __stcs(reinterpret_cast<uint4*>(p), make_uint4(a.x, a.y, b.x, b.y)); }
-__device__ __forceinline__ void st_cs_64(void* p, uint2 a) { __stcs(reinterpret_cast<uint2*>(p), a); }
+__device__ __forceinline__ void st_cs_128(void* p, uint2 a, uint2 b) {
+  SNK_CHECK_OBS(p, 16);
+  __stcs(reinterpret_cast<uint4*>(p), make_uint4(a.x, a.y, b.x, b.y));
+}
+__device__ __forceinline__ void st_cs_64(void* p, uint2 a) {
+  SNK_CHECK_OBS(p, 8);
+  __stcs(reinterpret_cast<uint2*>(p), a);
+}
 
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
   uint32_t v;
@@ -320,6 +353,7 @@ __device__ __forceinline__ GroupOut step_group(const KParams& p, const SH& sh, R
     if (a > 2u && !d.observer) { atomicOr(p.err, ERR_BAD_ACTION); a = 0; }
     dirv = d.observer ? turn_absolute(r.dir[i], a) : turn_relative(r.dir[i], a);            // :598-632
     tgt = (uint32_t)(r.head[i] + dir_delta(dirv, W));
+    SNK_ASSERT(p, tgt < (uint32_t)d.HW && r.head[i] < d.HW && r.tail[i] < d.HW);
   }
   // 2. one verdict per distinct target cell, on the pre-move grid                      :521-544
   const uint32_t same = __match_any_sync(FULL, tgt) & gmask;     // snakes of my env entering my cell
@@ -376,6 +410,7 @@ __device__ __forceinline__ GroupOut step_group(const KParams& p, const SH& sh, R
       const int hd = r.head[i];
 #pragma unroll 1
       for (int guard = 0; guard < d.HW; ++guard) {
+        SNK_ASSERT(p, (unsigned)c < (unsigned)d.HW);
         const int nxt = c + dir_delta(body_dir(d, r, c), W);
         r.grid[c] = (uint8_t)EMPTY;
         if (c == hd) break;
@@ -384,6 +419,7 @@ __device__ __forceinline__ GroupOut step_group(const KParams& p, const SH& sh, R
     } else if (!eater) {
       const int ot = r.tail[i];
       new_tail = ot + dir_delta(body_dir(d, r, ot), W);
+      SNK_ASSERT(p, (unsigned)new_tail < (unsigned)d.HW);
       r.grid[ot] = (uint8_t)EMPTY;
     } else {
       new_tail = r.tail[i];
@@ -677,8 +713,12 @@ __device__ __forceinline__ void encode_viewer_reg(const KParams& p, const SH& sh
   const uint32_t a1 = (e1 & bad) ? lutv32 : gorg + ((e1 & 0x7fffffffu) >> B);
   const uint32_t a2 = (e2 & bad) ? lutv32 : gorg + ((e2 & 0x7fffffffu) >> B);
   const uint32_t a3 = (e3 & bad) ? lutv32 : gorg + ((e3 & 0x7fffffffu) >> B);
+  SNK_ASSERT(p, (a0 == lutv32 || a0 - grid32 < (uint32_t)p.d.HW) && (a1 == lutv32 || a1 - grid32 < (uint32_t)p.d.HW) &&
+                (a2 == lutv32 || a2 - grid32 < (uint32_t)p.d.HW) && (a3 == lutv32 || a3 - grid32 < (uint32_t)p.d.HW));
   const uint32_t cm = (uint32_t)p.d.code_mask;
   const uint32_t k0 = lds_u8(a0) & cm, k1 = lds_u8(a1) & cm, k2 = lds_u8(a2) & cm, k3 = lds_u8(a3) & cm;
+  SNK_ASSERT(p, k0 < (uint32_t)sh.lut_stride() && k1 < (uint32_t)sh.lut_stride() && k2 < (uint32_t)sh.lut_stride() &&
+                k3 < (uint32_t)sh.lut_stride());
   const uint2 q0 = lds_v2(lutv32 + k0 * 8u), q1 = lds_v2(lutv32 + k1 * 8u);
   const uint2 q2 = lds_v2(lutv32 + k2 * 8u), q3 = lds_v2(lutv32 + k3 * 8u);
   const int ca0 = 2 * lane - shift, ca1 = ca0 + 64;
@@ -774,11 +814,15 @@ __device__ __forceinline__ void encode_env_stacked(const KParams& p, const SH& s
           f0 = *reinterpret_cast<const uint32_t*>(srow + (size_t)((hpos + 1) & 3) * d.ohw_p + c4);
           f1 = *reinterpret_cast<const uint32_t*>(srow + (size_t)((hpos + 2) & 3) * d.ohw_p + c4);
           f2 = *reinterpret_cast<const uint32_t*>(srow + (size_t)((hpos + 3) & 3) * d.ohw_p + c4);
+          SNK_CHECK_HIST(hrow + (size_t)hpos * d.ohw_p + c4, 4);
           *reinterpret_cast<uint32_t*>(hrow + (size_t)hpos * d.ohw_p + c4) = nw;
         } else {                                   // reset: every slot holds the first frame (:452-457)
           f0 = f1 = f2 = nw;
 #pragma unroll
-          for (int f = 0; f < 4; ++f) *reinterpret_cast<uint32_t*>(hrow + (size_t)f * d.ohw_p + c4) = nw;
+          for (int f = 0; f < 4; ++f) {
+            SNK_CHECK_HIST(hrow + (size_t)f * d.ohw_p + c4, 4);
+            *reinterpret_cast<uint32_t*>(hrow + (size_t)f * d.ohw_p + c4) = nw;
+          }
         }
         if (want_obs) {
           const uint32_t t0 = __byte_perm(f0, f1, 0x5140), t1 = __byte_perm(f2, nw, 0x5140);
@@ -814,10 +858,12 @@ __device__ __forceinline__ void encode_env_stacked(const KParams& p, const SH& s
         const uint8_t bits = lut[code];
         if (!init) {
           if (want_obs) stg[(size_t)cell * fs + (fs - 1)] = bits;
+          SNK_CHECK_HIST(hrow + (size_t)hpos * d.ohw_p + cell, 1);
           hrow[(size_t)hpos * d.ohw_p + cell] = bits;
         } else {
           for (int f = 0; f < fs; ++f) {
             if (want_obs) stg[(size_t)cell * fs + f] = bits;
+            SNK_CHECK_HIST(hrow + (size_t)f * d.ohw_p + cell, 1);
             hrow[(size_t)f * d.ohw_p + cell] = bits;
           }
         }
@@ -838,12 +884,14 @@ __device__ __forceinline__ void encode_env_stacked(const KParams& p, const SH& s
         uint4 qv;
         qv.x = spread4(two & 15u); qv.y = spread4((two >> 4) & 15u);
         qv.z = spread4((two >> 8) & 15u); qv.w = spread4(two >> 12);
+        SNK_CHECK_OBS(o4 + u, 16);
         __stcs(o4 + u, qv);
       }
     } else {
       uint2* o2 = reinterpret_cast<uint2*>(out);
       for (int u = (int)lane; u < total; u += 32) {
         const uint32_t b = s_stage[u];
+        SNK_CHECK_OBS(o2 + u, 8);
         __stcs(o2 + u, make_uint2(spread4(b & 15u), spread4(b >> 4)));
       }
     }
@@ -862,6 +910,9 @@ __global__ void __launch_bounds__(kCoop ? SNK_MAX_THREADS_COOP : SNK_MAX_THREADS
 snk_tile_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const Dims& d = p.d;
+#ifdef SNK_DEBUG_CHECKS
+  dbg_arm(p);
+#endif
   const Shape<kNS, kW, kOH, kOW, kFS> sh(d);
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, nwarps = nt >> 5;
