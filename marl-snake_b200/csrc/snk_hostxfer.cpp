@@ -8,6 +8,7 @@
 // widening of what the GPU produced, nothing else.
 #include <pthread.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <condition_variable>
@@ -57,7 +58,8 @@ __attribute__((target("avx512f,avx512bw"))) void widen_avx512(const uint8_t* src
 }
 bool cpu_has_avx512bw() {
   static const bool has = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
-  return has;
+  const char* off = getenv("SNK_NO_AVX512");          // tests exercise the scalar path on AVX-512 hosts with it
+  return has && !(off && *off == '1');
 }
 #endif
 

@@ -67,10 +67,13 @@ def test_spawn_table_matches_reference_enumeration():
 
 @pytest.mark.parametrize('n,threads,misalign', [(0, 1, 0), (1, 1, 0), (7, 1, 0), (121 * 4, 1, 0), (100003, 1, 0),
                                                  (100003, 4, 0), (1 << 20, 8, 0), (4099, 3, 8), (4099, 1, 3)])
-def test_widen_bits_host_is_little_endian_unpackbits(n, threads, misalign):
+@pytest.mark.parametrize('scalar', [False, True])
+def test_widen_bits_host_is_little_endian_unpackbits(monkeypatch, n, threads, misalign, scalar):
     """Host half of the packed transport: byte u, bit c -> obs byte 8*u + c (channel order of
-    snake_env.py:484-492).  Any size, any thread count, any output alignment."""
+    snake_env.py:484-492).  Any size, any thread count, any output alignment, AVX-512 or the scalar table."""
     import marl_snake_b200 as m
+    if scalar:
+        monkeypatch.setenv('SNK_NO_AVX512', '1')
     rng = np.random.RandomState(n + threads)
     bits = rng.randint(0, 256, size=n).astype(np.uint8)
     buf = np.full(8 * n + 64 + misalign, 0xAB, dtype=np.uint8)
