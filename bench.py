@@ -308,7 +308,7 @@ def ours(args):
                        'mean_episode_steps_rank0': st_after['episode_steps_sum'] / max(st_after['episodes'], 1.0),
                        'device_errors': errs},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': traffic,
+                         'frac': achieved / peak, 'frac_of_nominal_8000_gbs': achieved / 8000.0, 'traffic': traffic,
                          'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured)' if peaks else 'fallback 6650',
                          'algorithmic_bytes_per_env_step': bytes_per_env, 'kernel': 'snk_tile_kernel',
                          'launch_ms': ms / args.steps},
