@@ -43,14 +43,18 @@ def parse():
     ap.add_argument('--e2e-steps', type=int, default=8)
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-configs', action='store_true', help='skip the per-config block (cfg1-cfg4, strong scaling)')
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------ CPU legs
-def cpu_leg(seconds, chunk=250):
-    """Oracle port on all host cores for about `seconds`; returns (agent-steps/s, cores, sample text)."""
+def cpu_leg(seconds, kind, chunk=None):
+    """The reference's CPU step path on all host cores for about `seconds`: kind 'reference' = the UNMODIFIED
+    reference SnakeEnv installed in oracle/_ref (make -C oracle ref), kind 'port' = the oracle restatement.
+    Returns a cpu_baseline dict."""
     from oracle.cpu_runner import CpuPool
-    pool = CpuPool(ENV_KW)
+    chunk = chunk or (40 if kind == 'reference' else 250)
+    pool = CpuPool(ENV_KW, kind=kind)
     pool.run(chunk)
     total, wall = 0, 0.0
     while wall < seconds:
@@ -58,45 +62,41 @@ def cpu_leg(seconds, chunk=250):
         total += chunk
     pool.close()
     ns = ENV_KW['num_snakes']
-    val = total * pool.procs * ns / wall
-    return val, pool.procs, (f'{pool.procs} processes x 1 env (reference vectorisation), {total} env-steps each '
-                             f'incl. resets, {wall:.1f} s wall, Python {sys.version.split()[0]}')
+    what = ('unmodified reference SnakeEnv (oracle/_ref, gym stubbed)' if kind == 'reference'
+            else 'oracle port (oracle/snake_oracle.py)')
+    return {'value': total * pool.procs * ns / wall, 'unit': 'agent-steps/s', 'cores': pool.procs, 'kind': kind,
+            'sample': f'{what}: {pool.procs} processes x 1 env (reference vectorisation, wrappers.py:211-212), '
+                      f'{total} env-steps each incl. resets, {wall:.1f} s wall, Python {sys.version.split()[0]}'}
 
 
-def cpu_native_leg(seconds=4.0, n_envs=256):
+def reference_kind():
+    from oracle.cpu_runner import reference_available
+    return 'reference' if reference_available() else 'port'
+
+
+def cpu_native_leg(seconds=4.0):
     """Extra context, single thread: the device rule source compiled for the host (tests/hostsim, test
-    infrastructure) stepping `n_envs` envs -- what one CPU core does with native code instead of Python."""
+    infrastructure).  Runs in a SUBPROCESS so that no test code is loaded into the measuring process."""
+    import subprocess
     try:
-        sys.path.insert(0, os.path.join(ROOT, 'tests'))
-        import numpy as np
-        from hostsim_util import HostSim
-        hs = HostSim(n_envs, ENV_KW, rng_mode=0, auto_reset=1, seed=1)
-        hs.reset()
-        rng = np.random.RandomState(0)
-        acts = rng.randint(0, 3, size=(64, n_envs, ENV_KW['num_snakes'])).astype(np.uint8)
-        for t in range(8):
-            hs.step(acts[t])
-        t0, steps = time.perf_counter(), 0
-        while time.perf_counter() - t0 < seconds:
-            hs.step(acts[steps % 64])
-            steps += 1
-        wall = time.perf_counter() - t0
-        return {'value': steps * n_envs * ENV_KW['num_snakes'] / wall, 'unit': 'agent-steps/s', 'cores': 1,
-                'kind': 'native C++ host build of the rule source (tests/hostsim), incl. NumPy marshalling',
-                'sample': f'{n_envs} envs x {steps} steps, {wall:.1f} s'}
+        out = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'cpu_native_leg.py'), str(seconds)],
+                             capture_output=True, text=True, timeout=120)
+        return json.loads(out.stdout.strip().splitlines()[-1])
     except Exception as exc:      # noqa: BLE001
         return {'unavailable': repr(exc)}
 
 
 def reference_arm(args):
-    """--impl reference: the reference's CPU path (oracle port; the Python reference cannot travel to the
-    GPU box) on all host cores.  One 'step' = every worker process advances its env by 250 env-steps."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores -- the unmodified
+    reference from oracle/_ref when it was installed (kind "reference"), else the oracle port (kind "port").
+    One 'step' = every worker process advances its env by `chunk` env-steps (auto-reset included)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     from oracle.cpu_runner import CpuPool
-    chunk = 250
-    pool = CpuPool(ENV_KW)
+    kind = reference_kind()
+    chunk = 40 if kind == 'reference' else 250
+    pool = CpuPool(ENV_KW, kind=kind)
     for _ in range(max(args.warmup, 1)):
         pool.run(chunk)
     t = 0.0
@@ -105,16 +105,20 @@ def reference_arm(args):
     pool.close()
     ns = ENV_KW['num_snakes']
     val = args.steps * chunk * pool.procs * ns / t
-    sample = f'{pool.procs} processes x 1 env, {chunk} env-steps per bench step incl. resets'
-    print(json.dumps({
+    sample = (f'{"unmodified reference SnakeEnv from oracle/_ref" if kind == "reference" else "oracle port"}: '
+              f'{pool.procs} processes x 1 env, {chunk} env-steps per bench step incl. resets')
+    out = {
         'impl': 'reference', 'metric': 'agent_steps_per_sec', 'value': val, 'unit': 'agent-steps/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'envs_per_step': pool.procs, 'env_steps_per_bench_step': chunk},
-        'cpu_baseline': {'value': val, 'unit': 'agent-steps/s', 'cores': pool.procs, 'kind': 'port',
-                         'sample': sample},
+        'config': {'workload': WORKLOAD, 'envs_per_gpu': pool.procs, 'global_envs': pool.procs,
+                   'env_steps_per_bench_step': chunk},
+        'cpu_baseline': {'value': val, 'unit': 'agent-steps/s', 'cores': pool.procs, 'kind': kind, 'sample': sample},
         'e2e': {'value': val, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0}), file=RESULT_OUT, flush=True)
+        'gpu_launches': 0}
+    if kind == 'reference':           # the port beside it: how much faster the restatement is than the reference
+        out['cpu_port'] = cpu_leg(4.0, 'port')
+    print(json.dumps(out), file=RESULT_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------ clocks
@@ -174,10 +178,12 @@ def ours(args):
     dev = torch.device('cuda', local)
 
     # CPU baseline first (rank 0, N=1 only), before the GPU is busy
-    cpu = None
+    cpu = cpu_port = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, sample = cpu_leg(args.cpu_seconds)
-        cpu = {'value': v, 'unit': 'agent-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+        kind = reference_kind()
+        cpu = cpu_leg(args.cpu_seconds, kind)
+        if kind == 'reference':
+            cpu_port = cpu_leg(5.0, 'port')
         cpu_native = cpu_native_leg()
 
     ns = ENV_KW['num_snakes']
@@ -275,6 +281,47 @@ def ours(args):
     assert torch.equal(h_obs[:, :, V, V, 5].bool(), alive_now), 'packed transport: observation/state mismatch'
     assert int(h_obs[:8192].view(-1, 8).sum(1).max()) == 1
 
+    # ---- the other BASELINE configs (driver-visible): cfg1 single-env latency through make_snake, cfg2 / cfg3 /
+    #      cfg4 device-timed (1 GPU runs only); for N > 1 the strong-scaling reading of cfg5 (1,048,576 envs in
+    #      total, sharded over the ranks, max over ranks).
+    del h_obs, h_rew, h_done
+    mean_ep = st_after['episode_steps_sum'] / max(st_after['episodes'], 1.0)
+    algo_rec_bytes = batch.algorithmic_bytes_per_env_step()
+    obs_shape = batch.obs_shape
+    batch.close()
+    del batch, pool
+    torch.cuda.empty_cache()
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import bench_configs as bc
+    configs = {}
+    if not args.no_configs:
+        if world == 1:
+            configs['cfg1'] = bc.measure_single_env()
+            configs['cfg2'] = bc.measure('cfg2', steps=2000)
+            configs['cfg2_graph'] = bc.measure('cfg2', steps=2000, graph=True)
+            if hasattr(SnakeBatch, 'step_many'):
+                configs['cfg2_step_many'] = bc.measure('cfg2', steps=2048, many=32)
+            configs['cfg3'] = bc.measure('cfg3', steps=300)
+            configs['cfg4'] = bc.measure('cfg4', steps=300)
+            configs['cfg5_shard_131072'] = bc.measure('cfg5_shard', steps=400)
+        else:
+            total = 1 << 20
+            kw = dict(bc.CONFIGS['cfg5_full'])
+            kw['num_envs'] = total // world
+            dist.barrier()
+            r = bc.measure('cfg5_strong', steps=400, kw=kw, device=local, env_id_offset=rank * (total // world))
+            tms = torch.tensor([r['ms_per_step']], device=dev, dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms_strong = float(tms.item())
+            scale = r['ms_per_step'] / ms_strong
+            rf = r['roofline']
+            configs['cfg5_strong'] = {
+                'config': 'cfg5 read literally: 1,048,576 envs in total, %d per GPU' % (total // world),
+                'scaling': 'strong', 'n_gpus': world, 'ms_per_step': ms_strong,
+                'agent_steps_per_sec': total * ns / (ms_strong * 1e-3),
+                'roofline_per_gpu': {'frac': rf['frac'] * scale, 'frac_record': rf['frac_record'] * scale,
+                                     'achieved': rf['achieved'] * scale, 'peak': rf['peak'], 'unit': 'GB/s'}}
+
     if rank == 0:
         peaks = {}
         try:
@@ -282,16 +329,18 @@ def ours(args):
         except Exception:
             pass
         peak = float(peaks.get('hbm_gbs', 6650.0))
-        bytes_per_env = batch.algorithmic_bytes_per_env_step()
+        bytes_rec = algo_rec_bytes                      # what the kernel moves: 2 x 544-byte record + obs + I/O
+        bytes_per_env = bc.survey_bytes_per_env_step(ENV_KW)   # 2*H*W + ns*(O + P + 38) = 4 824
         obs_bytes = 1
-        for x in batch.obs_shape:
+        for x in obs_shape:
             obs_bytes *= x
-        rec_bytes = (bytes_per_env - obs_bytes - 10 * ns) // 2
+        rec_bytes = (bytes_rec - obs_bytes - 10 * ns) // 2
         per_launch = bytes_per_env * N
         achieved = per_launch / (ms / args.steps * 1e-3) / 1e9
+        achieved_rec = bytes_rec * N / (ms / args.steps * 1e-3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get('dram_bytes_per_launch')
+            traffic = bc.traffic_per_launch('cfg5_full')
         except Exception:
             pass
         value = N * world * ns * args.steps / (ms * 1e-3)
@@ -305,13 +354,17 @@ def ours(args):
                              'exceeds the 126 MB L2' % (N * rec_bytes / 1e6, N * obs_bytes / 1e6),
                        'parallelism': f'env-shard x{world}', 'rng': 'philox seed 0',
                        'tile_envs': os.environ.get('SNK_TILE_ENVS', 'auto'), 'threads': os.environ.get('SNK_THREADS', 'auto'),
-                       'mean_episode_steps_rank0': st_after['episode_steps_sum'] / max(st_after['episodes'], 1.0),
+                       'mean_episode_steps_rank0': mean_ep,
                        'device_errors': errs},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'frac_of_nominal_8000_gbs': achieved / 8000.0, 'traffic': traffic,
                          'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured)' if peaks else 'fallback 6650',
-                         'algorithmic_bytes_per_env_step': bytes_per_env, 'kernel': 'snk_tile_kernel',
+                         'algorithmic_bytes_per_env_step': bytes_per_env,
+                         'bytes_formula': 'SURVEY.md 8(d): 2*H*W + ns*(O + P + 38) with a 400-byte state',
+                         'record_bytes_per_env_step': bytes_rec, 'achieved_record': achieved_rec,
+                         'frac_record': achieved_rec / peak, 'kernel': 'snk_tile_kernel',
                          'launch_ms': ms / args.steps},
+            'configs': configs,
             'e2e': {'value': N * world * ns * K2 / e2e_s, 'unit': 'agent-steps/s',
                     # bytes that cross PCIe per step per rank: actions in; channel-bit observations, float64
                     # rewards and dones out.  The call delivers N*obs_bytes of uint8 NHWC into the host buffer.
@@ -334,6 +387,8 @@ def ours(args):
         }
         if cpu:
             out['cpu_baseline'] = cpu
+            if cpu_port:
+                out['cpu_port'] = cpu_port
             out['cpu_native_1thread'] = cpu_native
         print(json.dumps(out), file=RESULT_OUT, flush=True)
     if world > 1:

@@ -338,7 +338,8 @@ struct GroupOut {
 // `active`: this lane holds a real snake of a real environment.  All 32 lanes must call.
 template <class SH>
 __device__ __forceinline__ GroupOut step_group(const KParams& p, const SH& sh, Rec& r, bool active, int i,
-                                               uint32_t gmask, int gbase, size_t io, uint32_t action) {
+                                               uint32_t gmask, int gbase, size_t io, uint32_t action,
+                                               uint32_t* kl_scratch) {
   const Dims& d = p.d;
   const uint32_t FULL = 0xffffffffu;
   const uint32_t lane = lane_id();
@@ -370,21 +371,21 @@ __device__ __forceinline__ GroupOut step_group(const KParams& p, const SH& sh, R
   int counter = r.hdr->alive_counter - __popc(__ballot_sync(FULL, died) & gmask);        // :334
 
   // 3. kill attribution, tail-growth rule                                              :338-346
-  int kl = 0, dec = 0;
-  bool victim = false;
+  //    No loop over the group: kill credit is a shared-memory scatter (one word per lane), the tail-growth
+  //    rule one more match on {eater: own tail, others: target cell}.
+  kl_scratch[lane] = 0u;
+  __syncwarp();
+  if (credit && owner < (uint32_t)G) atomicAdd(&kl_scratch[gbase + (int)owner], 1u);   // once per cell (C2)
   const uint32_t my_tail = active ? (uint32_t)r.tail[i] : 0u;
-  for (int j = 0; j < G; ++j) {
-    const int src = gbase + j;
-    const uint32_t oj = __shfl_sync(FULL, credit ? owner : 0xFFu, src);
-    kl += (oj == (uint32_t)i) ? 1 : 0;
-    const uint32_t tj = __shfl_sync(FULL, eater ? my_tail : 0xFFFFFFFFu, src);
-    const bool hit = was_alive && tgt == tj;            // I enter the tail of an eater: it stays (C4)
-    const int hits = __popc(__ballot_sync(FULL, hit) & gmask);
-    victim |= hit;
-    dec += hits;                                        // counted even if already dead
-    if (j == i) kl += hits;
-  }
-  counter -= dec;
+  // An eater's tail stays this step (:338-346): every snake entering it dies and is counted again even if
+  // it already died (C4); each such snake is one kill for the eater.  A target cell is FRUIT for an eater
+  // and TAIL for its victims, so an eater never matches as a victim, and tails of two snakes never coincide.
+  const uint32_t meet = __match_any_sync(FULL, eater ? my_tail : tgt) & gmask;
+  const uint32_t eaters = __ballot_sync(FULL, eater);
+  const bool victim = was_alive && !eater && (meet & eaters) != 0u;
+  counter -= __popc(__ballot_sync(FULL, victim) & gmask);
+  __syncwarp();
+  int kl = (int)kl_scratch[lane] + (eater ? __popc(meet) - 1 : 0);
   died |= victim;
   const bool alive_now = was_alive && !died;
   const uint32_t alive_m = __ballot_sync(FULL, alive_now) & gmask;
@@ -488,7 +489,9 @@ __device__ __forceinline__ void tile_rules(const KParams& p, const SH& sh, uint8
   if (p.mode == MODE_STEP) {
     if (active && i == 0) r.hdr->event += 1;
     __syncwarp();
-    const GroupOut res = step_group(p, sh, r, active, i, gmask, gbase, io, action);
+    // kill-credit scratch: the tile's 32 viewer words, which are only filled after the rules
+    const GroupOut res = step_group(p, sh, r, active, i, gmask, gbase, io, action,
+                                    reinterpret_cast<uint32_t*>(s_flag + 48));
     fruit = res.fruit_taken;
     // terminal info, rollout statistics, statistics reset                          :396-412
     const bool fin = env_ok && res.finished;

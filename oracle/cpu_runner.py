@@ -1,15 +1,26 @@
-"""CPU timing of the oracle's Python restatement (TEST/BENCH INFRASTRUCTURE).
+"""CPU timing of the reference's step path (TEST/BENCH INFRASTRUCTURE).
 
-Used only by bench.py's `cpu_baseline` leg and its `--impl reference` arm: the reference is pure
-Python and cannot travel to the GPU box, so its stand-in is oracle/snake_oracle.py (kind "port"), run
-the way the reference vectorises -- one OS process per environment (wrappers.py:211-212), reset on
-all(done) (wrappers.py:141-143), random actions, module-global NumPy RNG.
+Used only by bench.py's `cpu_baseline` leg and its `--impl reference` arm.  Two kinds of worker:
+
+  kind "reference"  the UNMODIFIED reference `SnakeEnv` from oracle/_ref (installed there by
+                    `make -C oracle ref`, git-ignored, ships to the GPU box with the snapshot) behind the
+                    structural gym stub -- `gym.make('Snake-v1', **kw)` exactly as make_snake does
+                    (wrappers.py:206-209);
+  kind "port"       oracle/snake_oracle.py, the restatement (caches the spawn-pose enumeration the
+                    reference repeats on every reset and vectorises _encode, so it is ~10x faster).
+
+Either way the run is shaped like the reference's vectorisation: one OS process per environment
+(wrappers.py:211-212), reset on all(done) (wrappers.py:141-143), random actions, module-global NumPy RNG.
 """
 import multiprocessing as mp
 import os
+import sys
 import time
 
 import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, '_ref')
 
 
 def usable_cores():
@@ -19,10 +30,32 @@ def usable_cores():
         return max(1, os.cpu_count() or 1)
 
 
-def _worker(rank, kw, conn):
-    from oracle.snake_oracle import OracleSnakeEnv
+def reference_available():
+    return os.path.exists(os.path.join(REF_DIR, 'marlenv', 'envs', 'snake_env.py'))
+
+
+def make_reference_env(kw):
+    """gym.make('Snake-v1', **kw) on the unmodified reference installed in oracle/_ref."""
+    for p in (REF_DIR, os.path.join(HERE, 'gym_stub')):
+        if p in sys.path:
+            sys.path.remove(p)
+        sys.path.insert(0, p)
+    for name in [m for m in sys.modules if m == 'marlenv' or m.startswith('marlenv.')]:
+        if not (getattr(sys.modules[name], '__file__', '') or '').startswith(REF_DIR):
+            del sys.modules[name]                    # the repo's import shim of the same name
+    import gym
+    import marlenv  # noqa: F401  (registers Snake-v1 with the stub's registry)
+    assert marlenv.__file__.startswith(REF_DIR), marlenv.__file__
+    return gym.make('Snake-v1', **kw)
+
+
+def _worker(rank, kw, conn, kind):
     np.random.seed(1000 + rank)
-    env = OracleSnakeEnv(**kw)
+    if kind == 'reference':
+        env = make_reference_env(kw)
+    else:
+        from oracle.snake_oracle import OracleSnakeEnv
+        env = OracleSnakeEnv(**kw)
     ns = env.num_snakes
     env.reset()
     act = np.random.RandomState(rank).randint(0, 3, size=(4096, ns))
@@ -43,15 +76,18 @@ def _worker(rank, kw, conn):
 
 
 class CpuPool:
-    """P processes, one oracle env each; run(n) advances every env by n steps and returns wall seconds."""
+    """P processes, one env each; run(n) advances every env by n steps and returns wall seconds."""
 
-    def __init__(self, kw, procs=None):
+    def __init__(self, kw, procs=None, kind='port'):
+        if kind == 'reference' and not reference_available():
+            raise RuntimeError('oracle/_ref is missing: run `make -C oracle ref` where /root/reference exists')
+        self.kind = kind
         self.procs = procs or usable_cores()
         ctx = mp.get_context('spawn')
         self.pipes, self.ps = [], []
         for r in range(self.procs):
             a, b = ctx.Pipe()
-            p = ctx.Process(target=_worker, args=(r, kw, b), daemon=True)
+            p = ctx.Process(target=_worker, args=(r, kw, b, kind), daemon=True)
             p.start()
             self.pipes.append(a)
             self.ps.append(p)

