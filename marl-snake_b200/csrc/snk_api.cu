@@ -62,7 +62,7 @@ struct snk_env {
   cudaEvent_t chunk_ev[XFER_MAX_CHUNKS] = {};
   int n_chunk_ev = 0;
   double env_steps = 0.0;
-  int force_generic = 0, coop = 0, lut_dual = 0, use_tma = 0, enc_flavour = 0;
+  int force_generic = 0, coop = 0, lut_dual = 0, use_tma = 0, enc_flavour = 0, pdl = 1;
   bool was_reset = false;
 };
 
@@ -84,11 +84,17 @@ static KParams base_params(const snk_env* h) {
   p.E = h->tile_envs;
   p.force_generic = h->force_generic;
   p.enc_blob = h->enc_blob; p.enc_blob_bytes = h->enc_blob_bytes; p.enc_tab_off = h->enc_tab_off; p.use_tab = h->use_tab;
-  p.lut_dual = h->lut_dual; p.coop = h->coop; p.use_tma = h->use_tma;
+  p.lut_dual = h->lut_dual; p.coop = h->coop; p.use_tma = h->use_tma; p.pdl = h->pdl;
   p.enc_flavour = h->enc_flavour;
   p.enc_copy_bytes = (h->enc_flavour == ENC_LEGACY) ? h->enc_blob_bytes : h->enc_tab_off;     // LUT only
   p.view_bits = h->d.oh + h->d.ow;
   p.view_bias = h->d.V * h->d.W + h->d.V;
+  {
+    const uint64_t one = (uint64_t)1 << 32;
+    const uint64_t wpr = (uint64_t)(h->d.W >> 2 > 1 ? h->d.W >> 2 : 2), nw = (uint64_t)h->d.H * wpr;
+    p.inv_grid_words = (uint32_t)((one + nw - 1) / nw);
+    p.inv_row_words = (uint32_t)((one + wpr - 1) / wpr);
+  }
   return p;
 }
 
@@ -158,7 +164,10 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
     return fail(SNK_E_INVALID, "SNK_TILE_ENVS must be a power of two <= %d", EPW_full);
   }
   // frame_stack > 1 encodes one environment per warp, so more warps than environments would idle
-  int threads = env_int("SNK_THREADS", !coop ? 32 : d.fs > 1 ? 32 * (EPW < 8 ? EPW : 8) : 96);
+  // (the padded-plane encode wants an even number of warps: with an odd window a warp then only ever sees viewer
+  // blocks of one address parity and keeps one set of cell offsets in registers)
+  int threads = env_int("SNK_THREADS", !coop ? 32 : d.fs > 1 ? 32 * (EPW < 8 ? EPW : 8)
+                                       : encode_flavour(d, true) == ENC_PAD ? 128 : 96);
   const int max_threads = coop ? SNK_MAX_THREADS_COOP : SNK_MAX_THREADS;
   if (threads < 32 || threads > max_threads || (threads & 31)) { delete h; return fail(SNK_E_INVALID, "SNK_THREADS must be a multiple of 32 in 32..%d", max_threads); }
   // large grids: fewer environments per tile until two CTAs fit an SM, then fewer warps if it still does not fit
@@ -168,6 +177,7 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
   h->tile_envs = EPW; h->threads = threads; h->coop = coop;
   h->force_generic = env_int("SNK_FORCE_GENERIC", 0);
   h->use_tma = env_int("SNK_TMA", 1);
+  h->pdl = env_int("SNK_PDL", 1);
   h->smem_bytes = tile_smem_bytes(d, threads / 32, coop != 0, EPW);
   if (h->smem_bytes > 227 * 1024) {
     const size_t need = h->smem_bytes;
@@ -195,7 +205,9 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
     h->enc_blob_bytes = (int)nb; h->enc_tab_off = (int)tab_off;
     h->lut_dual = encode_lut_dual(d) ? 1 : 0;
     h->use_tab = encode_uses_table(d) && (h->lut_dual || !env_int("SNK_NO_TABLE", 0)) ? 1 : 0;
-    h->enc_flavour = env_int("SNK_ENC_LEGACY", 0) ? ENC_LEGACY : encode_flavour(d);
+    // SNK_ENC_LEGACY=1 / SNK_ENC_NOPAD=1: A/B switches (the cooperative ENC_PAD encode falls back to what warp-private
+    // tiles of the same shape run)
+    h->enc_flavour = env_int("SNK_ENC_LEGACY", 0) ? ENC_LEGACY : encode_flavour(d, coop != 0 && !env_int("SNK_ENC_NOPAD", 0));
   }
   CUH(cudaMemset(h->err, 0, sizeof(uint32_t)));
   CUH(cudaMemset(h->stats, 0, STAT_COUNT * sizeof(double)));

@@ -62,6 +62,9 @@ struct Dims {
   int32_t stage_env_bytes;        // ns*ohw*fs  (staging area per env, output order)
   int32_t obs_env_bytes;          // ns*ohw*fs*8
   int32_t scr_bytes;              // per-env scratch: tgt u16[ns], st u8[ns], kl u8[ns], tdir u8[ns], padded to 8
+  // zero-bordered copy of a grid for the ENC_PAD encode: (H + 2V) rows of pad_pitch bytes, grid column c at
+  // byte pad_left + c; pad_left >= V is a multiple of 4 and pad_pitch / 4 is odd (rows rotate through the banks)
+  int32_t pad_pitch, pad_left, pad_env_bytes;
   uint32_t n_cand;
   uint32_t seed_lo, seed_hi, env_off_lo, env_off_hi;
   double r_fruit, r_kill, r_lose, r_win, r_time, max_steps;
@@ -84,6 +87,10 @@ inline void finalize_layout(Dims& d) {
   d.stage_env_bytes = d.ns * d.ohw * d.fs;
   d.obs_env_bytes = d.stage_env_bytes * 8;
   d.scr_bytes = round_up(5 * d.ns, 8);
+  d.pad_left = round_up(d.V, 4);
+  d.pad_pitch = round_up(d.pad_left + d.W + d.V, 4);
+  if (((d.pad_pitch >> 2) & 1) == 0) d.pad_pitch += 4;
+  d.pad_env_bytes = round_up((d.H + 2 * d.V) * d.pad_pitch, 16);
 }
 
 // ---- record field accessors ---------------------------------------------------------------------

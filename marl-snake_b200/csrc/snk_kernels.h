@@ -18,7 +18,11 @@ enum : int { MODE_STEP = 0, MODE_RESET = 1, MODE_ENCODE = 2 };
 //               as packed words, one packed word per viewer (crop origin + invalid rows/columns) is
 //               prepared by the rule warp -- no table loads, no per-viewer origin arithmetic
 //   ENC_DIRECT  full-grid observation: window cell == grid cell
-enum : int { ENC_LEGACY = 0, ENC_REG = 1, ENC_DIRECT = 2 };
+//   ENC_PAD     cooperative tiles, egocentric window of at most 255 cells, grid width a multiple of 4: the CTA
+//               copies each grid into a zero-bordered plane with a bank-conflict-free pitch (Dims::pad_*), so a
+//               window cell is origin + constant offset -- no validity masks, no window table, one byte load
+//               and one LUT row per cell; the offsets of the cells a lane owns live in registers
+enum : int { ENC_LEGACY = 0, ENC_REG = 1, ENC_DIRECT = 2, ENC_PAD = 3 };
 constexpr int TILE_AUX_BYTES = 48 + 128;   // per tile: flags (32 B), mbarrier (8 B), pad, viewer words (32 x 4 B)
 
 struct KParams {
@@ -58,6 +62,9 @@ struct KParams {
   int32_t enc_copy_bytes;      // bytes of the blob the kernel stages (the table is skipped when unused)
   int32_t view_bits;           // ENC_REG: oh + ow, the width of the row/column one-hot field
   int32_t view_bias;           // ENC_REG: V*W + V, added to the crop origin so it packs as unsigned
+  uint32_t inv_grid_words;     // ENC_PAD: ceil(2^32 / (H*W/4)) and ceil(2^32 / (W/4)): exact division of word indices
+  uint32_t inv_row_words;      //          below 2^16 by a multiply-high
+  int32_t pdl;                 // launch with programmatic stream serialization (SNK_PDL=0 switches it off)
 };
 
 struct StateView {
@@ -69,7 +76,8 @@ int tile_group(int ns);
 size_t tile_smem_bytes(const Dims& d, int warps, bool coop, int tile_envs);
 bool encode_lut_dual(const Dims& d);
 bool encode_uses_table(const Dims& d);
-int encode_flavour(const Dims& d);
+int encode_flavour(const Dims& d, bool coop);
+size_t pad_plane_bytes(const Dims& d, int tile_envs);     // ENC_PAD: padded planes of one tile
 size_t encode_blob_bytes(const Dims& d, size_t* tab_off);
 void encode_blob_fill(const Dims& d, uint8_t* out);
 cudaError_t launch_tile_kernel(const KParams& p, int threads, size_t smem_bytes, cudaStream_t stream);
