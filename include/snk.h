@@ -12,7 +12,13 @@
  * message for the calling thread.  Pointers named *_dev are CUDA device pointers
  * on the handle's device, *_host are host pointers.  `stream` is a cudaStream_t
  * passed as void* (NULL = legacy default stream); device-pointer calls only
- * enqueue work on it and never synchronise.  A handle is not thread-safe.
+ * enqueue work on it and never synchronise.  The *_host calls run on a stream
+ * owned by the handle, first wait (on the device) for whatever the most recent
+ * device-pointer call of this handle left on its stream, and synchronise before
+ * they return -- so device-pointer and host-buffer calls may be mixed freely as
+ * long as consecutive device-pointer calls use one stream (or are ordered by the
+ * caller).  Every call leaves the calling thread's current CUDA device unchanged.
+ * A handle is not thread-safe.
  *
  * Batched layouts (N = num_envs, ns = num_snakes, oh x ow = observation window):
  *   actions  uint8  [N, ns]             0 keep, 1 turn left, 2 turn right (observer 'snake');
@@ -48,7 +54,8 @@ enum {
   SNK_DEV_REPLAY_UNDERRUN = 2,   /* replay stream exhausted                                         */
   SNK_DEV_REPLAY_RANGE = 4,      /* replayed draw out of range / replayed spawn overlaps            */
   SNK_DEV_SPAWN_GIVEUP = 8,      /* no overlap-free spawn found within the attempt cap               */
-  SNK_DEV_INTERNAL = 16          /* a bounds / alignment check failed (debug build, -DSNK_DEBUG_CHECKS) */
+  SNK_DEV_INTERNAL = 16,         /* a bounds / alignment check failed (debug build, -DSNK_DEBUG_CHECKS) */
+  SNK_DEV_TMA_TIMEOUT = 32       /* a record tile's bulk copy did not complete within 2 s; that tile was not stepped */
 };
 
 enum { SNK_RNG_PHILOX = 0, SNK_RNG_REPLAY = 1 };
@@ -136,15 +143,37 @@ int snk_reset(snk_env* env, const uint8_t* mask_dev, uint8_t* obs_dev, void* str
 int snk_step(snk_env* env, const uint8_t* actions_dev, uint8_t* obs_dev, double* rewards_dev,
              uint8_t* dones_dev, const snk_step_extra* extra, void* stream);
 
+/* The same two calls delivering the observation as CHANNEL BITS: bits_dev is uint8 [N, ns, oh, ow, frame_stack],
+ * one byte per window cell and frame, bit c = channel c of _encode (snake_env.py:484-492) -- i.e.
+ * np.packbits(obs.reshape(..., frame_stack, 8), axis=-1, bitorder='little').  The encode writes them directly (no
+ * NHWC block, an eighth of the observation traffic): the format for device-side replay buffers and for shipping
+ * observations over PCIe.  snk_pack_obs gives the same bytes from an NHWC block. */
+int snk_reset_bits(snk_env* env, const uint8_t* mask_dev, uint8_t* bits_dev, void* stream);
+int snk_step_bits(snk_env* env, const uint8_t* actions_dev, uint8_t* bits_dev, double* rewards_dev,
+                  uint8_t* dones_dev, const snk_step_extra* extra, void* stream);
+
+/* num_steps consecutive snk_step calls as ONE call, for callers whose actions do not depend on the intermediate
+ * observations (random or scripted rollouts, replaying recorded action streams, open-loop evaluation):
+ *   actions_dev [T, N, ns], rewards_dev [T, N, ns], dones_dev [T, N, ns]; every non-NULL pointer of `extra` is
+ *   [T, ...] likewise (finished [T, N], rank [T, N, ns], ...);
+ *   obs_dev / bits_dev (either or both may be NULL): [T, N, ...] when obs_every_step != 0, else only the last
+ *   step's block [N, ...] is written.
+ * Bit-identical to T single steps.  frame_stack 1: one kernel launch -- a tile's records are loaded into shared memory
+ * once, stepped T times there and written back once, so a small batch (BASELINE cfg2: 4 096 envs) is no longer bound
+ * by T launch latencies and 2 x T record transfers.  frame_stack > 1: T launches (the frame history is per step). */
+int snk_step_many(snk_env* env, int32_t num_steps, const uint8_t* actions_dev, uint8_t* obs_dev, uint8_t* bits_dev,
+                  int32_t obs_every_step, double* rewards_dev, uint8_t* dones_dev, const snk_step_extra* extra,
+                  void* stream);
+
 /* Same call with HOST buffers (the reference's step() takes and returns host objects,
  * snake_env.py:414): copies actions in, steps, copies obs / rewards / dones out and synchronises.
  * Pinned buffers make the copies asynchronous to the host until the final synchronise.  obs_host may
  * be NULL.  The observation block crosses the PCIe link in one of two ways (same bytes land in
  * obs_host either way):
  *   SNK_XFER_RAW     one device-to-host copy of the uint8 NHWC block;
- *   SNK_XFER_PACKED  the device packs the eight 0/1 channel bytes of every (cell, frame) into one
- *                    channel-bit byte, the block crosses the link 8x smaller in chunks, and a pool of
- *                    host threads widens each chunk back to 0/1 bytes while the next ones are in flight.
+ *   SNK_XFER_PACKED  the step kernel emits channel bits (as snk_step_bits: no NHWC block is written on the
+ *                    device at all), the block crosses the link 8x smaller in chunks, and a pool of host
+ *                    threads widens each chunk back to 0/1 bytes while the next ones are in flight.
  * Default: packed when the block is >= 4 MiB, raw below (environment SNK_HOST_TRANSPORT=raw|packed and
  * SNK_HOST_THREADS override at create time). */
 int snk_step_host(snk_env* env, const uint8_t* actions_host, uint8_t* obs_host,
@@ -207,7 +236,7 @@ enum {
   SNK_STAT_FRUITS,         /* sum of episode_fruits                           */
   SNK_STAT_KILLS,          /* sum of episode_kills                            */
   SNK_STAT_DEATHS,         /* snakes that died                                */
-  SNK_STAT_ENV_STEPS,      /* env steps executed                              */
+  SNK_STAT_ENV_STEPS,      /* env steps executed (counted on the device, so CUDA-graph replays count too) */
   SNK_STAT_COUNT = 8
 };
 /* Device pointer to SNK_STAT_COUNT doubles accumulated on device (for an in-place NCCL allreduce). */

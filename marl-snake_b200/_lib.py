@@ -15,7 +15,8 @@ SNK_RNG_PHILOX, SNK_RNG_REPLAY = 0, 1
 SNK_XFER_RAW, SNK_XFER_PACKED = 0, 1
 DEV_ERRORS = {1: 'action outside {0,1,2}', 2: 'replay stream exhausted',
               4: 'replayed draw out of range / replayed spawn overlaps', 8: 'spawn sampling gave up',
-              16: 'internal bounds check failed (debug build)'}
+              16: 'internal bounds check failed (debug build)',
+              32: "a record tile's bulk copy timed out; the tile was skipped"}
 STAT_NAMES = ('episodes', 'return_sum', 'episode_steps_sum', 'fruits_sum', 'kills_sum', 'deaths',
               'env_steps', 'reserved')
 
@@ -56,6 +57,11 @@ PROTOTYPES = {
     'snk_reset': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'snk_step': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                            C.POINTER(SnkStepExtra), C.c_void_p]),
+    'snk_reset_bits': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'snk_step_bits': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.POINTER(SnkStepExtra), C.c_void_p]),
+    'snk_step_many': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                C.c_void_p, C.POINTER(SnkStepExtra), C.c_void_p]),
     'snk_step_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'snk_step_host_info': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.POINTER(SnkStepExtra)]),

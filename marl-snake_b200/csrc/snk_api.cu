@@ -27,6 +27,20 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// Entry points run on the handle's device and leave the calling thread's current device as they found it.
+struct DeviceGuard {
+  int prev = -1, want = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) : want(dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() { if (prev >= 0 && prev != want) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(h)                                                                                   \
+  DeviceGuard _guard((h)->device);                                                                     \
+  if (_guard.err != cudaSuccess) return fail(SNK_E_CUDA, "cudaSetDevice(%d): %s", (h)->device, cudaGetErrorString(_guard.err))
+
 #define CU(call)                                                                              \
   do {                                                                                        \
     cudaError_t _e = (call);                                                                  \
@@ -39,6 +53,8 @@ struct snk_env {
   int device = 0;
   int tile_envs = 0, threads = 0;
   size_t smem_bytes = 0;
+  int many_tile_envs = 0, many_threads = 0;      // tile shape of multi-step launches (snk_step_many, cooperative tiles)
+  size_t many_smem_bytes = 0;
   uint8_t* recs = nullptr;
   uint8_t* hist = nullptr;
   uint64_t* spawn = nullptr;
@@ -47,7 +63,11 @@ struct snk_env {
   uint32_t* err = nullptr;
   double* stats = nullptr;
   uint8_t* enc_blob = nullptr;
-  int enc_blob_bytes = 0, enc_tab_off = 0, use_tab = 0;
+  int enc_blob_bytes = 0, enc_tab_off = 0, enc_lutb_off = 0, use_tab = 0;
+  // ordering between the caller's streams (device-pointer calls) and own_stream (host-buffer calls)
+  cudaStream_t last_user_stream = nullptr;
+  bool user_work_pending = false;
+  cudaEvent_t user_ev = nullptr;
   // device mirrors used by the *_host entry points
   uint8_t* h_actions = nullptr; uint8_t* h_obs = nullptr; double* h_rew = nullptr; uint8_t* h_done = nullptr;
   uint8_t* h_fin = nullptr; int32_t* h_rank = nullptr; double* h_scores = nullptr; int32_t* h_counts = nullptr;   // [3][N, ns]
@@ -61,7 +81,6 @@ struct snk_env {
   WidenPool* pool = nullptr;
   cudaEvent_t chunk_ev[XFER_MAX_CHUNKS] = {};
   int n_chunk_ev = 0;
-  double env_steps = 0.0;
   int force_generic = 0, coop = 0, lut_dual = 0, use_tma = 0, enc_flavour = 0, pdl = 1;
   bool was_reset = false;
 };
@@ -84,7 +103,9 @@ static KParams base_params(const snk_env* h) {
   p.E = h->tile_envs;
   p.force_generic = h->force_generic;
   p.enc_blob = h->enc_blob; p.enc_blob_bytes = h->enc_blob_bytes; p.enc_tab_off = h->enc_tab_off; p.use_tab = h->use_tab;
+  p.enc_lutb_off = h->enc_lutb_off;
   p.lut_dual = h->lut_dual; p.coop = h->coop; p.use_tma = h->use_tma; p.pdl = h->pdl;
+  p.T = 1;
   p.enc_flavour = h->enc_flavour;
   p.enc_copy_bytes = (h->enc_flavour == ENC_LEGACY) ? h->enc_blob_bytes : h->enc_tab_off;     // LUT only
   p.view_bits = h->d.oh + h->d.ow;
@@ -175,6 +196,17 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
     while (EPW > 1 && tile_smem_bytes(d, coop ? threads / 32 : 1, coop != 0, EPW) > 100 * 1024) EPW >>= 1;
   while (threads > 32 && tile_smem_bytes(d, threads / 32, coop != 0, EPW) > 200 * 1024) threads -= 32;
   h->tile_envs = EPW; h->threads = threads; h->coop = coop;
+  {
+    // snk_step_many: every CTA lives for the whole launch, so the grid should be ONE resident wave -- as many
+    // environments per cooperative tile as the rule warp has lane groups (fewer, longer-lived CTAs), more warps to
+    // share the tile's viewers.  Warp-private tiles keep their shape.
+    int me = coop ? env_int("SNK_MANY_TILE_ENVS", EPW_full) : EPW;
+    int mt = coop ? env_int("SNK_MANY_THREADS", 128) : threads;
+    if (me < 1 || me > EPW_full || (me & (me - 1)) || mt < 32 || mt > max_threads || (mt & 31)) { me = EPW; mt = threads; }
+    while (me > 1 && tile_smem_bytes(d, coop ? mt / 32 : 1, coop != 0, me) > 100 * 1024) me >>= 1;
+    h->many_tile_envs = me; h->many_threads = mt;
+    h->many_smem_bytes = tile_smem_bytes(d, mt / 32, coop != 0, me);
+  }
   h->force_generic = env_int("SNK_FORCE_GENERIC", 0);
   h->use_tma = env_int("SNK_TMA", 1);
   h->pdl = env_int("SNK_PDL", 1);
@@ -185,8 +217,8 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
     return fail(SNK_E_INVALID, "configuration needs %zu bytes of shared memory per tile", need);
   }
 
-  cudaError_t e = cudaSetDevice(c->device);
-  if (e != cudaSuccess) { delete h; return fail(SNK_E_CUDA, "cudaSetDevice(%d): %s", c->device, cudaGetErrorString(e)); }
+  DeviceGuard guard(c->device);
+  if (guard.err != cudaSuccess) { delete h; return fail(SNK_E_CUDA, "cudaSetDevice(%d): %s", c->device, cudaGetErrorString(guard.err)); }
 #define CUH(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { int rc = fail(SNK_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); snk_destroy(h); return rc; } } while (0)
   CUH(cudaMalloc(&h->recs, (size_t)d.N * d.rec_bytes));
   if (d.hist_env_bytes) CUH(cudaMalloc(&h->hist, (size_t)d.N * d.hist_env_bytes));
@@ -196,13 +228,13 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
   CUH(cudaMalloc(&h->replay_off, ((size_t)d.N + 1) * sizeof(int64_t)));
   CUH(cudaMemcpy(h->spawn, table.data(), table.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
   {
-    size_t tab_off = 0;
-    const size_t nb = encode_blob_bytes(d, &tab_off);
+    size_t tab_off = 0, lutb_off = 0;
+    const size_t nb = encode_blob_bytes(d, &tab_off, &lutb_off);
     std::vector<uint8_t> blob(nb, 0);
     encode_blob_fill(d, blob.data());
     CUH(cudaMalloc(&h->enc_blob, nb));
     CUH(cudaMemcpy(h->enc_blob, blob.data(), nb, cudaMemcpyHostToDevice));
-    h->enc_blob_bytes = (int)nb; h->enc_tab_off = (int)tab_off;
+    h->enc_blob_bytes = (int)nb; h->enc_tab_off = (int)tab_off; h->enc_lutb_off = (int)lutb_off;
     h->lut_dual = encode_lut_dual(d) ? 1 : 0;
     h->use_tab = encode_uses_table(d) && (h->lut_dual || !env_int("SNK_NO_TABLE", 0)) ? 1 : 0;
     // SNK_ENC_LEGACY=1 / SNK_ENC_NOPAD=1: A/B switches (the cooperative ENC_PAD encode falls back to what warp-private
@@ -215,6 +247,7 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
   if (d.hist_env_bytes) CUH(cudaMemset(h->hist, 0, (size_t)d.N * d.hist_env_bytes));
   CUH(launch_init_records(d, h->recs, nullptr));
   CUH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  CUH(cudaEventCreateWithFlags(&h->user_ev, cudaEventDisableTiming));
   CUH(cudaDeviceSynchronize());
 #undef CUH
   {
@@ -232,7 +265,7 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
 
 extern "C" int snk_destroy(snk_env* h) {
   if (!h) return SNK_OK;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   cudaFree(h->recs); cudaFree(h->hist); cudaFree(h->spawn); cudaFree(h->replay); cudaFree(h->replay_off);
   cudaFree(h->err); cudaFree(h->stats); cudaFree(h->enc_blob);
   cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_rew); cudaFree(h->h_done);
@@ -243,6 +276,7 @@ extern "C" int snk_destroy(snk_env* h) {
   if (h->p_bits) cudaFreeHost(h->p_bits);
   delete h->pool;
   for (int i = 0; i < h->n_chunk_ev; ++i) cudaEventDestroy(h->chunk_ev[i]);
+  if (h->user_ev) cudaEventDestroy(h->user_ev);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return SNK_OK;
@@ -271,66 +305,165 @@ static int check_vec16(const snk_env* h, const uint8_t* obs) {
   return (((uintptr_t)obs & 15) == 0 && h->d.obs_env_bytes % 16 == 0) ? 1 : 0;    // every env block 16-byte aligned
 }
 
-extern "C" int snk_reset(snk_env* h, const uint8_t* mask_dev, uint8_t* obs_dev, void* stream) {
-  if (!h) return fail(SNK_E_INVALID, "null handle");
+// Device-pointer calls only enqueue work on the caller's stream.  The host-buffer calls run on the handle's own
+// stream and synchronise before they return, so ordering is needed in one direction only: before a host-buffer
+// call launches, own_stream waits for whatever the last device-pointer call left on the caller's stream.
+static void note_user_stream(snk_env* h, cudaStream_t s) {
+  if (s == h->own_stream) return;
+  h->last_user_stream = s;
+  h->user_work_pending = true;
+}
+static int own_stream_after_user_work(snk_env* h) {
+  if (!h->user_work_pending) return SNK_OK;
+  h->user_work_pending = false;
+  // (a stream that is being captured cannot record an event for the outside world; such work is ordered by the
+  // graph launch, which the caller issues on a stream of their own)
+  if (cudaEventRecord(h->user_ev, h->last_user_stream) != cudaSuccess) { cudaGetLastError(); return SNK_OK; }
+  CU(cudaStreamWaitEvent(h->own_stream, h->user_ev, 0));
+  return SNK_OK;
+}
+
+static int reset_impl(snk_env* h, const uint8_t* mask_dev, uint8_t* obs_dev, uint8_t* bits_dev, cudaStream_t stream) {
   if (obs_dev && ((uintptr_t)obs_dev & 7)) return fail(SNK_E_INVALID, "obs must be 8-byte aligned");
-  CU(cudaSetDevice(h->device));
   KParams p = base_params(h);
-  p.mode = MODE_RESET; p.mask = mask_dev; p.obs = obs_dev;
-  CU(launch_tile_kernel(p, h->threads, h->smem_bytes, (cudaStream_t)stream));
+  p.mode = MODE_RESET; p.mask = mask_dev; p.obs = obs_dev; p.bits = bits_dev;
+  p.vec16 = check_vec16(h, obs_dev);
+  CU(launch_tile_kernel(p, h->threads, h->smem_bytes, stream));
+  note_user_stream(h, stream);
   h->was_reset = true;
   return SNK_OK;
 }
 
-extern "C" int snk_step(snk_env* h, const uint8_t* actions_dev, uint8_t* obs_dev, double* rewards_dev,
-                        uint8_t* dones_dev, const snk_step_extra* x, void* stream) {
-  if (!h) return fail(SNK_E_INVALID, "null handle");
+static int step_impl(snk_env* h, const uint8_t* actions_dev, uint8_t* obs_dev, uint8_t* bits_dev, double* rewards_dev,
+                     uint8_t* dones_dev, const snk_step_extra* x, cudaStream_t stream) {
   if (!actions_dev || !rewards_dev || !dones_dev) return fail(SNK_E_INVALID, "actions, rewards and dones are required");
   if (!h->was_reset) return fail(SNK_E_STATE, "step before reset");
   if (obs_dev && ((uintptr_t)obs_dev & 7)) return fail(SNK_E_INVALID, "obs must be 8-byte aligned");
   if ((uintptr_t)rewards_dev & 7) return fail(SNK_E_INVALID, "rewards must be 8-byte aligned");
-  CU(cudaSetDevice(h->device));
   KParams p = base_params(h);
   p.mode = MODE_STEP;
-  p.actions = actions_dev; p.obs = obs_dev; p.rew = rewards_dev; p.done = dones_dev;
+  p.actions = actions_dev; p.obs = obs_dev; p.bits = bits_dev; p.rew = rewards_dev; p.done = dones_dev;
   if (x) {
     p.fin = x->finished; p.rank = x->rank; p.ep_scores = x->episode_scores;
     p.ep_steps = x->episode_steps; p.ep_fruits = x->episode_fruits; p.ep_kills = x->episode_kills;
   }
   p.vec16 = check_vec16(h, obs_dev);
-  CU(launch_tile_kernel(p, h->threads, h->smem_bytes, (cudaStream_t)stream));
-  h->env_steps += (double)h->d.N;
+  CU(launch_tile_kernel(p, h->threads, h->smem_bytes, stream));
+  note_user_stream(h, stream);
   return SNK_OK;
 }
 
-static int ensure_mirrors(snk_env* h) {
+// T steps in one call.  frame_stack 1: ONE launch, every tile's records stay in shared memory for all T steps.
+// frame_stack > 1 (the frame history is written per step): T ordinary launches -- same results, same arrays.
+static int step_many_impl(snk_env* h, int T, const uint8_t* actions_dev, uint8_t* obs_dev, uint8_t* bits_dev, int every,
+                          double* rewards_dev, uint8_t* dones_dev, const snk_step_extra* x, cudaStream_t stream) {
+  if (T < 1 || T > 65536) return fail(SNK_E_INVALID, "num_steps must be in 1..65536");
+  const Dims& d = h->d;
+  const size_t nn = (size_t)d.N * d.ns;
+  if (d.fs == 1) {
+    if (!actions_dev || !rewards_dev || !dones_dev) return fail(SNK_E_INVALID, "actions, rewards and dones are required");
+    if (!h->was_reset) return fail(SNK_E_STATE, "step before reset");
+    if (obs_dev && ((uintptr_t)obs_dev & 7)) return fail(SNK_E_INVALID, "obs must be 8-byte aligned");
+    if ((uintptr_t)rewards_dev & 7) return fail(SNK_E_INVALID, "rewards must be 8-byte aligned");
+    KParams p = base_params(h);
+    const bool many = T > 1;
+    if (many) p.E = h->many_tile_envs;
+    p.mode = MODE_STEP; p.T = T; p.obs_every_step = every ? 1 : 0;
+    p.actions = actions_dev; p.obs = obs_dev; p.bits = bits_dev; p.rew = rewards_dev; p.done = dones_dev;
+    if (x) {
+      p.fin = x->finished; p.rank = x->rank; p.ep_scores = x->episode_scores;
+      p.ep_steps = x->episode_steps; p.ep_fruits = x->episode_fruits; p.ep_kills = x->episode_kills;
+    }
+    CU(launch_tile_kernel(p, many ? h->many_threads : h->threads, many ? h->many_smem_bytes : h->smem_bytes, stream));
+    note_user_stream(h, stream);
+    return SNK_OK;
+  }
+  for (int t = 0; t < T; ++t) {
+    snk_step_extra xt;
+    memset(&xt, 0, sizeof xt);
+    if (x) {
+      if (x->finished) xt.finished = x->finished + (size_t)t * d.N;
+      if (x->rank) xt.rank = x->rank + t * nn;
+      if (x->episode_scores) xt.episode_scores = x->episode_scores + t * nn;
+      if (x->episode_steps) xt.episode_steps = x->episode_steps + t * nn;
+      if (x->episode_fruits) xt.episode_fruits = x->episode_fruits + t * nn;
+      if (x->episode_kills) xt.episode_kills = x->episode_kills + t * nn;
+    }
+    const bool render = every || t == T - 1;
+    uint8_t* o = (obs_dev && render) ? obs_dev + (every ? (size_t)t * d.N * d.obs_env_bytes : 0) : nullptr;
+    uint8_t* b = (bits_dev && render) ? bits_dev + (every ? (size_t)t * d.N * d.stage_env_bytes : 0) : nullptr;
+    int rc = step_impl(h, actions_dev + t * nn, o, b, rewards_dev + t * nn, dones_dev + t * nn, x ? &xt : nullptr, stream);
+    if (rc) return rc;
+  }
+  return SNK_OK;
+}
+
+extern "C" int snk_step_many(snk_env* h, int32_t num_steps, const uint8_t* actions_dev, uint8_t* obs_dev, uint8_t* bits_dev,
+                             int32_t obs_every_step, double* rewards_dev, uint8_t* dones_dev, const snk_step_extra* x,
+                             void* stream) {
+  if (!h) return fail(SNK_E_INVALID, "null handle");
+  if (!actions_dev || !rewards_dev || !dones_dev) return fail(SNK_E_INVALID, "actions, rewards and dones are required");
+  ON_DEVICE(h);
+  return step_many_impl(h, num_steps, actions_dev, obs_dev, bits_dev, obs_every_step, rewards_dev, dones_dev, x, (cudaStream_t)stream);
+}
+
+extern "C" int snk_reset(snk_env* h, const uint8_t* mask_dev, uint8_t* obs_dev, void* stream) {
+  if (!h) return fail(SNK_E_INVALID, "null handle");
+  ON_DEVICE(h);
+  return reset_impl(h, mask_dev, obs_dev, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int snk_reset_bits(snk_env* h, const uint8_t* mask_dev, uint8_t* bits_dev, void* stream) {
+  if (!h) return fail(SNK_E_INVALID, "null handle");
+  ON_DEVICE(h);
+  return reset_impl(h, mask_dev, nullptr, bits_dev, (cudaStream_t)stream);
+}
+
+extern "C" int snk_step(snk_env* h, const uint8_t* actions_dev, uint8_t* obs_dev, double* rewards_dev,
+                        uint8_t* dones_dev, const snk_step_extra* x, void* stream) {
+  if (!h) return fail(SNK_E_INVALID, "null handle");
+  ON_DEVICE(h);
+  return step_impl(h, actions_dev, obs_dev, nullptr, rewards_dev, dones_dev, x, (cudaStream_t)stream);
+}
+
+extern "C" int snk_step_bits(snk_env* h, const uint8_t* actions_dev, uint8_t* bits_dev, double* rewards_dev,
+                             uint8_t* dones_dev, const snk_step_extra* x, void* stream) {
+  if (!h) return fail(SNK_E_INVALID, "null handle");
+  ON_DEVICE(h);
+  return step_impl(h, actions_dev, nullptr, bits_dev, rewards_dev, dones_dev, x, (cudaStream_t)stream);
+}
+
+static bool packed(const snk_env* h) { return h->xfer_mode == XFER_PACKED; }
+
+// Device mirrors of the host-buffer calls.  The NHWC mirror (N * obs bytes) exists only for the raw transport;
+// the packed transport has the step kernel emit channel bits straight into d_bits (an eighth of the bytes).
+static int ensure_mirrors(snk_env* h, bool want_obs, bool want_bits) {
   const Dims& d = h->d;
   if (!h->h_actions) CU(cudaMalloc(&h->h_actions, (size_t)d.N * d.ns));
-  if (!h->h_obs) CU(cudaMalloc(&h->h_obs, (size_t)d.N * d.obs_env_bytes));
+  if (want_obs && !h->h_obs) CU(cudaMalloc(&h->h_obs, (size_t)d.N * d.obs_env_bytes));
+  if (want_bits && !h->d_bits) CU(cudaMalloc(&h->d_bits, (size_t)d.N * d.stage_env_bytes));
   if (!h->h_rew) CU(cudaMalloc(&h->h_rew, (size_t)d.N * d.ns * sizeof(double)));
   if (!h->h_done) CU(cudaMalloc(&h->h_done, (size_t)d.N * d.ns));
   return SNK_OK;
 }
 
-// Observation block of the device mirror -> obs_host on stream s.  Raw: one D2H of the NHWC bytes.
-// Packed: pack to channel bits on the device, D2H in chunks, widen each chunk on the host pool as soon as
-// its copy lands while the next chunks are still on the link.  Returns with the host buffer complete.
+// Observation block of the device mirror -> obs_host on stream s.  Raw: one D2H of the NHWC bytes (h_obs).
+// Packed: the kernel already wrote channel bits into d_bits; D2H in chunks, widen each chunk on the host pool as
+// soon as its copy lands while the next chunks are still on the link.  Returns with the host buffer complete.
 static int obs_to_host(snk_env* h, uint8_t* obs_host, cudaStream_t s) {
   const Dims& d = h->d;
   const size_t total = (size_t)d.N * d.obs_env_bytes;
-  if (h->xfer_mode == XFER_RAW) {
+  if (!packed(h)) {
     CU(cudaMemcpyAsync(obs_host, h->h_obs, total, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     return SNK_OK;
   }
   const size_t units = total / 8;
-  if (!h->d_bits) CU(cudaMalloc(&h->d_bits, units));
   if (!h->p_bits) CU(cudaMallocHost(&h->p_bits, units));
   if (!h->pool) {
     h->pool = new (std::nothrow) WidenPool(h->xfer_threads > 0 ? h->xfer_threads : default_host_threads());
     if (!h->pool) return fail(SNK_E_NOMEM, "out of host memory");
   }
-  CU(launch_pack_obs(h->h_obs, h->d_bits, units, s));
   size_t chunk = (size_t)8 << 20;
   if ((units + chunk - 1) / chunk > XFER_MAX_CHUNKS) chunk = ((units + XFER_MAX_CHUNKS - 1) / XFER_MAX_CHUNKS + 4095) / 4096 * 4096;
   const int nchunks = (int)((units + chunk - 1) / chunk);
@@ -384,6 +517,7 @@ static int step_host_small(snk_env* h, const SmallLayout& L, const uint8_t* acti
   uint8_t* dv = h->small_dev;
   uint8_t* hv = h->small_host;
   memcpy(hv + L.act, actions_host, nn);
+  { int rc0 = own_stream_after_user_work(h); if (rc0) return rc0; }
   CU(cudaMemcpyAsync(dv + L.act, hv + L.act, nn, cudaMemcpyHostToDevice, s));
   snk_step_extra xd;
   memset(&xd, 0, sizeof xd);
@@ -391,7 +525,7 @@ static int step_host_small(snk_env* h, const SmallLayout& L, const uint8_t* acti
     xd.finished = dv + L.fin; xd.rank = (int32_t*)(dv + L.rank); xd.episode_scores = (double*)(dv + L.scores);
     xd.episode_steps = (int32_t*)(dv + L.counts); xd.episode_fruits = xd.episode_steps + nn; xd.episode_kills = xd.episode_fruits + nn;
   }
-  int rc = snk_step(h, dv + L.act, obs_host ? dv + L.obs : nullptr, (double*)(dv + L.rew), dv + L.done, xh ? &xd : nullptr, s);
+  int rc = step_impl(h, dv + L.act, obs_host ? dv + L.obs : nullptr, nullptr, (double*)(dv + L.rew), dv + L.done, xh ? &xd : nullptr, s);
   if (rc) return rc;
   const size_t lo = obs_host ? L.obs : L.rew, hi = xh ? L.total : L.fin;
   CU(cudaMemcpyAsync(hv + lo, dv + lo, hi - lo, cudaMemcpyDeviceToHost, s));
@@ -414,12 +548,15 @@ extern "C" int snk_step_host_info(snk_env* h, const uint8_t* actions_host, uint8
                                   double* rewards_host, uint8_t* dones_host, const snk_step_extra* xh) {
   if (!h) return fail(SNK_E_INVALID, "null handle");
   if (!actions_host || !rewards_host || !dones_host) return fail(SNK_E_INVALID, "actions, rewards and dones are required");
-  CU(cudaSetDevice(h->device));
+  ON_DEVICE(h);
   {
     const SmallLayout L = small_layout(h->d);
     if (L.total <= 64 * 1024) return step_host_small(h, L, actions_host, obs_host, rewards_host, dones_host, xh);
   }
-  int rc = ensure_mirrors(h);
+  const bool as_bits = obs_host && packed(h);  // packed transport: the kernel emits channel bits, no NHWC block at all
+  int rc = ensure_mirrors(h, obs_host && !as_bits, as_bits);
+  if (rc) return rc;
+  rc = own_stream_after_user_work(h);
   if (rc) return rc;
   const Dims& d = h->d;
   const size_t nn = (size_t)d.N * d.ns;
@@ -439,7 +576,8 @@ extern "C" int snk_step_host_info(snk_env* h, const uint8_t* actions_host, uint8
     if (xh->episode_kills) xd.episode_kills = h->h_counts + 2 * nn;
   }
   CU(cudaMemcpyAsync(h->h_actions, actions_host, nn, cudaMemcpyHostToDevice, s));
-  rc = snk_step(h, h->h_actions, obs_host ? h->h_obs : nullptr, h->h_rew, h->h_done, xh ? &xd : nullptr, s);
+  rc = step_impl(h, h->h_actions, obs_host && !as_bits ? h->h_obs : nullptr, as_bits ? h->d_bits : nullptr, h->h_rew, h->h_done,
+                 xh ? &xd : nullptr, s);
   if (rc) return rc;
   CU(cudaMemcpyAsync(rewards_host, h->h_rew, nn * sizeof(double), cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(dones_host, h->h_done, nn, cudaMemcpyDeviceToHost, s));
@@ -458,17 +596,17 @@ extern "C" int snk_step_host_bits(snk_env* h, const uint8_t* actions_host, uint8
                                   double* rewards_host, uint8_t* dones_host) {
   if (!h) return fail(SNK_E_INVALID, "null handle");
   if (!actions_host || !bits_host || !rewards_host || !dones_host) return fail(SNK_E_INVALID, "null argument");
-  CU(cudaSetDevice(h->device));
-  int rc = ensure_mirrors(h);
+  ON_DEVICE(h);
+  int rc = ensure_mirrors(h, false, true);
+  if (rc) return rc;
+  rc = own_stream_after_user_work(h);
   if (rc) return rc;
   const Dims& d = h->d;
-  const size_t nn = (size_t)d.N * d.ns, units = (size_t)d.N * d.obs_env_bytes / 8;
+  const size_t nn = (size_t)d.N * d.ns, units = (size_t)d.N * d.stage_env_bytes;
   cudaStream_t s = h->own_stream;
-  if (!h->d_bits) CU(cudaMalloc(&h->d_bits, units));
   CU(cudaMemcpyAsync(h->h_actions, actions_host, nn, cudaMemcpyHostToDevice, s));
-  rc = snk_step(h, h->h_actions, h->h_obs, h->h_rew, h->h_done, nullptr, s);
+  rc = step_impl(h, h->h_actions, nullptr, h->d_bits, h->h_rew, h->h_done, nullptr, s);   // channel bits straight from the encode
   if (rc) return rc;
-  CU(launch_pack_obs(h->h_obs, h->d_bits, units, s));
   CU(cudaMemcpyAsync(rewards_host, h->h_rew, nn * sizeof(double), cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(dones_host, h->h_done, nn, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(bits_host, h->d_bits, units, cudaMemcpyDeviceToHost, s));
@@ -483,11 +621,14 @@ extern "C" int snk_step_host(snk_env* h, const uint8_t* actions_host, uint8_t* o
 
 extern "C" int snk_reset_host(snk_env* h, uint8_t* obs_host) {
   if (!h) return fail(SNK_E_INVALID, "null handle");
-  CU(cudaSetDevice(h->device));
-  int rc = ensure_mirrors(h);
+  ON_DEVICE(h);
+  const bool as_bits = obs_host && packed(h);
+  int rc = ensure_mirrors(h, obs_host && !as_bits, as_bits);
+  if (rc) return rc;
+  rc = own_stream_after_user_work(h);
   if (rc) return rc;
   cudaStream_t s = h->own_stream;
-  rc = snk_reset(h, nullptr, obs_host ? h->h_obs : nullptr, s);
+  rc = reset_impl(h, nullptr, obs_host && !as_bits ? h->h_obs : nullptr, as_bits ? h->d_bits : nullptr, s);
   if (rc) return rc;
   if (obs_host) return obs_to_host(h, obs_host, s);
   CU(cudaStreamSynchronize(s));
@@ -514,7 +655,7 @@ extern "C" int snk_pack_obs(snk_env* h, const uint8_t* obs_dev, uint8_t* bits_de
   if (!h || !obs_dev || !bits_dev) return fail(SNK_E_INVALID, "null argument");
   if (((uintptr_t)obs_dev & 15) || ((uintptr_t)bits_dev & 3) || (n_bytes & 7))
     return fail(SNK_E_INVALID, "obs must be 16-byte aligned, bits 4-byte aligned, n_bytes a multiple of 8");
-  CU(cudaSetDevice(h->device));
+  ON_DEVICE(h);
   CU(launch_pack_obs(obs_dev, bits_dev, n_bytes / 8, (cudaStream_t)stream));
   return SNK_OK;
 }
@@ -538,8 +679,9 @@ static StateView to_view(const snk_state_view* v) {
 extern "C" int snk_get_state(snk_env* h, const snk_state_view* out, void* stream) {
   if (!h || !out) return fail(SNK_E_INVALID, "null argument");
   if (out->cells && out->max_cells < 1) return fail(SNK_E_INVALID, "max_cells must be >= 1 when cells is given");
-  CU(cudaSetDevice(h->device));
+  ON_DEVICE(h);
   CU(launch_get_state(h->d, h->recs, to_view(out), (cudaStream_t)stream));
+  note_user_stream(h, (cudaStream_t)stream);
   return SNK_OK;
 }
 
@@ -548,11 +690,13 @@ extern "C" int snk_set_state(snk_env* h, const snk_state_view* in, uint8_t* obs_
   if (!in->grid || !in->alive || !in->dir || !in->cells || !in->length || !in->alive_counter || !in->episode_length || in->max_cells < 2)
     return fail(SNK_E_INVALID, "set_state needs grid, alive, dir, cells, length, alive_counter, episode_length");
   if (obs_dev && ((uintptr_t)obs_dev & 7)) return fail(SNK_E_INVALID, "obs must be 8-byte aligned");
-  CU(cudaSetDevice(h->device));
+  ON_DEVICE(h);
   CU(launch_set_state(h->d, h->recs, to_view(in), (cudaStream_t)stream));
   KParams p = base_params(h);
   p.mode = MODE_ENCODE; p.obs = obs_dev;
+  p.vec16 = check_vec16(h, obs_dev);
   CU(launch_tile_kernel(p, h->threads, h->smem_bytes, (cudaStream_t)stream));
+  note_user_stream(h, (cudaStream_t)stream);
   h->was_reset = true;
   return SNK_OK;
 }
@@ -570,11 +714,11 @@ extern "C" size_t snk_checkpoint_bytes(const snk_env* h) {
 extern "C" int snk_checkpoint_save(snk_env* h, void* blob_host, size_t bytes) {
   if (!h || !blob_host) return fail(SNK_E_INVALID, "null argument");
   if (bytes < snk_checkpoint_bytes(h)) return fail(SNK_E_INVALID, "checkpoint buffer too small: %zu < %zu", bytes, snk_checkpoint_bytes(h));
-  CU(cudaSetDevice(h->device));
+  ON_DEVICE(h);
   CU(cudaDeviceSynchronize());
   const Dims& d = h->d;
   uint8_t* out = (uint8_t*)blob_host;
-  CkptHeader hd = {CKPT_MAGIC, d.N, d.H, d.W, d.ns, d.K, d.V, d.fs, d.dig, d.rec_bytes, d.hist_env_bytes, h->env_steps};
+  CkptHeader hd = {CKPT_MAGIC, d.N, d.H, d.W, d.ns, d.K, d.V, d.fs, d.dig, d.rec_bytes, d.hist_env_bytes, 0.0};
   memcpy(out, &hd, sizeof hd); out += sizeof hd;
   CU(cudaMemcpy(out, h->recs, (size_t)d.N * d.rec_bytes, cudaMemcpyDeviceToHost)); out += (size_t)d.N * d.rec_bytes;
   if (d.hist_env_bytes) { CU(cudaMemcpy(out, h->hist, (size_t)d.N * d.hist_env_bytes, cudaMemcpyDeviceToHost)); out += (size_t)d.N * d.hist_env_bytes; }
@@ -592,12 +736,11 @@ extern "C" int snk_checkpoint_load(snk_env* h, const void* blob_host, size_t byt
   if (hd.magic != CKPT_MAGIC || hd.N != d.N || hd.H != d.H || hd.W != d.W || hd.ns != d.ns || hd.K != d.K || hd.V != d.V ||
       hd.fs != d.fs || hd.dig != d.dig || hd.rec_bytes != d.rec_bytes || hd.hist_env_bytes != d.hist_env_bytes)
     return fail(SNK_E_INVALID, "checkpoint was written by a handle of a different shape");
-  CU(cudaSetDevice(h->device));
+  ON_DEVICE(h);
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(h->recs, in, (size_t)d.N * d.rec_bytes, cudaMemcpyHostToDevice)); in += (size_t)d.N * d.rec_bytes;
   if (d.hist_env_bytes) { CU(cudaMemcpy(h->hist, in, (size_t)d.N * d.hist_env_bytes, cudaMemcpyHostToDevice)); in += (size_t)d.N * d.hist_env_bytes; }
   CU(cudaMemcpy(h->stats, in, STAT_COUNT * sizeof(double), cudaMemcpyHostToDevice));
-  h->env_steps = hd.env_steps;
   h->was_reset = true;
   return SNK_OK;
 }
@@ -605,7 +748,7 @@ extern "C" int snk_checkpoint_load(snk_env* h, const void* blob_host, size_t byt
 extern "C" int snk_set_replay(snk_env* h, const int32_t* draws_host, const int64_t* offsets_host) {
   if (!h || !offsets_host) return fail(SNK_E_INVALID, "null argument");
   if (h->d.rng_mode != RNG_REPLAY) return fail(SNK_E_STATE, "handle was not created with SNK_RNG_REPLAY");
-  CU(cudaSetDevice(h->device));
+  ON_DEVICE(h);
   const int N = h->d.N;
   const int64_t total = offsets_host[N];
   if (offsets_host[0] != 0 || total < 0) return fail(SNK_E_INVALID, "offsets must start at 0 and be non-decreasing");
@@ -625,7 +768,7 @@ extern "C" int snk_set_replay(snk_env* h, const int32_t* draws_host, const int64
 
 extern "C" int snk_replay_cursors(snk_env* h, int32_t* cursors_host) {
   if (!h || !cursors_host) return fail(SNK_E_INVALID, "null argument");
-  CU(cudaSetDevice(h->device));
+  ON_DEVICE(h);
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy2D(cursors_host, sizeof(int32_t), h->recs + h->d.off_hdr + offsetof(EnvHdr, cursor), (size_t)h->d.rec_bytes,
                   sizeof(int32_t), (size_t)h->d.N, cudaMemcpyDeviceToHost));
@@ -634,7 +777,7 @@ extern "C" int snk_replay_cursors(snk_env* h, int32_t* cursors_host) {
 
 extern "C" int snk_device_errors(snk_env* h, uint32_t* bits, int clear) {
   if (!h || !bits) return fail(SNK_E_INVALID, "null argument");
-  CU(cudaSetDevice(h->device));
+  ON_DEVICE(h);
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(bits, h->err, sizeof(uint32_t), cudaMemcpyDeviceToHost));
   if (clear) CU(cudaMemset(h->err, 0, sizeof(uint32_t)));
@@ -649,11 +792,10 @@ extern "C" int snk_stats_dev(snk_env* h, double** stats_dev) {
 
 extern "C" int snk_stats(snk_env* h, double* out_host, int clear) {
   if (!h || !out_host) return fail(SNK_E_INVALID, "null argument");
-  CU(cudaSetDevice(h->device));
+  ON_DEVICE(h);
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(out_host, h->stats, STAT_COUNT * sizeof(double), cudaMemcpyDeviceToHost));
-  out_host[STAT_ENV_STEPS] = h->env_steps;
-  if (clear) { CU(cudaMemset(h->stats, 0, STAT_COUNT * sizeof(double))); h->env_steps = 0.0; }
+  if (clear) CU(cudaMemset(h->stats, 0, STAT_COUNT * sizeof(double)));
   return SNK_OK;
 }
 

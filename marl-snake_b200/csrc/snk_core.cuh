@@ -24,7 +24,8 @@ enum : int { EMPTY = 0, WALL = 1, FRUIT = 2, HEAD = 3, BODY = 4, TAIL = 5 };
 // direction codes 0 UP(-1,0) 1 RIGHT(0,1) 2 DOWN(1,0) 3 LEFT(0,-1)    core/snake.py:33-37
 enum : int { RNG_PHILOX = 0, RNG_REPLAY = 1 };
 enum : uint32_t { ERR_BAD_ACTION = 1, ERR_REPLAY_UNDERRUN = 2, ERR_REPLAY_RANGE = 4, ERR_SPAWN_GIVEUP = 8,
-                  ERR_INTERNAL = 16 };     // a bounds / alignment check of the debug build (-DSNK_DEBUG_CHECKS) failed
+                  ERR_INTERNAL = 16,       // a bounds / alignment check of the debug build (-DSNK_DEBUG_CHECKS) failed
+                  ERR_TMA_TIMEOUT = 32 };  // a record tile's bulk copy did not land within two seconds; tile skipped
 enum : int { DRAW_STEP_FRUIT = 0, DRAW_SPAWN = 1, DRAW_RESET_FRUIT = 2 };
 enum : int { STAT_EPISODES = 0, STAT_RETURN, STAT_EP_STEPS, STAT_FRUITS, STAT_KILLS, STAT_DEATHS,
              STAT_ENV_STEPS, STAT_COUNT = 8 };
@@ -185,15 +186,26 @@ SNK_HD void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
   }
 }
 
-SNK_HD uint32_t draw_word(const Dims& d, uint32_t env_local, uint32_t event, int purpose, uint32_t idx) {
-  const uint64_t gid = ((uint64_t)d.env_off_hi << 32 | d.env_off_lo) + env_local;
+// The stream parameters by value: functions that receive the configuration by reference (out-of-line device
+// functions read it through generic loads) copy them once instead of reloading them around every store.
+struct StreamKey { uint32_t seed_lo, seed_hi, env_off_lo, env_off_hi; };
+SNK_HD StreamKey stream_key(const Dims& d) { StreamKey k = {d.seed_lo, d.seed_hi, d.env_off_lo, d.env_off_hi}; return k; }
+
+SNK_HD uint32_t draw_word(const StreamKey& sk, uint32_t env_local, uint32_t event, int purpose, uint32_t idx) {
+  const uint64_t gid = ((uint64_t)sk.env_off_hi << 32 | sk.env_off_lo) + env_local;
   uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32) ^ 0x534E4B31u, event,
                    ((uint32_t)purpose << 24) | (idx >> 2)};
-  philox4x32_10(c, d.seed_lo, d.seed_hi);
+  philox4x32_10(c, sk.seed_lo, sk.seed_hi);
   const uint32_t k = idx & 3u;                 // select chain: a dynamic index would put c[] in local memory
   return k == 0u ? c[0] : k == 1u ? c[1] : k == 2u ? c[2] : c[3];
 }
+SNK_HD uint32_t draw_word(const Dims& d, uint32_t env_local, uint32_t event, int purpose, uint32_t idx) {
+  return draw_word(stream_key(d), env_local, event, purpose, idx);
+}
 
+SNK_HD uint32_t draw_below(const StreamKey& sk, uint32_t env_local, uint32_t event, int purpose, uint32_t idx, uint32_t n) {
+  return mulhi32(draw_word(sk, env_local, event, purpose, idx), n);
+}
 SNK_HD uint32_t draw_below(const Dims& d, uint32_t env_local, uint32_t event, int purpose, uint32_t idx,
                            uint32_t n) {
   return mulhi32(draw_word(d, env_local, event, purpose, idx), n);

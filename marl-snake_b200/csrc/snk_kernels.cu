@@ -36,10 +36,12 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 #ifdef SNK_DEBUG_CHECKS
 __device__ const uint8_t* dbg_obs_lo; __device__ const uint8_t* dbg_obs_hi;
 __device__ const uint8_t* dbg_hist_lo; __device__ const uint8_t* dbg_hist_hi;
+__device__ const uint8_t* dbg_bits_lo; __device__ const uint8_t* dbg_bits_hi;
 __device__ uint32_t* dbg_err;
 __device__ __forceinline__ void dbg_arm(const KParams& p) {        // every thread writes the same values
   dbg_obs_lo = p.obs; dbg_obs_hi = p.obs ? p.obs + (size_t)p.d.N * p.d.obs_env_bytes : nullptr;
   dbg_hist_lo = p.hist; dbg_hist_hi = p.hist ? p.hist + (size_t)p.d.N * p.d.hist_env_bytes : nullptr;
+  dbg_bits_lo = p.bits; dbg_bits_hi = p.bits ? p.bits + (size_t)p.d.N * p.d.stage_env_bytes : nullptr;
   dbg_err = p.err;
 }
 __device__ __forceinline__ void dbg_store(const void* q, size_t n, const uint8_t* lo, const uint8_t* hi) {
@@ -47,10 +49,12 @@ __device__ __forceinline__ void dbg_store(const void* q, size_t n, const uint8_t
   if (a < lo || a + n > hi || (reinterpret_cast<uintptr_t>(a) & (n - 1))) atomicOr(dbg_err, ERR_INTERNAL);
 }
 #define SNK_CHECK_OBS(q, n) dbg_store((q), (n), dbg_obs_lo, dbg_obs_hi)
+#define SNK_CHECK_BITS(q, n) dbg_store((q), (n), dbg_bits_lo, dbg_bits_hi)
 #define SNK_CHECK_HIST(q, n) dbg_store((q), (n), dbg_hist_lo, dbg_hist_hi)
 #define SNK_ASSERT(p, cond) do { if (!(cond)) atomicOr((p).err, ERR_INTERNAL); } while (0)
 #else
 #define SNK_CHECK_OBS(q, n) ((void)0)
+#define SNK_CHECK_BITS(q, n) ((void)0)
 #define SNK_CHECK_HIST(q, n) ((void)0)
 #define SNK_ASSERT(p, cond) ((void)0)
 #endif
@@ -63,7 +67,13 @@ __device__ __forceinline__ void dbg_store(const void* q, size_t n, const uint8_t
 __device__ unsigned long long* snk_trace_buf;
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define SNK_T(var) const unsigned long long var = gtime()
+// reset timeline of the last reset of a CTA: trace2[cta * 8 + k], k = entry, walls, spawn, snakes, fruits, attempts
+__device__ unsigned long long* snk_trace2_buf;
+#define SNK_R(k) do { if (lane_id() == 0 && snk_trace2_buf) snk_trace2_buf[(size_t)blockIdx.x * 8 + (k)] = gtime(); } while (0)
+#define SNK_RV(k, v) do { if (lane_id() == 0 && snk_trace2_buf) snk_trace2_buf[(size_t)blockIdx.x * 8 + (k)] = (v); } while (0)
 #else
+#define SNK_R(k) ((void)0)
+#define SNK_RV(k, v) ((void)0)
 #define SNK_T(var) ((void)0)
 #endif
 
@@ -90,12 +100,14 @@ __device__ __forceinline__ uint32_t warp_inclusive_sum(uint32_t v, uint32_t lane
 // prefix sum locates the lane range holding a drawn rank, and the warp then scans only that range.
 // (The record is passed as its base address, not as a Rec&: a Rec whose address escapes lives in local
 // memory, and every byte store into the grid would force its pointer fields to be reloaded from there.)
+// (Likewise every configuration value is copied into a local first: `p` arrives as a generic reference here, and
+// a field read after a shared-memory store would be reloaded through a generic load -- 1 to 2 us per reset.)
 __device__ __noinline__ void place_fruits_warp(const KParams& p, uint8_t* rec_base, uint32_t env_local, int k, int purpose) {
   const Dims& d = p.d;
   const Rec r = rec_view(rec_base, d);
   const uint32_t FULL = 0xffffffffu;
   const uint32_t lane = lane_id();
-  const int HW = d.HW;
+  const int HW = d.HW, rng_mode = d.rng_mode;
   const int nwords = (HW + 3) >> 2, cw = (nwords + 31) >> 5;
   const uint32_t* gw = reinterpret_cast<const uint32_t*>(r.grid);        // record start is 16-byte aligned
   auto load_zeros = [&](int w) -> uint32_t {                              // 0x80 per EMPTY cell of word w
@@ -116,7 +128,7 @@ __device__ __noinline__ void place_fruits_warp(const KParams& p, uint8_t* rec_ba
   if (n_empty == 0 || k <= 0) return;              // reference draws nothing when no cell is empty
   int rank = -1;
   if ((int)lane < k) {
-    if (d.rng_mode == RNG_PHILOX) {
+    if (rng_mode == RNG_PHILOX) {
       rank = (int)draw_below(d, env_local, r.hdr->event, purpose, lane, (uint32_t)n_empty);
     } else {
       const int64_t lo = p.replay_off[env_local], hi = p.replay_off[env_local + 1];
@@ -129,7 +141,7 @@ __device__ __noinline__ void place_fruits_warp(const KParams& p, uint8_t* rec_ba
     }
   }
   __syncwarp();
-  if (lane == 0 && d.rng_mode == RNG_REPLAY) r.hdr->cursor += (uint32_t)k;
+  if (lane == 0 && rng_mode == RNG_REPLAY) r.hdr->cursor += (uint32_t)k;
   int mycell = -1;
   if (cw <= 64) {
     // Every drawing lane resolves its own rank, all draws in parallel: a binary search over the lanes' prefix sums
@@ -202,27 +214,32 @@ __device__ __noinline__ void reset_env_warp(const KParams& p, uint8_t* rec_base,
   const Dims& d = p.d;
   const Rec r = rec_view(rec_base, d);
   const uint32_t lane = lane_id();
-  const int ns = d.ns, K = d.K, W = d.W;
+  // values read inside loops live in registers (see place_fruits_warp); what a rare branch reads once stays in `p`
+  const int ns = d.ns, K = d.K, W = d.W, H = d.H, rng_mode = d.rng_mode;
+  const uint32_t n_cand = d.n_cand, inv_row_words = p.inv_row_words;
+  const uint64_t* const spawn = p.spawn;
+  SNK_R(0);
   // make_grid: walled empty box (core/grid_util.py:14-20), one grid row at a time so no division is needed
   if ((W & 3) == 0 && W >= 8) {          // flat over the grid's 32-bit words; row = word / (W/4) by a multiply-high
     uint32_t* gw = reinterpret_cast<uint32_t*>(r.grid);
-    const int wpr = W >> 2, nw = d.H * wpr;
+    const int wpr = W >> 2, nw = H * wpr;
     for (int j = (int)lane; j < nw; j += 32) {
-      const int rr = (int)__umulhi((uint32_t)j, p.inv_row_words), x = j - rr * wpr;
-      const bool edge = rr == 0 || rr == d.H - 1;
+      const int rr = (int)__umulhi((uint32_t)j, inv_row_words), x = j - rr * wpr;
+      const bool edge = rr == 0 || rr == H - 1;
       gw[j] = edge ? 0x01010101u : (x == 0 ? 0x00000001u : 0u) | (x == wpr - 1 ? 0x01000000u : 0u);
     }
   } else {
-    for (int rr = 0; rr < d.H; ++rr) {
-      const bool edge = rr == 0 || rr == d.H - 1;
+    for (int rr = 0; rr < H; ++rr) {
+      const bool edge = rr == 0 || rr == H - 1;
       for (int c = (int)lane; c < W; c += 32) r.grid[rr * W + c] = (uint8_t)((edge || c == 0 || c == W - 1) ? WALL : EMPTY);
     }
   }
   __syncwarp();
 
+  SNK_R(1);
   uint64_t entry = 0;
   const bool me = (int)lane < ns;
-  if (d.rng_mode == RNG_REPLAY) {
+  if (rng_mode == RNG_REPLAY) {
     if (me) {
       const int64_t lo = p.replay_off[env_local], hi = p.replay_off[env_local + 1];
       const int64_t at = lo + r.hdr->cursor + lane;
@@ -230,9 +247,9 @@ __device__ __noinline__ void reset_env_warp(const KParams& p, uint8_t* rec_base,
       if (at >= hi) atomicOr(p.err, ERR_REPLAY_UNDERRUN);
       else {
         pick = p.replay[at];
-        if (pick < 0 || (uint32_t)pick >= d.n_cand) { atomicOr(p.err, ERR_REPLAY_RANGE); pick = 0; }
+        if (pick < 0 || (uint32_t)pick >= n_cand) { atomicOr(p.err, ERR_REPLAY_RANGE); pick = 0; }
       }
-      entry = p.spawn[pick];
+      entry = spawn[pick];
     }
     __syncwarp();
     if (lane == 0) r.hdr->cursor += (uint32_t)ns;
@@ -240,8 +257,8 @@ __device__ __noinline__ void reset_env_warp(const KParams& p, uint8_t* rec_base,
   // sample poses until no two snakes share a cell (np.random.permutation(n)[:ns] retry loop, :579-586;
   // ns independent uniform picks conditioned on "no shared cell" have the same law)
   for (uint32_t attempt = 0;; ++attempt) {
-    if (d.rng_mode == RNG_PHILOX && me)
-      entry = p.spawn[draw_below(d, env_local, r.hdr->event, DRAW_SPAWN, attempt * (uint32_t)ns + lane, d.n_cand)];
+    if (rng_mode == RNG_PHILOX && me)
+      entry = spawn[draw_below(d, env_local, r.hdr->event, DRAW_SPAWN, attempt * (uint32_t)ns + lane, n_cand)];
     if (me) {
       int c = spawn_head(entry);
       r.grid[c] = (uint8_t)(BODY + 10 * lane);
@@ -255,8 +272,9 @@ __device__ __noinline__ void reset_env_warp(const KParams& p, uint8_t* rec_base,
       for (int j = 1; j < K; ++j) { c += dir_delta(spawn_link(entry, j), W); clash |= r.grid[c] != BODY + 10 * lane; }
     }
     const uint32_t any_clash = __ballot_sync(0xffffffffu, clash);
+    SNK_RV(5, (unsigned long long)attempt + 1);
     if (!any_clash) break;
-    if (d.rng_mode == RNG_REPLAY) { if (lane == 0) atomicOr(p.err, ERR_REPLAY_RANGE); break; }
+    if (rng_mode == RNG_REPLAY) { if (lane == 0) atomicOr(p.err, ERR_REPLAY_RANGE); break; }
     if (attempt + 1 >= SPAWN_ATTEMPT_CAP) { if (lane == 0) atomicOr(p.err, ERR_SPAWN_GIVEUP); break; }
     __syncwarp();
     if (me) {
@@ -269,6 +287,7 @@ __device__ __noinline__ void reset_env_warp(const KParams& p, uint8_t* rec_base,
   __syncwarp();
   // snake table + body directions (toward the head), all snakes at once: with directions in the grid bytes (dig) a
   // snake only touches its own cells, with a direction plane the shared words are updated atomically
+  SNK_R(2);
   auto write_snake = [&](int s) {
     int c = spawn_head(entry);
     r.head[s] = (uint16_t)c;
@@ -277,7 +296,7 @@ __device__ __noinline__ void reset_env_warp(const KParams& p, uint8_t* rec_base,
       const int l = spawn_link(entry, j);
       c += dir_delta(l, W);
       r.grid[c] = (uint8_t)((j == K - 1 ? TAIL : BODY) + 10 * s);
-      if (d.dig) set_body_dir(d, r, c, (l + 2) & 3);   // toward the head
+      if (d.dig) r.grid[c] = (uint8_t)((r.grid[c] & 63) | (((l + 2) & 3) << 6));   // toward the head
       else dirp_set_atomic(r.dirp, c, (l + 2) & 3);    // plane words are shared between snakes
     }
     r.tail[s] = (uint16_t)c;
@@ -288,9 +307,11 @@ __device__ __noinline__ void reset_env_warp(const KParams& p, uint8_t* rec_base,
   };
   if (me) write_snake((int)lane);
   __syncwarp();
+  SNK_R(3);
   place_fruits_warp(p, rec_base, env_local, d.nfruits, DRAW_RESET_FRUIT);
   if (lane == 0) { r.hdr->alive_counter = ns; r.hdr->episode_length = 0; }
   __syncwarp();
+  SNK_R(4);
 }
 
 // ---- the fused step / reset / encode kernel -------------------------------------------------------
@@ -332,6 +353,18 @@ __device__ __forceinline__ void st_cs_64(void* p, uint2 a) {
   __stcs(reinterpret_cast<uint2*>(p), a);
 }
 
+// Channel-bit output (snk_step_bits): one byte per window cell, bit c = channel c.  The byte LUT mirrors the 8-byte
+// LUT entry for entry, so the entry address `e8` of a cell (lut32 + 8 * index) names its byte at lutb32 + index.
+__device__ __forceinline__ void st_bits(uint8_t* q, uint32_t v) {
+  SNK_CHECK_BITS(q, 1);
+  *q = (uint8_t)v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a);
+__device__ __forceinline__ void emit_bits(uint8_t* bitsv, int ca, int ohw, uint32_t lut32, uint32_t lutb32, uint32_t e8a, uint32_t e8b) {
+  if (ca >= 0 && ca < ohw) st_bits(bitsv + ca, lds_u8(lutb32 + ((e8a - lut32) >> 3)));
+  if (ca + 1 >= 0 && ca + 1 < ohw) st_bits(bitsv + ca + 1, lds_u8(lutb32 + ((e8b - lut32) >> 3)));
+}
+
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
   uint32_t v;
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
@@ -358,13 +391,22 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+// Waits for the phase; gives up after two seconds of wall time (%globaltimer, not a poll count: a debugger, a
+// profiler replay or a time-sliced GPU may stall a correct run for long) and returns false -- the caller raises the
+// sticky ERR_TMA_TIMEOUT bit and skips the tile instead of trapping the whole context.
+__device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
   uint32_t done = 0;
-  int spins = 0;
-  while (!done) {
+  unsigned long long t0 = 0;
+  for (uint32_t spins = 1; ; ++spins) {
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                  : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
-    if (!done && ++spins > (1 << 22)) __trap();          // never hang the GPU on a lost transaction
+    if (done) return true;
+    if ((spins & 1023u) == 0u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) return false;
+    }
   }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -516,7 +558,7 @@ __device__ __forceinline__ GroupOut step_group(const KParams& p, const SH& sh, R
 // Leaves per-environment flags in s_flag[] (F_RESET / F_INIT / F_SKIP).
 template <class SH>
 __device__ __forceinline__ void tile_rules(const KParams& p, const SH& sh, uint8_t* s_rec, int e0, int ne,
-                                           uint8_t* s_flag, uint32_t action) {
+                                           uint8_t* s_flag, uint32_t action, int t) {
   const Dims& d = p.d;
   const uint32_t FULL = 0xffffffffu;
   const uint32_t lane = lane_id();
@@ -529,11 +571,14 @@ __device__ __forceinline__ void tile_rules(const KParams& p, const SH& sh, uint8
   const bool active = env_ok && i < ns;
   const int e = e0 + g;
   Rec r = rec_view(s_rec + (size_t)(env_ok ? g : 0) * d.rec_bytes, d);
-  const size_t io = (size_t)e * ns + i;
+  // outputs of step t of a multi-step launch (snk_step_many) land t * [N, ns] (t * [N] for `finished`) further on
+  const size_t io = (size_t)t * d.N * ns + (size_t)e * ns + i;
+  const size_t ie = (size_t)t * d.N + e;
 
   uint8_t flag = 0;            // per environment (identical on its lanes)
   int fruit = 0;
   if (p.mode == MODE_STEP) {
+    if (e0 == 0 && lane == 0) atomicAdd(p.stats + STAT_ENV_STEPS, (double)d.N);   // once per launch: env steps executed
     if (active && i == 0) r.hdr->event += 1;
     __syncwarp();
     // kill-credit scratch: the tile's 32 viewer words, which are only filled after the rules
@@ -542,7 +587,7 @@ __device__ __forceinline__ void tile_rules(const KParams& p, const SH& sh, uint8
     fruit = res.fruit_taken;
     // terminal info, rollout statistics, statistics reset                          :396-412
     const bool fin = env_ok && res.finished;
-    if (active && i == 0 && p.fin) p.fin[e] = fin ? 1 : 0;
+    if (active && i == 0 && p.fin) p.fin[ie] = fin ? 1 : 0;
     const uint32_t fin_m = __ballot_sync(FULL, fin && i == 0);
     const uint32_t dead_m = __ballot_sync(FULL, res.newly_dead);
     if (lane == 0 && dead_m) atomicAdd(p.stats + STAT_DEATHS, (double)__popc(dead_m));
@@ -624,7 +669,8 @@ __device__ __forceinline__ uint32_t window_mask(int V, int oh, int ow, int H, in
 // when ohw is odd, so units are laid out from the address parity and the end units may be half units.
 template <class SH>
 __device__ __forceinline__ void encode_viewer_fs1(const KParams& p, const SH& sh, const uint8_t* base,
-                                                  uint32_t grid32, int v, uint8_t* outv, uint32_t lut32) {
+                                                  uint32_t grid32, int v, uint8_t* outv, uint32_t lut32,
+                                                  uint8_t* bitsv, uint32_t lutb32) {
   const Dims& d = p.d;
   const uint32_t lane = lane_id();
   const int ns = sh.ns(), W = sh.W(), ohw = sh.ohw(), ow = sh.ow(), oh = sh.oh(), LS = sh.lut_stride();
@@ -665,16 +711,22 @@ __device__ __forceinline__ void encode_viewer_fs1(const KParams& p, const SH& sh
         la1 = (((ka1 * 205u) >> 11) == (uint32_t)v) ? lutown : lut32;
         lb1 = (((kb1 * 205u) >> 11) == (uint32_t)v) ? lutown : lut32;
       }
-      const uint2 qa0 = lds_v2(la0 + ka0 * 8u), qb0 = lds_v2(lb0 + kb0 * 8u);
-      const uint2 qa1 = lds_v2(la1 + ka1 * 8u), qb1 = lds_v2(lb1 + kb1 * 8u);
-      uint8_t* dst0 = outv + (ptrdiff_t)ca0 * 8;
-      if (ca0 >= 0 && ca0 + 1 < ohw) st_cs_128(dst0, qa0, qb0);
-      else if (ca0 >= 0) st_cs_64(dst0, qa0);
-      else st_cs_64(dst0 + 8, qb0);
-      if (has1) {
-        uint8_t* dst1 = outv + (ptrdiff_t)ca1 * 8;
-        if (ca1 + 1 < ohw) st_cs_128(dst1, qa1, qb1);
-        else st_cs_64(dst1, qa1);
+      if (outv) {
+        const uint2 qa0 = lds_v2(la0 + ka0 * 8u), qb0 = lds_v2(lb0 + kb0 * 8u);
+        const uint2 qa1 = lds_v2(la1 + ka1 * 8u), qb1 = lds_v2(lb1 + kb1 * 8u);
+        uint8_t* dst0 = outv + (ptrdiff_t)ca0 * 8;
+        if (ca0 >= 0 && ca0 + 1 < ohw) st_cs_128(dst0, qa0, qb0);
+        else if (ca0 >= 0) st_cs_64(dst0, qa0);
+        else st_cs_64(dst0 + 8, qb0);
+        if (has1) {
+          uint8_t* dst1 = outv + (ptrdiff_t)ca1 * 8;
+          if (ca1 + 1 < ohw) st_cs_128(dst1, qa1, qb1);
+          else st_cs_64(dst1, qa1);
+        }
+      }
+      if (bitsv) {
+        emit_bits(bitsv, ca0, ohw, lut32, lutb32, la0 + ka0 * 8u, lb0 + kb0 * 8u);
+        if (has1) emit_bits(bitsv, ca1, ohw, lut32, lutb32, la1 + ka1 * 8u, lb1 + kb1 * 8u);
       }
     }
   } else {                       // windows wider than 16 cells: plain index arithmetic, per-viewer LUT
@@ -683,26 +735,31 @@ __device__ __forceinline__ void encode_viewer_fs1(const KParams& p, const SH& sh
       const int ca = 2 * u - shift, cb = ca + 1;
       const bool va = ca >= 0, vb = cb < ohw;
       uint2 qa, qb;
+      uint32_t codea = 0, codeb = 0;
       {
         const int c = va ? ca : 0;
         const int ci = c / ow, cj = c - ci * ow;
         const int rr = r0 + ci, cc = c0 + cj;
-        uint32_t code = 0;
-        if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = cell_code(d, grid[rr * W + cc]);
-        qa = lut[code];
+        if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) codea = cell_code(d, grid[rr * W + cc]);
+        qa = lut[codea];
       }
       {
         const int c = vb ? cb : 0;
         const int ci = c / ow, cj = c - ci * ow;
         const int rr = r0 + ci, cc = c0 + cj;
-        uint32_t code = 0;
-        if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) code = cell_code(d, grid[rr * W + cc]);
-        qb = lut[code];
+        if ((unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W) codeb = cell_code(d, grid[rr * W + cc]);
+        qb = lut[codeb];
       }
-      uint8_t* dst = outv + (ptrdiff_t)ca * 8;
-      if (va && vb) st_cs_128(dst, qa, qb);
-      else if (va) st_cs_64(dst, qa);
-      else st_cs_64(dst + 8, qb);
+      if (outv) {
+        uint8_t* dst = outv + (ptrdiff_t)ca * 8;
+        if (va && vb) st_cs_128(dst, qa, qb);
+        else if (va) st_cs_64(dst, qa);
+        else st_cs_64(dst + 8, qb);
+      }
+      if (bitsv) {
+        const uint32_t lv = lut32 + (uint32_t)(v * LS) * 8u;
+        emit_bits(bitsv, ca, ohw, lut32, lutb32, lv + codea * 8u, lv + codeb * 8u);
+      }
     }
   }
 }
@@ -749,7 +806,8 @@ __device__ __forceinline__ uint32_t make_viewer_word(const KParams& p, const SH&
 
 template <class SH>
 __device__ __forceinline__ void encode_viewer_reg(const KParams& p, const SH& sh, uint32_t grid32, uint32_t vw,
-                                                  const CellWords& cw, int v, uint8_t* outv, uint32_t lut32) {
+                                                  const CellWords& cw, int v, uint8_t* outv, uint32_t lut32,
+                                                  uint8_t* bitsv, uint32_t lutb32) {
   const int lane = (int)lane_id();
   const int ohw = sh.ohw(), B = p.view_bits;
   const uint32_t lutv32 = lut32 + (uint32_t)(v * sh.lut_stride()) * 8u;          // entry 0 is all zero
@@ -769,19 +827,25 @@ __device__ __forceinline__ void encode_viewer_reg(const KParams& p, const SH& sh
   const uint32_t k0 = lds_u8(a0) & cm, k1 = lds_u8(a1) & cm, k2 = lds_u8(a2) & cm, k3 = lds_u8(a3) & cm;
   SNK_ASSERT(p, k0 < (uint32_t)sh.lut_stride() && k1 < (uint32_t)sh.lut_stride() && k2 < (uint32_t)sh.lut_stride() &&
                 k3 < (uint32_t)sh.lut_stride());
-  const uint2 q0 = lds_v2(lutv32 + k0 * 8u), q1 = lds_v2(lutv32 + k1 * 8u);
-  const uint2 q2 = lds_v2(lutv32 + k2 * 8u), q3 = lds_v2(lutv32 + k3 * 8u);
   const int ca0 = 2 * lane - shift, ca1 = ca0 + 64;
-  if (lane < units) {
-    uint8_t* dst0 = outv + (ptrdiff_t)ca0 * 8;
-    if (ca0 >= 0 && ca0 + 1 < ohw) st_cs_128(dst0, q0, q1);
-    else if (ca0 >= 0) st_cs_64(dst0, q0);
-    else st_cs_64(dst0 + 8, q1);
+  if (outv) {
+    const uint2 q0 = lds_v2(lutv32 + k0 * 8u), q1 = lds_v2(lutv32 + k1 * 8u);
+    const uint2 q2 = lds_v2(lutv32 + k2 * 8u), q3 = lds_v2(lutv32 + k3 * 8u);
+    if (lane < units) {
+      uint8_t* dst0 = outv + (ptrdiff_t)ca0 * 8;
+      if (ca0 >= 0 && ca0 + 1 < ohw) st_cs_128(dst0, q0, q1);
+      else if (ca0 >= 0) st_cs_64(dst0, q0);
+      else st_cs_64(dst0 + 8, q1);
+    }
+    if (lane + 32 < units) {
+      uint8_t* dst1 = outv + (ptrdiff_t)ca1 * 8;
+      if (ca1 + 1 < ohw) st_cs_128(dst1, q2, q3);
+      else st_cs_64(dst1, q2);
+    }
   }
-  if (lane + 32 < units) {
-    uint8_t* dst1 = outv + (ptrdiff_t)ca1 * 8;
-    if (ca1 + 1 < ohw) st_cs_128(dst1, q2, q3);
-    else st_cs_64(dst1, q2);
+  if (bitsv) {
+    emit_bits(bitsv, ca0, ohw, lut32, lutb32, lutv32 + k0 * 8u, lutv32 + k1 * 8u);
+    emit_bits(bitsv, ca1, ohw, lut32, lutb32, lutv32 + k2 * 8u, lutv32 + k3 * 8u);
   }
 }
 
@@ -809,7 +873,8 @@ __device__ __forceinline__ PadCells<kU> make_pad_cells(const SH& sh, int shift) 
 
 template <class SH, int kU>
 __device__ __forceinline__ void encode_viewer_pad(const KParams& p, const SH& sh, uint32_t org32, const PadCells<kU>& pc,
-                                                  int shift, int v, uint8_t* outv, uint32_t lut32) {
+                                                  int shift, int v, uint8_t* outv, uint32_t lut32,
+                                                  uint8_t* bitsv, uint32_t lutb32) {
   const int lane = (int)lane_id(), ohw = sh.ohw(), LS = sh.lut_stride();
   const bool dual = SH::kMayDual && p.lut_dual != 0;        // {as-other, as-own} pair instead of one LUT per viewer
   const uint32_t lutv32 = dual ? lut32 : lut32 + (uint32_t)(v * LS) * 8u;
@@ -825,19 +890,25 @@ __device__ __forceinline__ void encode_viewer_pad(const KParams& p, const SH& sh
       a0 += (c0 - own_lo < 3u) ? own_delta : 0u; a1 += (c1 - own_lo < 3u) ? own_delta : 0u;
       a2 += (c2 - own_lo < 3u) ? own_delta : 0u; a3 += (c3 - own_lo < 3u) ? own_delta : 0u;
     }
-    const uint2 q0 = lds_v2(a0), q1 = lds_v2(a1), q2 = lds_v2(a2), q3 = lds_v2(a3);
     const int u0 = lane + 32 * k2, u1 = u0 + 32;
     const int ca0 = 2 * u0 - shift, ca1 = 2 * u1 - shift;
-    if (u0 < units) {
-      uint8_t* dst0 = outv + (ptrdiff_t)ca0 * 8;
-      if (ca0 >= 0 && ca0 + 1 < ohw) st_cs_128(dst0, q0, q1);
-      else if (ca0 >= 0) st_cs_64(dst0, q0);
-      else st_cs_64(dst0 + 8, q1);
+    if (outv) {
+      const uint2 q0 = lds_v2(a0), q1 = lds_v2(a1), q2 = lds_v2(a2), q3 = lds_v2(a3);
+      if (u0 < units) {
+        uint8_t* dst0 = outv + (ptrdiff_t)ca0 * 8;
+        if (ca0 >= 0 && ca0 + 1 < ohw) st_cs_128(dst0, q0, q1);
+        else if (ca0 >= 0) st_cs_64(dst0, q0);
+        else st_cs_64(dst0 + 8, q1);
+      }
+      if (u1 < units) {
+        uint8_t* dst1 = outv + (ptrdiff_t)ca1 * 8;
+        if (ca1 + 1 < ohw) st_cs_128(dst1, q2, q3);
+        else st_cs_64(dst1, q2);
+      }
     }
-    if (u1 < units) {
-      uint8_t* dst1 = outv + (ptrdiff_t)ca1 * 8;
-      if (ca1 + 1 < ohw) st_cs_128(dst1, q2, q3);
-      else st_cs_64(dst1, q2);
+    if (bitsv) {
+      emit_bits(bitsv, ca0, ohw, lut32, lutb32, a0, a1);
+      emit_bits(bitsv, ca1, ohw, lut32, lutb32, a2, a3);
     }
   }
 }
@@ -845,7 +916,7 @@ __device__ __forceinline__ void encode_viewer_pad(const KParams& p, const SH& sh
 // Full-grid observation: the window IS the grid, so window cell c reads grid byte c.
 template <class SH>
 __device__ __forceinline__ void encode_viewer_direct(const SH& sh, uint32_t grid32, int v, uint8_t* outv, uint32_t lut32,
-                                                     uint32_t cm) {
+                                                     uint32_t cm, uint8_t* bitsv, uint32_t lutb32) {
   const int lane = (int)lane_id();
   const int ohw = sh.ohw();
   const uint32_t lutv32 = lut32 + (uint32_t)(v * sh.lut_stride()) * 8u;
@@ -859,16 +930,22 @@ __device__ __forceinline__ void encode_viewer_direct(const SH& sh, uint32_t grid
     const uint32_t k1 = lds_u8(ca0 + 1 < ohw ? grid32 + (uint32_t)(ca0 + 1) : lutv32) & cm;
     const uint32_t k2 = lds_u8(ca1 >= 0 ? grid32 + (uint32_t)ca1 : lutv32) & cm;
     const uint32_t k3 = lds_u8(ca1 + 1 < ohw ? grid32 + (uint32_t)(ca1 + 1) : lutv32) & cm;
-    const uint2 q0 = lds_v2(lutv32 + k0 * 8u), q1 = lds_v2(lutv32 + k1 * 8u);
-    const uint2 q2 = lds_v2(lutv32 + k2 * 8u), q3 = lds_v2(lutv32 + k3 * 8u);
-    uint8_t* dst0 = outv + (ptrdiff_t)ca0 * 8;
-    if (ca0 >= 0 && ca0 + 1 < ohw) st_cs_128(dst0, q0, q1);
-    else if (ca0 >= 0) st_cs_64(dst0, q0);
-    else st_cs_64(dst0 + 8, q1);
-    if (has1) {
-      uint8_t* dst1 = outv + (ptrdiff_t)ca1 * 8;
-      if (ca1 + 1 < ohw) st_cs_128(dst1, q2, q3);
-      else st_cs_64(dst1, q2);
+    if (outv) {
+      const uint2 q0 = lds_v2(lutv32 + k0 * 8u), q1 = lds_v2(lutv32 + k1 * 8u);
+      const uint2 q2 = lds_v2(lutv32 + k2 * 8u), q3 = lds_v2(lutv32 + k3 * 8u);
+      uint8_t* dst0 = outv + (ptrdiff_t)ca0 * 8;
+      if (ca0 >= 0 && ca0 + 1 < ohw) st_cs_128(dst0, q0, q1);
+      else if (ca0 >= 0) st_cs_64(dst0, q0);
+      else st_cs_64(dst0 + 8, q1);
+      if (has1) {
+        uint8_t* dst1 = outv + (ptrdiff_t)ca1 * 8;
+        if (ca1 + 1 < ohw) st_cs_128(dst1, q2, q3);
+        else st_cs_64(dst1, q2);
+      }
+    }
+    if (bitsv) {
+      emit_bits(bitsv, ca0, ohw, lut32, lutb32, lutv32 + k0 * 8u, lutv32 + k1 * 8u);
+      if (has1) emit_bits(bitsv, ca1, ohw, lut32, lutb32, lutv32 + k2 * 8u, lutv32 + k3 * 8u);
     }
   }
 }
@@ -877,7 +954,7 @@ __device__ __forceinline__ void encode_viewer_direct(const SH& sh, uint32_t grid
 // output order ([viewer][cell][frame], oldest first) in the warp's staging area, then expanded to NHWC
 // with flat 128-bit stores.  The frame history lives in HBM as one byte per window cell per stored frame,
 // rows of a ring (hist layout); each step reads fs-1 rows and writes one.
-template <class SH, int kFS>
+template <class SH, int kFS, bool kBits>
 __device__ __forceinline__ void encode_env_stacked(const KParams& p, const SH& sh, const uint8_t* base, int e,
                                                    int qflag, uint8_t* s_stage, uint32_t lut32, const uint8_t* s_lut,
                                                    const uint8_t* s_hist) {
@@ -885,8 +962,10 @@ __device__ __forceinline__ void encode_env_stacked(const KParams& p, const SH& s
   const uint32_t lane = lane_id();
   const int ns = sh.ns(), W = sh.W(), ohw = sh.ohw(), ow = sh.ow(), oh = sh.oh(), LS = sh.lut_stride(), fs = sh.fs();
   const int H = d.H, V = d.V;
-  const bool want_obs = p.obs != nullptr;
-  const bool vec16 = want_obs && p.vec16 != 0;
+  uint8_t* const bits_out = kBits ? p.bits : nullptr;
+  const bool want_nhwc = p.obs != nullptr;
+  const bool want_obs = want_nhwc || bits_out != nullptr;      // staging is needed for either output
+  const bool vec16 = want_nhwc && p.vec16 != 0;
   const uint32_t tab32 = lut32 + (uint32_t)p.enc_tab_off + 8u;
   const uint8_t* grid = base;
   const uint32_t grid32 = (uint32_t)__cvta_generic_to_shared(grid);
@@ -978,8 +1057,19 @@ __device__ __forceinline__ void encode_env_stacked(const KParams& p, const SH& s
     }
   }
   __syncwarp();
+  // ---- channel bits as they are (snk_step_bits): the staging area IS the [viewer][cell][frame] block
+  if (bits_out) {
+    uint8_t* outb = bits_out + (size_t)e * d.stage_env_bytes;
+    const int total = d.stage_env_bytes;
+    if (((reinterpret_cast<uintptr_t>(outb) | (uintptr_t)total) & 3) == 0) {
+      const uint32_t* s4 = reinterpret_cast<const uint32_t*>(s_stage);
+      for (int u = (int)lane; u < (total >> 2); u += 32) { SNK_CHECK_BITS(outb + 4 * u, 4); reinterpret_cast<uint32_t*>(outb)[u] = s4[u]; }
+    } else {
+      for (int u = (int)lane; u < total; u += 32) st_bits(outb + u, s_stage[u]);
+    }
+  }
   // ---- channel bits -> NHWC uint8, coalesced
-  if (want_obs) {
+  if (want_nhwc) {
     uint8_t* out = p.obs + (size_t)e * d.obs_env_bytes;
     const int total = d.stage_env_bytes;                 // staging bytes == 8-byte output units
     if (vec16) {
@@ -1012,9 +1102,14 @@ __device__ __forceinline__ void encode_env_stacked(const KParams& p, const SH& s
 // kCoop = true:  the CTA owns ONE tile; all threads move the records, warp 0 runs the rules, then the
 //                warps share the tile's viewers -- for small batches and large records, where one warp per
 //                tile leaves the GPU short of parallel work.
-template <int kNS, int kW, int kOH, int kOW, int kFS, bool kCoop, int kEnc>
+// kVar: 0 the plain step (NHWC observation, one step per launch) -- the lean instance every benchmark line runs;
+//       1 channel-bit output as well / instead (snk_step_bits); 2 several steps per launch (snk_step_many), any output.
+//       The variants only differ in code that is compiled out of variant 0, which keeps its register count.
+template <int kNS, int kW, int kOH, int kOW, int kFS, bool kCoop, int kEnc, int kVar>
 __global__ void __launch_bounds__(kCoop ? SNK_MAX_THREADS_COOP : SNK_MAX_THREADS)
 snk_tile_kernel(const __grid_constant__ KParams p) {
+  constexpr bool kBits = kVar >= 1, kMulti = kVar == 2;
+  uint8_t* const bits_out = kBits ? p.bits : nullptr;
   extern __shared__ __align__(16) uint8_t smem[];
   const Dims& d = p.d;
 #ifdef SNK_DEBUG_CHECKS
@@ -1097,7 +1192,7 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   __syncthreads();
   SNK_T(t_issued);
   if (!kCoop && ne == 0) return;
-  const bool want_obs = p.obs != nullptr;
+  const bool want_obs = p.obs != nullptr || bits_out != nullptr;          // NHWC bytes, channel bits, or both
   constexpr int kU = Shape<kNS, kW, kOH, kOW, kFS>::kUnits;
   PadCells<kU> pc;
   int pc_shift = -1;
@@ -1111,15 +1206,34 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
       for (int k = tid - 32 * zw; k < n16; k += nt - 32 * zw) z[k] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (warp != 0 && warp < ne * ns) {
-      pc_shift = (int)((reinterpret_cast<uintptr_t>(p.obs + ((size_t)e0 * ns + warp) * (size_t)ohw * 8) >> 3) & 1);
+      pc_shift = p.obs ? (int)((reinterpret_cast<uintptr_t>(p.obs + ((size_t)e0 * ns + warp) * (size_t)ohw * 8) >> 3) & 1) : 0;
       pc = make_pad_cells<Shape<kNS, kW, kOH, kOW, kFS>, kU>(sh, pc_shift);
     }
   }
-  if (p.use_tma && ne > 0) mbar_wait(mbar, 0);
+  if (p.use_tma && ne > 0 && !mbar_wait(mbar, 0)) {      // lost transaction: flag it, leave the tile untouched
+    if (lane == 0) atomicOr(p.err, ERR_TMA_TIMEOUT);
+    return;
+  }
   SNK_T(t_loaded);
 
+  const uint32_t lut32 = (uint32_t)__cvta_generic_to_shared(s_lut);
+  const uint32_t lutb32 = lut32 + (uint32_t)p.enc_lutb_off;            // fs == 1: byte LUT (channel bits) behind the 8-byte LUT
+  const int wfirst = kCoop ? warp : 0, wstep = kCoop ? nwarps : 1;
+  // snk_step_many: T > 1 steps of this tile back to back with the records resident in shared memory (frame_stack 1
+  // only; T == 1 is the ordinary step).  Step t reads actions[t], writes rewards[t] / dones[t] and, when asked for
+  // every step, obs[t]; otherwise only the last step renders.
+  const int T = (kMulti && fs == 1 && p.mode == MODE_STEP) ? p.T : 1;
+  CellWords cw;
+  bool cw_ready = false;
+#pragma unroll 1
+  for (int t = 0; t < T; ++t) {
+  const bool last = t == T - 1;
   if (!kCoop || warp == 0) {
-    if (ne > 0) tile_rules(p, sh, s_rec, e0, ne, s_flag, action);
+    if (t > 0) {
+      const int g = (int)lane / G, i = (int)lane - g * G;
+      action = (g < ne && i < ns) ? __ldg(p.actions + ((size_t)t * d.N + e0 + g) * ns + i) : 0u;
+    }
+    if (ne > 0) tile_rules(p, sh, s_rec, e0, ne, s_flag, action, t);
     if (kEnc == ENC_REG && ne > 0) {           // crop origin + out-of-grid rows / columns of every viewer of the tile
       const int g = (int)lane / G, i = (int)lane - g * G;
       if (g < ne && i < ns) s_view[lane] = make_viewer_word(p, sh, s_rec + (size_t)g * d.rec_bytes, i);
@@ -1132,7 +1246,7 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
         s_view[lane] = (uint32_t)((r0 + d.V) * sh.pad_pitch() + c0 + sh.pad_left());
       }
     }
-    if (p.use_tma) fence_proxy_async();        // the rules' shared-memory writes -> visible to the bulk store
+    if (p.use_tma && last) fence_proxy_async();   // the rules' shared-memory writes -> visible to the bulk store
     __syncwarp();
   }
   SNK_T(t_ruled);
@@ -1140,23 +1254,26 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   SNK_T(t_synced);
   if (ne == 0) return;
 
-  const uint32_t lut32 = (uint32_t)__cvta_generic_to_shared(s_lut);
-  const int wfirst = kCoop ? warp : 0, wstep = kCoop ? nwarps : 1;
-
   if (fs == 1) {
     // ---- write the records back: shared -> HBM (nothing below modifies them).  The bulk store runs
     //      asynchronously under the encode; its issuer waits for the shared-memory reads before exiting.
-    if (p.use_tma) {
-      if (elected) bulk_store(p.recs + (size_t)e0 * d.rec_bytes, rec32, tile_load_bytes);
-    } else {
-      uint4* dst = reinterpret_cast<uint4*>(p.recs + (size_t)e0 * d.rec_bytes);
-      const uint4* src = reinterpret_cast<const uint4*>(s_rec);
-      const int n16 = ne * (d.rec_bytes >> 4);
-      if (kCoop) { for (int k = tid; k < n16; k += nt) dst[k] = src[k]; }
-      else { for (int k = (int)lane; k < n16; k += 32) dst[k] = src[k]; }
+    if (last) {
+      if (p.use_tma) {
+        if (elected) bulk_store(p.recs + (size_t)e0 * d.rec_bytes, rec32, tile_load_bytes);
+      } else {
+        uint4* dst = reinterpret_cast<uint4*>(p.recs + (size_t)e0 * d.rec_bytes);
+        const uint4* src = reinterpret_cast<const uint4*>(s_rec);
+        const int n16 = ne * (d.rec_bytes >> 4);
+        if (kCoop) { for (int k = tid; k < n16; k += nt) dst[k] = src[k]; }
+        else { for (int k = (int)lane; k < n16; k += 32) dst[k] = src[k]; }
+      }
     }
+    // this step's observation block (every step of a multi-step launch, or only the last one)
+    const bool render = want_obs && (last || (kMulti && p.obs_every_step));
+    uint8_t* const obs_t = (p.obs && render) ? p.obs + ((kMulti && p.obs_every_step) ? (size_t)t * d.N * d.obs_env_bytes : 0) : nullptr;
+    uint8_t* const bits_t = (kBits && bits_out && render) ? bits_out + (p.obs_every_step ? (size_t)t * d.N * d.stage_env_bytes : 0) : nullptr;
     if (kEnc == ENC_PAD) {
-      if (kCoop && want_obs) {
+      if (kCoop && render) {
         // ---- grid interiors -> padded planes (whole CTA, flat over the tile's grid words), then the viewers
         const int W = sh.W(), wpr = W >> 2, nw = d.H * wpr, P4 = sh.pad_pitch() >> 2;
         const uint32_t cm4 = (uint32_t)d.code_mask * 0x01010101u;
@@ -1172,25 +1289,26 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
         __syncthreads();
         const int nv = ne * ns;
         const size_t vbytes = (size_t)ohw * 8;
-        uint8_t* out_tile = p.obs + (size_t)e0 * ns * vbytes;
+        uint8_t* out_tile = obs_t ? obs_t + (size_t)e0 * ns * vbytes : nullptr;
+        uint8_t* bits_tile = bits_t ? bits_t + (size_t)e0 * ns * ohw : nullptr;
         const uint32_t pad32 = (uint32_t)__cvta_generic_to_shared(s_pad);
         int q = wfirst / ns, v = wfirst - q * ns;
 #pragma unroll 1
         for (int pv = wfirst; pv < nv; pv += wstep) {
           if (!(may_skip && (s_flag[q] & F_SKIP))) {
-            uint8_t* outv = out_tile + (size_t)pv * vbytes;
+            uint8_t* outv = out_tile ? out_tile + (size_t)pv * vbytes : nullptr;
             const int shift = (int)((reinterpret_cast<uintptr_t>(outv) >> 3) & 1);
             if (shift != pc_shift) { pc = make_pad_cells<Shape<kNS, kW, kOH, kOW, kFS>, kU>(sh, shift); pc_shift = shift; }
             encode_viewer_pad<Shape<kNS, kW, kOH, kOW, kFS>, kU>(p, sh, pad32 + (uint32_t)(q * d.pad_env_bytes) + s_view[q * G + v],
-                                                                 pc, shift, v, outv, lut32);
+                                                                 pc, shift, v, outv, lut32,
+                                                                 bits_tile ? bits_tile + (size_t)pv * ohw : nullptr, lutb32);
           }
           v += wstep;
           while (v >= ns) { v -= ns; ++q; }
         }
       }
-    } else if (want_obs) {
-      CellWords cw;
-      if (kEnc == ENC_REG) cw = make_cell_words(sh, p.view_bits);
+    } else if (render) {
+      if (kEnc == ENC_REG && !cw_ready) { cw = make_cell_words(sh, p.view_bits); cw_ready = true; }
       if (kCoop) {
 #pragma unroll 1
         for (int pv = wfirst; pv < ne * ns; pv += wstep) {
@@ -1198,10 +1316,11 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
           if (s_flag[q] & F_SKIP) continue;
           const uint8_t* base = s_rec + (size_t)q * d.rec_bytes;
           const uint32_t grid32 = (uint32_t)__cvta_generic_to_shared(base);
-          uint8_t* outv = p.obs + ((size_t)(e0 + q) * ns + v) * (size_t)ohw * 8;
-          if (kEnc == ENC_REG) encode_viewer_reg(p, sh, grid32, s_view[q * G + v], cw, v, outv, lut32);
-          else if (kEnc == ENC_DIRECT) encode_viewer_direct(sh, grid32, v, outv, lut32, (uint32_t)d.code_mask);
-          else encode_viewer_fs1(p, sh, base, grid32, v, outv, lut32);
+          uint8_t* outv = obs_t ? obs_t + ((size_t)(e0 + q) * ns + v) * (size_t)ohw * 8 : nullptr;
+          uint8_t* bitsv = bits_t ? bits_t + ((size_t)(e0 + q) * ns + v) * (size_t)ohw : nullptr;
+          if (kEnc == ENC_REG) encode_viewer_reg(p, sh, grid32, s_view[q * G + v], cw, v, outv, lut32, bitsv, lutb32);
+          else if (kEnc == ENC_DIRECT) encode_viewer_direct(sh, grid32, v, outv, lut32, (uint32_t)d.code_mask, bitsv, lutb32);
+          else encode_viewer_fs1(p, sh, base, grid32, v, outv, lut32, bitsv, lutb32);
         }
       } else {
 #pragma unroll 1
@@ -1209,16 +1328,22 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
           if (s_flag[q] & F_SKIP) continue;
           const uint8_t* base = s_rec + (size_t)q * d.rec_bytes;
           const uint32_t grid32 = (uint32_t)__cvta_generic_to_shared(base);
-          uint8_t* outq = p.obs + (size_t)(e0 + q) * ns * (size_t)ohw * 8;
+          uint8_t* outq = obs_t ? obs_t + (size_t)(e0 + q) * ns * (size_t)ohw * 8 : nullptr;
+          uint8_t* bitsq = bits_t ? bits_t + (size_t)(e0 + q) * ns * (size_t)ohw : nullptr;
 #pragma unroll 1
           for (int v = 0; v < ns; ++v) {
-            uint8_t* outv = outq + (size_t)v * ohw * 8;
-            if (kEnc == ENC_REG) encode_viewer_reg(p, sh, grid32, s_view[q * G + v], cw, v, outv, lut32);
-            else if (kEnc == ENC_DIRECT) encode_viewer_direct(sh, grid32, v, outv, lut32, (uint32_t)d.code_mask);
-            else encode_viewer_fs1(p, sh, base, grid32, v, outv, lut32);
+            uint8_t* outv = outq ? outq + (size_t)v * ohw * 8 : nullptr;
+            uint8_t* bitsv = bitsq ? bitsq + (size_t)v * ohw : nullptr;
+            if (kEnc == ENC_REG) encode_viewer_reg(p, sh, grid32, s_view[q * G + v], cw, v, outv, lut32, bitsv, lutb32);
+            else if (kEnc == ENC_DIRECT) encode_viewer_direct(sh, grid32, v, outv, lut32, (uint32_t)d.code_mask, bitsv, lutb32);
+            else encode_viewer_fs1(p, sh, base, grid32, v, outv, lut32, bitsv, lutb32);
           }
         }
       }
+    }
+    if (!last) {                                // the next step's rules rewrite the records and viewer words
+      if (kCoop) __syncthreads(); else __syncwarp();
+      continue;
     }
     SNK_T(t_encoded);
     if (p.use_tma && elected) bulk_store_wait_read();
@@ -1232,13 +1357,14 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
 #endif
     return;
   }
+  }   // step loop (frame_stack > 1 runs it once and continues below)
 
   // ---- frame_stack > 1
 #pragma unroll 1
   for (int q = wfirst; q < ne; q += wstep) {
     const int qflag = s_flag[q];
     if (qflag & F_SKIP) continue;
-    encode_env_stacked<Shape<kNS, kW, kOH, kOW, kFS>, kFS>(p, sh, s_rec + (size_t)q * d.rec_bytes, e0 + q, qflag,
+    encode_env_stacked<Shape<kNS, kW, kOH, kOW, kFS>, kFS, kBits>(p, sh, s_rec + (size_t)q * d.rec_bytes, e0 + q, qflag,
                                                            s_stage, lut32, s_lut, s_hist + (size_t)q * d.hist_env_bytes);
   }
   if (kCoop) __syncthreads(); else __syncwarp();
@@ -1366,9 +1492,12 @@ bool encode_lut_dual(const Dims& d) {
 // Encode blob: LUT over cell codes, then (optionally) uint2 tab[-1 .. ohw] per window cell.
 //   fs == 1: uint2 (8 output bytes) per code, per viewer -- or {as-other, as-own} when encode_lut_dual
 //   fs  > 1: one channel-bit byte per code, per viewer
-size_t encode_blob_bytes(const Dims& d, size_t* tab_off) {
+size_t encode_blob_bytes(const Dims& d, size_t* tab_off, size_t* lutb_off) {
   const int LS = 10 * d.ns + 6;
-  const size_t lut = (size_t)round_up(d.fs == 1 ? (encode_lut_dual(d) ? 2 : d.ns) * LS * 8 : d.ns * LS, 16);
+  const int nl = encode_lut_dual(d) ? 2 : d.ns;
+  size_t lut = (size_t)round_up(d.fs == 1 ? nl * LS * 8 : d.ns * LS, 16);
+  if (lutb_off) *lutb_off = d.fs == 1 ? lut : 0;
+  if (d.fs == 1) lut += (size_t)round_up(nl * LS, 16);          // channel-bit byte per code, same indexing
   if (tab_off) *tab_off = lut;
   return (size_t)round_up((int)(lut + (encode_uses_table(d) ? (size_t)(d.ohw + 2) * 8 : 0)), 16);
 }
@@ -1376,6 +1505,9 @@ size_t encode_blob_bytes(const Dims& d, size_t* tab_off) {
 void encode_blob_fill(const Dims& d, uint8_t* out) {
   const int LS = 10 * d.ns + 6;
   uint32_t* w = reinterpret_cast<uint32_t*>(out);
+  size_t off, lutb;
+  encode_blob_bytes(d, &off, &lutb);
+  uint8_t* wb = out + lutb;                                       // fs == 1: the byte LUT
   if (encode_lut_dual(d)) {
     for (int own = 0; own < 2; ++own)
       for (int code = 0; code < LS; ++code) {
@@ -1384,6 +1516,7 @@ void encode_blob_fill(const Dims& d, uint8_t* out) {
         const uint32_t bits = cell_bits((uint32_t)code, own ? owner : owner + 1u);
         w[2 * (own * LS + code)] = spread4(bits & 15u);
         w[2 * (own * LS + code) + 1] = spread4(bits >> 4);
+        wb[own * LS + code] = (uint8_t)bits;
       }
   } else {
     for (int v = 0; v < d.ns; ++v)
@@ -1392,14 +1525,13 @@ void encode_blob_fill(const Dims& d, uint8_t* out) {
         if (d.fs == 1) {
           w[2 * (v * LS + code)] = spread4(bits & 15u);
           w[2 * (v * LS + code) + 1] = spread4(bits >> 4);
+          wb[v * LS + code] = (uint8_t)bits;
         } else {
           out[v * LS + code] = (uint8_t)bits;
         }
       }
   }
   if (!encode_uses_table(d)) return;
-  size_t off;
-  encode_blob_bytes(d, &off);
   uint32_t* t = reinterpret_cast<uint32_t*>(out + off);
   for (int c = -1; c <= d.ohw; ++c) {
     uint32_t bits = 0xFFFFFFFFu, goff = 0;            // out-of-window sentinels never validate
@@ -1435,15 +1567,18 @@ size_t tile_smem_bytes(const Dims& d, int warps, bool coop, int EPW) {
   size_t b = ntiles * (size_t)EPW * ((size_t)d.rec_bytes + (size_t)d.hist_env_bytes);
   if (d.fs > 1) b += (size_t)warps * (size_t)round_up(d.stage_env_bytes, 16);
   b += ntiles * TILE_AUX_BYTES;
-  b += encode_blob_bytes(d, nullptr) + 16;
+  b += encode_blob_bytes(d, nullptr, nullptr) + 16;
   if (encode_flavour(d, coop) == ENC_PAD) b += pad_plane_bytes(d, EPW);
   return b;
 }
 
-template <int kNS, int kW, int kOH, int kOW, int kFS, bool kCoop, int kEnc>
-static cudaError_t launch_instance(const KParams& p, int threads, size_t smem_bytes, cudaStream_t stream) {
-  static size_t configured[64] = {};          // per device: function attributes belong to the device's context
-  auto kern = snk_tile_kernel<kNS, kW, kOH, kOW, kFS, kCoop, kEnc>;
+template <int kNS, int kW, int kOH, int kOW, int kFS, bool kCoop, int kEnc, int kVar>
+static cudaError_t launch_variant(const KParams& p, int threads, size_t smem_bytes, cudaStream_t stream) {
+  // dynamic shared memory opt-in, once per (instance, device) and size: function attributes belong to the device's
+  // context.  (Process-wide on purpose: the attribute is a property of the kernel, not of a handle; concurrent first
+  // launches from two threads set the same or a larger value, which is harmless.)
+  static size_t configured[64] = {};
+  auto kern = snk_tile_kernel<kNS, kW, kOH, kOW, kFS, kCoop, kEnc, kVar>;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
@@ -1465,6 +1600,13 @@ static cudaError_t launch_instance(const KParams& p, int threads, size_t smem_by
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = p.pdl ? 1u : 0u;
   return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+template <int kNS, int kW, int kOH, int kOW, int kFS, bool kCoop, int kEnc>
+static cudaError_t launch_instance(const KParams& p, int threads, size_t smem_bytes, cudaStream_t stream) {
+  if (p.T > 1) return launch_variant<kNS, kW, kOH, kOW, kFS, kCoop, kEnc, 2>(p, threads, smem_bytes, stream);
+  if (p.bits) return launch_variant<kNS, kW, kOH, kOW, kFS, kCoop, kEnc, 1>(p, threads, smem_bytes, stream);
+  return launch_variant<kNS, kW, kOH, kOW, kFS, kCoop, kEnc, 0>(p, threads, smem_bytes, stream);
 }
 
 template <int kNS, int kW, int kOH, int kOW, int kFS, int kEnc>
@@ -1519,6 +1661,9 @@ cudaError_t launch_pack_obs(const uint8_t* obs, uint8_t* bits, size_t n_units, c
 // Profiling build only: point the kernels at a device trace buffer (n_ctas * 64 u64), or detach with nullptr.
 extern "C" int snk_prof_set_trace(unsigned long long* dev_buf) {
   return (int)cudaMemcpyToSymbol(snk_trace_buf, &dev_buf, sizeof dev_buf);
+}
+extern "C" int snk_prof_set_trace2(unsigned long long* dev_buf) {
+  return (int)cudaMemcpyToSymbol(snk_trace2_buf, &dev_buf, sizeof dev_buf);
 }
 #endif
 

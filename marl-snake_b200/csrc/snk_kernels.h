@@ -37,7 +37,8 @@ struct KParams {
   double* stats;               // [STAT_COUNT]
   // per-call I/O
   const uint8_t* actions;
-  uint8_t* obs;
+  uint8_t* obs;                // uint8 NHWC observation block, or null
+  uint8_t* bits;               // channel-bit observation block [N, ns, oh, ow, fs] (one byte per cell and frame), or null
   double* rew;
   uint8_t* done;
   uint8_t* fin;
@@ -54,6 +55,7 @@ struct KParams {
   const uint8_t* enc_blob;     // fs == 1: host-built encode tables (see encode_blob_fill)
   int32_t enc_blob_bytes;
   int32_t enc_tab_off;         // byte offset of the window-cell table inside the blob
+  int32_t enc_lutb_off;        // fs == 1: byte offset of the channel-bit byte LUT inside the blob
   int32_t use_tab;
   int32_t lut_dual;            // fs == 1: {as-other, as-own} LUT pair instead of one LUT per viewer
   int32_t coop;                // CTA-cooperative tile (small batches / large records)
@@ -65,6 +67,8 @@ struct KParams {
   uint32_t inv_grid_words;     // ENC_PAD: ceil(2^32 / (H*W/4)) and ceil(2^32 / (W/4)): exact division of word indices
   uint32_t inv_row_words;      //          below 2^16 by a multiply-high
   int32_t pdl;                 // launch with programmatic stream serialization (SNK_PDL=0 switches it off)
+  int32_t T;                   // steps per launch (snk_step_many; frame_stack 1).  actions / rewards / dones / extras are
+  int32_t obs_every_step;      //   [T, ...]; obs / bits are [T, ...] when obs_every_step, else the last step's block only
 };
 
 struct StateView {
@@ -78,7 +82,7 @@ bool encode_lut_dual(const Dims& d);
 bool encode_uses_table(const Dims& d);
 int encode_flavour(const Dims& d, bool coop);
 size_t pad_plane_bytes(const Dims& d, int tile_envs);     // ENC_PAD: padded planes of one tile
-size_t encode_blob_bytes(const Dims& d, size_t* tab_off);
+size_t encode_blob_bytes(const Dims& d, size_t* tab_off, size_t* lutb_off);
 void encode_blob_fill(const Dims& d, uint8_t* out);
 cudaError_t launch_tile_kernel(const KParams& p, int threads, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_get_state(const Dims& d, const uint8_t* recs, const StateView& sv, cudaStream_t s);

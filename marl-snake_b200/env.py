@@ -76,6 +76,8 @@ class SnakeBatch:
         check(lib.snk_obs_shape(self._h, C.byref(shape)))
         self.obs_shape = tuple(shape)                                  # (ns, oh, ow, 8*fs)
         self.obs_ch = self.obs_shape[-1]
+        self.bits_shape = self.obs_shape[:-1] + (self.obs_shape[-1] // 8,)   # channel-bit form: one byte per cell and frame
+        self._bits = None
         N, ns, dev = self.num_envs, self.num_snakes, self.device
         self._obs = torch.empty((N,) + self.obs_shape, dtype=torch.uint8, device=dev)
         self._rew = torch.empty((N, ns), dtype=torch.float64, device=dev)
@@ -108,14 +110,46 @@ class SnakeBatch:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ---- hot path ----------------------------------------------------------------------------------
-    def reset(self, mask=None, copy=False):
-        """SnakeEnv.reset for all envs (or those with mask != 0). Returns uint8 [N, ns, oh, ow, 8*fs]."""
+    def _bits_buffer(self):
+        if self._bits is None:
+            self._bits = torch.zeros((self.num_envs,) + self.bits_shape, dtype=torch.uint8, device=self.device)
+        return self._bits
+
+    def reset(self, mask=None, copy=False, bits=False):
+        """SnakeEnv.reset for all envs (or those with mask != 0). Returns uint8 [N, ns, oh, ow, 8*fs], or with
+        bits=True the channel-bit form uint8 [N, ns, oh, ow, fs] (see step_bits)."""
         if mask is not None:
             if mask.numel() != self.num_envs:
                 raise ValueError('mask must have one entry per environment')
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
-        check(lib.snk_reset(self._h, _ptr(mask), _ptr(self._obs), self._stream()))
-        return self._obs.clone() if copy else self._obs
+        with torch.cuda.device(self.device):
+            if bits:
+                out = self._bits_buffer()
+                check(lib.snk_reset_bits(self._h, _ptr(mask), _ptr(out), self._stream()))
+            else:
+                out = self._obs
+                check(lib.snk_reset(self._h, _ptr(mask), _ptr(out), self._stream()))
+        return out.clone() if copy else out
+
+    def step_bits(self, actions, copy=False, want_info=True):
+        """As step(), but the observation comes as channel bits: uint8 [N, ns, oh, ow, fs], one byte per window cell
+        and frame, bit c = channel c (np.packbits(obs.reshape(..., fs, 8), -1, bitorder='little')).  The encode
+        writes them directly -- no NHWC block, an eighth of the observation traffic; `unpack_obs` widens them."""
+        if actions.dtype != torch.uint8 or actions.device != self.device or not actions.is_contiguous() \
+                or actions.numel() != self.num_envs * self.num_snakes:
+            raise ValueError('actions must be a contiguous uint8 CUDA tensor of shape [num_envs, num_snakes]')
+        out = self._bits_buffer()
+        check(lib.snk_step_bits(self._h, _ptr(actions), _ptr(out), _ptr(self._rew), _ptr(self._done),
+                                C.byref(self._extra) if want_info else None, self._stream()))
+        info = {}
+        if want_info:
+            info = dict(finished=self._fin.view(torch.bool), rank=self._rank, episode_scores=self._ep_scores,
+                        episode_steps=self._ep_steps, episode_fruits=self._ep_fruits,
+                        episode_kills=self._ep_kills)
+        res = (out, self._rew, self._done.view(torch.bool), info)
+        if copy:
+            res = (out.clone(), res[1].clone(), res[2].clone(), {k: v.clone() for k, v in info.items()})
+        return res
 
     def step(self, actions, copy=False, want_obs=True, want_info=True):
         """actions: uint8 CUDA tensor [N, ns] in {0,1,2} (observer 'snake') or {0..4} ('human').  Returns (obs, rewards f64, dones bool, info)
@@ -137,6 +171,44 @@ class SnakeBatch:
             out = (None if out[0] is None else out[0].clone(), out[1].clone(), out[2].clone(),
                    {k: v.clone() for k, v in info.items()})
         return out
+
+    def step_many(self, actions, obs=None, rewards=None, dones=None, bits=None, finished=None):
+        """T steps in one call (snk_step_many) for open-loop action streams.  actions: uint8 CUDA [T, N, ns].
+        rewards f64 / dones uint8 [T, N, ns] are allocated when not given.  obs (uint8) / bits: a [T, N, ...] tensor
+        receives every step's block, an [N, ...] tensor only the last step's; None skips that output.  finished:
+        optional uint8 [T, N].  Returns (obs, rewards, dones, bits).  Bit-identical to T calls of step()."""
+        N, ns = self.num_envs, self.num_snakes
+        if actions.dtype != torch.uint8 or actions.device != self.device or not actions.is_contiguous() \
+                or actions.dim() != 3 or tuple(actions.shape[1:]) != (N, ns):
+            raise ValueError('actions must be a contiguous uint8 CUDA tensor of shape [T, num_envs, num_snakes]')
+        T = actions.shape[0]
+        if rewards is None:
+            rewards = torch.empty((T, N, ns), dtype=torch.float64, device=self.device)
+        if dones is None:
+            dones = torch.empty((T, N, ns), dtype=torch.uint8, device=self.device)
+        every = None
+        for name, buf, shape in (('obs', obs, self.obs_shape), ('bits', bits, self.bits_shape)):
+            if buf is None:
+                continue
+            if buf.dtype != torch.uint8 or buf.device != self.device or not buf.is_contiguous():
+                raise ValueError(f'{name} must be a contiguous uint8 CUDA tensor')
+            if tuple(buf.shape) == (T, N) + shape and (T > 1 or buf.dim() == len(shape) + 2):
+                e = True
+            elif tuple(buf.shape) == (N,) + shape:
+                e = False
+            else:
+                raise ValueError(f'{name} must have shape [T, N, ...] (every step) or [N, ...] (last step only)')
+            if every is not None and every != e:
+                raise ValueError('obs and bits must both hold every step or both hold the last step only')
+            every = e
+        extra = None
+        if finished is not None:
+            if tuple(finished.shape) != (T, N) or finished.dtype != torch.uint8 or not finished.is_contiguous():
+                raise ValueError('finished must be a contiguous uint8 CUDA tensor of shape [T, N]')
+            extra = SnkStepExtra(finished.data_ptr(), 0, 0, 0, 0, 0)
+        check(lib.snk_step_many(self._h, T, _ptr(actions), _ptr(obs), _ptr(bits), int(bool(every)), _ptr(rewards),
+                                _ptr(dones), C.byref(extra) if extra is not None else None, self._stream()))
+        return obs, rewards, dones, bits
 
     def step_host(self, actions, obs, rewards, dones):
         """Reference-shaped call on HOST buffers (pinned NumPy/torch CPU arrays): copies actions in,

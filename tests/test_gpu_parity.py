@@ -831,3 +831,128 @@ def test_gpu_state_roundtrip():
     quiet = (~ia['finished']) & (a.get_state()['grid'] == b.get_state()['grid']).all(2).all(1)
     assert int(quiet.sum()) > N // 2
     assert torch.equal(oa[quiet], ob[quiet])
+
+
+BITS_CASES = [
+    (dict(num_snakes=4, vision_range=5), 1237, {}),                                   # register encode, warp-private
+    (dict(num_snakes=4, vision_range=5), 700, {'SNK_COOP': '1'}),                     # register encode, cooperative
+    (dict(num_snakes=4), 300, {}),                                                    # full-grid (direct) encode
+    (dict(num_snakes=3, vision_range=2, frame_stack=3), 811, {}),                     # stacked
+    (dict(num_snakes=4, vision_range=5, frame_stack=4), 130, {'SNK_COOP': '0'}),      # stacked, specialised fs 4
+    (dict(height=64, width=64, num_snakes=16, snake_length=5, vision_range=7), 40, {}),          # padded-plane encode, dual LUT
+    (dict(height=64, width=64, num_snakes=16, snake_length=5, vision_range=7), 40, {'SNK_ENC_NOPAD': '1'}),   # table encode, dual LUT
+    (dict(height=24, width=24, num_snakes=9, snake_length=3, vision_range=9), 50, {}),            # window > 16: index arithmetic
+    (dict(height=32, width=32, num_snakes=8, snake_length=4, vision_range=6), 90, {'SNK_COOP': '1'}),   # padded plane, per-viewer LUT
+    (dict(num_snakes=4, vision_range=5), 400, {'SNK_ENC_LEGACY': '1'}),               # table encode, per-viewer LUT
+    (dict(height=13, width=11, num_snakes=2, vision_range=3), 77, {'SNK_FORCE_GENERIC': '1'}),
+]
+
+
+@pytest.mark.parametrize('kw,N,env', BITS_CASES)
+def test_gpu_step_bits_equals_packbits_of_obs(monkeypatch, kw, N, env):
+    """snk_step_bits / snk_reset_bits (channel bits written by the encode itself, no NHWC block) deliver exactly
+    np.packbits of what snk_step / snk_reset deliver, for every encode flavour and tile mode."""
+    from marl_snake_b200 import SnakeBatch, unpack_obs
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    ns = kw['num_snakes']
+    a, b = SnakeBatch(N, seed=19, max_episode_steps=25, **kw), SnakeBatch(N, seed=19, max_episode_steps=25, **kw)
+    o = a.reset()
+    bits = b.reset(bits=True)
+    assert bits.shape == (N,) + a.obs_shape[:-1] + (a.obs_shape[-1] // 8,)
+    want = np.packbits(o.cpu().numpy().reshape(-1, 8), axis=1, bitorder='little').reshape(bits.shape)
+    assert np.array_equal(bits.cpu().numpy(), want)
+    g = torch.Generator(device='cuda').manual_seed(2)
+    for t in range(40):
+        act = torch.randint(0, 3, (N, ns), dtype=torch.uint8, device='cuda', generator=g)
+        o, r1, d1, i1 = a.step(act)
+        bits, r2, d2, i2 = b.step_bits(act)
+        assert torch.equal(r1, r2) and torch.equal(d1, d2) and torch.equal(i1['finished'], i2['finished']), t
+        assert torch.equal(unpack_obs(bits), o), t
+    assert a.device_errors() == 0 and b.device_errors() == 0
+
+
+def test_gpu_mixed_stream_ordering():
+    """device-pointer calls on the caller's stream followed by host-buffer calls (the handle's own
+    stream) and back, with no synchronisation in between, see each other's results."""
+    from marl_snake_b200 import SnakeBatch
+    N, ns = 20000, 4
+    kw = dict(num_snakes=ns, vision_range=5, seed=3)
+    a, b = SnakeBatch(N, **kw), SnakeBatch(N, **kw)
+    h_obs = torch.empty((N,) + a.obs_shape, dtype=torch.uint8).pin_memory()
+    h_rew = torch.empty((N, ns), dtype=torch.float64).pin_memory()
+    h_done = torch.empty((N, ns), dtype=torch.uint8).pin_memory()
+    side = torch.cuda.Stream()
+    g = torch.Generator().manual_seed(1)
+    acts = [torch.randint(0, 3, (N, ns), dtype=torch.uint8, generator=g) for _ in range(12)]
+    dacts = [x.cuda() for x in acts]
+    torch.cuda.synchronize()
+    b.reset()
+    for t in range(12):
+        b.step(dacts[t])
+    want = b._obs.cpu()
+    with torch.cuda.stream(side):                 # device-pointer calls on a non-default stream, no sync after them
+        a.reset()
+        for t in range(5):
+            a.step(dacts[t])
+    a.step_host(acts[5], h_obs, h_rew, h_done)    # must wait for the five steps queued on `side`
+    with torch.cuda.stream(side):
+        for t in range(6, 11):
+            a.step(dacts[t])
+    a.step_host(acts[11], h_obs, h_rew, h_done)
+    assert torch.equal(h_obs, want)
+    assert a.stats()['env_steps'] == 12 * N        # counted on the device
+
+
+def test_gpu_calls_leave_current_device_alone():
+    """entry points restore the calling thread's current CUDA device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    from marl_snake_b200 import SnakeBatch
+    b = SnakeBatch(64, num_snakes=2, vision_range=2, device=1)
+    torch.cuda.set_device(0)
+    b.reset()
+    b.step(torch.zeros((64, 2), dtype=torch.uint8, device='cuda:1'))
+    b.stats()
+    assert torch.cuda.current_device() == 0
+
+
+@pytest.mark.parametrize('kw,N,T,env', [
+    (dict(num_snakes=4), 4096, 24, {}),                                             # BASELINE cfg2: full-grid, cooperative tiles
+    (dict(num_snakes=4, vision_range=5), 3001, 17, {'SNK_COOP': '0'}),             # warp-private tiles, ragged batch
+    (dict(num_snakes=4, vision_range=5), 1500, 9, {'SNK_COOP': '1'}),
+    (dict(height=64, width=64, num_snakes=16, snake_length=5, vision_range=7), 33, 12, {}),    # padded-plane encode
+    (dict(height=12, width=14, num_snakes=3, vision_range=2, max_episode_steps=7), 257, 30, {}),   # resets inside the launch
+    (dict(num_snakes=3, vision_range=3, frame_stack=3), 200, 8, {}),                # frame_stack > 1: T launches
+])
+def test_gpu_step_many_equals_single_steps(monkeypatch, kw, N, T, env):
+    """snk_step_many (records resident in shared memory for T steps) is bit-identical to T calls of snk_step:
+    every step's observation, rewards, dones, finished flags, the final state and the statistics."""
+    from marl_snake_b200 import SnakeBatch, unpack_obs
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    ns = kw['num_snakes']
+    a, b, c = (SnakeBatch(N, seed=41, **kw) for _ in range(3))
+    for x in (a, b, c):
+        x.reset()
+    g = torch.Generator(device='cuda').manual_seed(7)
+    for rep in range(2):
+        acts = torch.randint(0, 3, (T, N, ns), dtype=torch.uint8, device='cuda', generator=g)
+        obs_all = torch.empty((T, N) + a.obs_shape, dtype=torch.uint8, device='cuda')
+        fin_all = torch.empty((T, N), dtype=torch.uint8, device='cuda')
+        _, rew, done, _ = b.step_many(acts, obs=obs_all, finished=fin_all)
+        last_bits = torch.empty((N,) + a.bits_shape, dtype=torch.uint8, device='cuda')
+        _, rew_c, done_c, _ = c.step_many(acts, bits=last_bits)                  # last step only, as channel bits
+        for t in range(T):
+            o, r, d, info = a.step(acts[t])
+            assert torch.equal(obs_all[t], o), (rep, t)
+            assert torch.equal(rew[t], r) and torch.equal(done[t].bool(), d), (rep, t)
+            assert torch.equal(fin_all[t].bool(), info['finished']), (rep, t)
+        assert torch.equal(rew_c, rew) and torch.equal(done_c, done)
+        assert torch.equal(unpack_obs(last_bits), o)
+    sa, sb = a.get_state(max_cells=12), b.get_state(max_cells=12)
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    st_a, st_b = a.stats(), b.stats()
+    assert st_a['env_steps'] == st_b['env_steps'] == 2 * T * N and st_a['episodes'] == st_b['episodes']
+    assert a.device_errors() == 0 and b.device_errors() == 0 and c.device_errors() == 0

@@ -23,7 +23,10 @@ import marl_snake_b200 as m  # noqa: E402
 NAMES = ['prologue', 'load_wait', 'rules', 'barrier', 'encode', 'drain']
 
 for name in sys.argv[1:] or ['cfg4', 'cfg5_shard', 'cfg2']:
-    kw = dict(bc.CONFIGS[name])
+    kw = dict(bc.CONFIGS[name.split(':')[0]])
+    if ':' in name:                      # e.g. cfg5_shard:max_episode_steps=1 -> every step ends the episode
+        k, v = name.split(':')[1].split('=')
+        kw[k] = int(v)
     N = kw.pop('num_envs')
     ns = kw['num_snakes']
     b = m.SnakeBatch(N, seed=0, **kw)
@@ -34,18 +37,30 @@ for name in sys.argv[1:] or ['cfg4', 'cfg5_shard', 'cfg2']:
         b.step(pool[t % 64], want_info=False)
     max_ctas = N + 8
     trace = torch.zeros((max_ctas, 8, 8), dtype=torch.int64, device='cuda')
+    trace2 = torch.zeros((max_ctas, 8), dtype=torch.int64, device='cuda')
     m.lib.snk_prof_set_trace(C.c_void_p(trace.data_ptr()))
+    m.lib.snk_prof_set_trace2(C.c_void_p(trace2.data_ptr()))
     torch.cuda.synchronize()
     b.step(pool[7], want_info=False)
     torch.cuda.synchronize()
     m.lib.snk_prof_set_trace(C.c_void_p(0))
+    m.lib.snk_prof_set_trace2(C.c_void_p(0))
+    t2 = trace2.cpu().numpy()
+    t2 = t2[t2[:, 4] != 0]
+    if len(t2):
+        dd = np.diff(t2[:, :5].astype(np.float64), axis=1)
+        reset = {k: round(float(dd[:, i].mean())) for i, k in enumerate(['walls', 'spawn', 'snakes', 'fruits'])}
+        reset.update(resets=len(t2), attempts_mean=float(t2[:, 5].mean()), attempts_max=int(t2[:, 5].max()),
+                     total_p50_p99=[int(np.percentile(t2[:, 4] - t2[:, 0], q)) for q in (50, 99)])
+    else:
+        reset = None
     tr = trace.cpu().numpy()
     used = tr[:, 0, 0] != 0
     tr = tr[used]
     nct = tr.shape[0]
     nwarps = int((tr[0, :, 0] != 0).sum())
     t0 = tr[:, :nwarps, 0].min()
-    rec = {'config': name, 'ctas': nct, 'warps_per_cta': nwarps}
+    rec = {'config': name, 'ctas': nct, 'warps_per_cta': nwarps, 'reset_ns': reset}
     for role, sl in (('rule_warp', slice(0, 1)), ('other_warps', slice(1, nwarps))):
         if sl.start >= nwarps:
             continue
