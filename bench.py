@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 ENV_KW = dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5, frame_stack=1)
 WORKLOAD = 'cfg5: 20x20, 4 snakes, len 3, vision_range 5, frame_stack 1, auto-reset, random actions'
 BURN_IN = 256          # steps before warm-up so the alive / reset mix is stationary (mean episode ~68)
+CLOCK_RAMP_S = 1.0     # extra untimed stepping after the CPU legs so the GPU is back at its load clocks
 
 
 def parse():
@@ -128,7 +129,7 @@ class ClockSampler(threading.Thread):
            'hw_power_brake_slowdown': 0x80}
     NOTE = {'sw_power_cap': 0x4}
 
-    def __init__(self, index, period=0.02):
+    def __init__(self, index, period=0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], 0
@@ -206,6 +207,15 @@ def ours(args):
         batch.step(pool[step_no % NPOOL], want_info=False)
         step_no += 1
     torch.cuda.synchronize()
+    # The CPU baseline legs above leave the GPU idle for ~20 s and it drops to its idle clocks; a quarter of a second
+    # of burn-in does not always bring the memory clock back (seen: 1.02 ms per step instead of 0.87).  Keep stepping
+    # for about a second of wall time before the timed region (these are extra warm-up steps, not timed).
+    t_ramp = time.perf_counter()
+    while time.perf_counter() - t_ramp < CLOCK_RAMP_S:
+        for _ in range(64):
+            batch.step(pool[step_no % NPOOL], want_info=False)
+            step_no += 1
+        torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -271,7 +281,38 @@ def ours(args):
     t0 = time.perf_counter()
     for t in range(K2):
         batch.step_host_bits(h_act[t % 4], h_bits, h_rew, h_done)
+    torch.cuda.synchronize()
     e2e_bits_s = time.perf_counter() - t0
+    if world > 1:
+        ts = torch.tensor([e2e_bits_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        e2e_bits_s = float(ts.item())
+    # the two ends of the packed transport on their own: (a) the device leg -- the step kernel emitting channel bits
+    # (no NHWC block), CUDA events; (b) the host leg -- widening a block of channel bits that is already in host
+    # memory into the caller's uint8 NHWC buffer with this rank's threads, i.e. the host-DRAM ceiling of the call
+    d_act = [pool[t] for t in range(4)]
+    for t in range(3):
+        batch.step_bits(d_act[t % 4], want_info=False)
+    evb0, evb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evb0.record()
+    for t in range(20):
+        batch.step_bits(d_act[t % 4], want_info=False)
+    evb1.record()
+    torch.cuda.synchronize()
+    dev_leg_ms = evb0.elapsed_time(evb1) / 20
+    import ctypes as C
+    from marl_snake_b200 import lib as snk_lib
+    n_units = h_bits.numel()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for t in range(3):
+        snk_lib.snk_widen_bits_host(C.c_void_p(h_bits.data_ptr()), C.c_void_p(h_obs.data_ptr()), n_units, host_threads)
+    widen_s = (time.perf_counter() - t0) / 3
+    if world > 1:
+        ts = torch.tensor([widen_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        widen_s = float(ts.item())
     del h_bits
     e2e_s = time_host_steps('packed')
     # the delivered block against the device state of the same step: the window centre of a live snake is
@@ -304,6 +345,10 @@ def ours(args):
             configs['cfg3'] = bc.measure('cfg3', steps=300)
             configs['cfg4'] = bc.measure('cfg4', steps=300)
             configs['cfg5_shard_131072'] = bc.measure('cfg5_shard', steps=400)
+            try:                              # env + reference DQN + packed replay ring, all on the device
+                configs['n1_rollout_cfg3'] = bc.measure_rollout()
+            except Exception as exc:          # noqa: BLE001  (cuDNN / memory trouble must not cost the headline line)
+                configs['n1_rollout_cfg3'] = {'unavailable': repr(exc)[:300]}
         else:
             total = 1 << 20
             kw = dict(bc.CONFIGS['cfg5_full'])
@@ -349,7 +394,7 @@ def ours(args):
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
             'higher_is_better': True, 'scaling': 'strong' if args.envs_total else 'weak', 'vs_baseline': None,
             'dtype': 'u8', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'envs_per_gpu': N, 'global_envs': N * world, 'burn_in_steps': BURN_IN,
+            'config': {'workload': WORKLOAD, 'envs_per_gpu': N, 'global_envs': N * world, 'burn_in_steps': BURN_IN, 'clock_ramp_s': CLOCK_RAMP_S,
                        'l2': 'no flush: per-step working set (records %.0f MB read + written, obs %.0f MB written) '
                              'exceeds the 126 MB L2' % (N * rec_bytes / 1e6, N * obs_bytes / 1e6),
                        'parallelism': f'env-shard x{world}', 'rng': 'philox seed 0',
@@ -371,13 +416,22 @@ def ours(args):
                     'h2d_bytes_per_step': N * ns, 'd2h_bytes_per_step': N * obs_bytes // 8 + N * ns * 9,
                     'host_obs_bytes_delivered_per_step': N * obs_bytes,
                     'steps': K2, 'ms_per_step': 1e3 * e2e_s / K2,
-                    'api': 'snk_step_host (C ABI, pinned host buffers), packed transport: device packs 8 channel '
-                           'bytes -> 1, %d MB over PCIe in chunks, %d host threads per rank widen to uint8 NHWC'
+                    'api': 'snk_step_host (C ABI, pinned host buffers), packed transport: the step kernel emits channel '
+                           'bits, %d MB over PCIe in chunks, %d host threads per rank widen to uint8 NHWC'
                            % (obs_bytes * N // 8 // 1000000, host_threads),
                     'host_threads_per_rank': host_threads,
-                    'bits_to_host_rank0': {'agent_steps_per_sec_per_gpu': N * ns * K2 / e2e_bits_s, 'ms_per_step': 1e3 * e2e_bits_s / K2,
-                                           'note': 'snk_step_host_bits: channel bits delivered as they are (not the '
-                                                   'reference format; context only)'},
+                    'bits_format': {'value': N * world * ns * K2 / e2e_bits_s, 'ms_per_step': 1e3 * e2e_bits_s / K2,
+                                    'd2h_bytes_per_step': N * obs_bytes // 8 + N * ns * 9,
+                                    'note': 'snk_step_host_bits: the same call delivering channel bits as they are (one '
+                                            'byte per cell, bit c = channel c; np.packbits of the reference format) -- no '
+                                            'host widening, PCIe-bound'},
+                    'device_leg_ms': dev_leg_ms,
+                    'device_leg_note': 'step kernel emitting channel bits (snk_step_bits), CUDA events, per step',
+                    'host_widen_only_ms': 1e3 * widen_s,
+                    'host_dram_ceiling': {'value': N * world * ns / widen_s, 'unit': 'agent-steps/s',
+                                          'note': 'all ranks widening a resident bit block into their uint8 NHWC host '
+                                                  'buffers at once, no GPU, no PCIe: what the box\'s host memory system '
+                                                  'allows for the reference format (%d threads per rank)' % host_threads},
                     'raw_transport': {'value': N * world * ns * K2 / e2e_raw_s, 'ms_per_step': 1e3 * e2e_raw_s / K2,
                                       'd2h_bytes_per_step': N * obs_bytes + N * ns * 9}},
             'gpu_launches': args.steps * world,       # timed region of `value`: one snk_tile_kernel per step per rank

@@ -119,6 +119,12 @@ typedef struct snk_state_view {
 /* SnakeEnv.__init__ for N environments (snake_env.py:58-129) + make_snake batching (wrappers.py:203-223).
  * Builds the spawn-candidate table (core/grid_util.py:73-115) and allocates all device state. */
 int snk_create(const snk_config* cfg, snk_env** out);
+/* The same with a custom wall layout instead of make_grid's walled box: walls_host is uint8 [height * width], row-major,
+ * nonzero = WALL -- the array make_grid_from_txt(map_path, {'#': 1, '.': 0}) returns (core/grid_util.py:23-33; maps
+ * under assets/).  Every reset starts from this layout, the spawn poses are enumerated on it (dfs_sweep_empty takes
+ * any grid, :73-99) and fruits land on its empty cells.  The outer ring must be wall (SNK_E_INVALID otherwise): the
+ * reference would let a snake walk out of the array there.  The map is copied; walls_host may be freed after the call. */
+int snk_create_map(const snk_config* cfg, const uint8_t* walls_host, snk_env** out);
 /* SnakeEnv.close (snake_env.py:298) */
 int snk_destroy(snk_env* env);
 const char* snk_last_error(void);
@@ -249,6 +255,10 @@ int snk_stats(snk_env* env, double* out_host /* [SNK_STAT_COUNT] */, int clear);
 int64_t snk_spawn_count(int32_t height, int32_t width, int32_t snake_length);
 /* Writes them, in the reference's order, as flat cell indices [count, snake_length], head first. */
 int snk_spawn_cells(int32_t height, int32_t width, int32_t snake_length, int32_t* out, int64_t count);
+/* The same two on a custom wall layout (walls_host as for snk_create_map; the border is not checked here). */
+int64_t snk_spawn_count_map(int32_t height, int32_t width, int32_t snake_length, const uint8_t* walls_host);
+int snk_spawn_cells_map(int32_t height, int32_t width, int32_t snake_length, const uint8_t* walls_host, int32_t* out,
+                        int64_t count);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,7 @@ class SnkStateView(C.Structure):
 # name -> (restype, argtypes); tests check that the library exports every one of these.
 PROTOTYPES = {
     'snk_create': (C.c_int, [C.POINTER(SnkConfig), C.POINTER(C.c_void_p)]),
+    'snk_create_map': (C.c_int, [C.POINTER(SnkConfig), C.c_void_p, C.POINTER(C.c_void_p)]),
     'snk_destroy': (C.c_int, [C.c_void_p]),
     'snk_last_error': (C.c_char_p, []),
     'snk_abi_version': (C.c_int, []),
@@ -83,6 +84,8 @@ PROTOTYPES = {
     'snk_stats': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     'snk_spawn_count': (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     'snk_spawn_cells': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
+    'snk_spawn_count_map': (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    'snk_spawn_cells_map': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]),
 }
 
 

@@ -58,6 +58,7 @@ struct snk_env {
   uint8_t* recs = nullptr;
   uint8_t* hist = nullptr;
   uint64_t* spawn = nullptr;
+  uint32_t* wall_map = nullptr;                  // custom wall layout (snk_create_map): H*W cell codes, padded to words
   int32_t* replay = nullptr;
   int64_t* replay_off = nullptr;
   uint32_t* err = nullptr;
@@ -97,7 +98,7 @@ static KParams base_params(const snk_env* h) {
   KParams p;
   memset(&p, 0, sizeof p);
   p.d = h->d;
-  p.recs = h->recs; p.hist = h->hist; p.spawn = h->spawn;
+  p.recs = h->recs; p.hist = h->hist; p.spawn = h->spawn; p.wall_map = h->wall_map;
   p.replay = h->replay; p.replay_off = h->replay_off;
   p.err = h->err; p.stats = h->stats;
   p.E = h->tile_envs;
@@ -119,7 +120,14 @@ static KParams base_params(const snk_env* h) {
   return p;
 }
 
-extern "C" int snk_create(const snk_config* c, snk_env** out) {
+static int create_impl(const snk_config* c, const uint8_t* walls_host, snk_env** out);
+extern "C" int snk_create(const snk_config* c, snk_env** out) { return create_impl(c, nullptr, out); }
+extern "C" int snk_create_map(const snk_config* c, const uint8_t* walls_host, snk_env** out) {
+  if (!walls_host) return fail(SNK_E_INVALID, "null wall map");
+  return create_impl(c, walls_host, out);
+}
+
+static int create_impl(const snk_config* c, const uint8_t* walls_host, snk_env** out) {
   if (!c || !out) return fail(SNK_E_INVALID, "null argument");
   if (c->abi_version != SNK_ABI_VERSION) return fail(SNK_E_INVALID, "abi_version %d != %d", c->abi_version, SNK_ABI_VERSION);
   if (c->num_envs < 1) return fail(SNK_E_INVALID, "num_envs must be >= 1");
@@ -148,8 +156,24 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
   finalize_layout(d);
   h->device = c->device;
 
+  // custom wall layout (make_grid_from_txt, core/grid_util.py:23-33): normalised to cell codes, one word-padded plane.
+  // The outer ring must be wall -- it is what keeps a head inside the array (the reference would index out of it).
+  std::vector<uint8_t> walls;
+  if (walls_host) {
+    walls.assign(((size_t)d.HW + 3) / 4 * 4, 0);
+    for (int i = 0; i < d.HW; ++i) walls[i] = walls_host[i] ? (uint8_t)WALL : (uint8_t)EMPTY;
+    for (int i = 0; i < d.HW; ++i) {
+      const int r = i / d.W, cc = i % d.W;
+      if ((r == 0 || r == d.H - 1 || cc == 0 || cc == d.W - 1) && !walls[i]) {
+        delete h;
+        return fail(SNK_E_INVALID, "wall map: border cell (%d, %d) is not a wall", r, cc);
+      }
+    }
+  }
+  const uint8_t* wm = walls_host ? walls.data() : nullptr;
+
   // spawn table (host) -- core/grid_util.py:73-115
-  const int64_t n_cand = spawn_enumerate(d.H, d.W, d.K, nullptr, nullptr, 0, SPAWN_TABLE_LIMIT);
+  const int64_t n_cand = spawn_enumerate(d.H, d.W, d.K, nullptr, nullptr, 0, SPAWN_TABLE_LIMIT, wm);
   if (n_cand < d.ns) { delete h; return fail(SNK_E_INVALID, "only %lld spawn poses for %d snakes", (long long)n_cand, c->num_snakes); }
   if (n_cand > SPAWN_TABLE_LIMIT) {
     delete h;
@@ -157,7 +181,7 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
                 "them on every reset; here the table would not fit)", (long long)SPAWN_TABLE_LIMIT, c->height, c->width, c->snake_length);
   }
   std::vector<uint64_t> table((size_t)n_cand);
-  spawn_enumerate(d.H, d.W, d.K, table.data(), nullptr, n_cand);
+  spawn_enumerate(d.H, d.W, d.K, table.data(), nullptr, n_cand, 0, wm);
   d.n_cand = (uint32_t)n_cand;
 
   // tile shape: a tile is 32/G environments (G = num_snakes rounded up to a power of two).  Large
@@ -227,6 +251,10 @@ extern "C" int snk_create(const snk_config* c, snk_env** out) {
   CUH(cudaMalloc(&h->stats, STAT_COUNT * sizeof(double)));
   CUH(cudaMalloc(&h->replay_off, ((size_t)d.N + 1) * sizeof(int64_t)));
   CUH(cudaMemcpy(h->spawn, table.data(), table.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  if (wm) {
+    CUH(cudaMalloc(&h->wall_map, walls.size()));
+    CUH(cudaMemcpy(h->wall_map, walls.data(), walls.size(), cudaMemcpyHostToDevice));
+  }
   {
     size_t tab_off = 0, lutb_off = 0;
     const size_t nb = encode_blob_bytes(d, &tab_off, &lutb_off);
@@ -267,7 +295,7 @@ extern "C" int snk_destroy(snk_env* h) {
   if (!h) return SNK_OK;
   DeviceGuard guard(h->device);
   cudaFree(h->recs); cudaFree(h->hist); cudaFree(h->spawn); cudaFree(h->replay); cudaFree(h->replay_off);
-  cudaFree(h->err); cudaFree(h->stats); cudaFree(h->enc_blob);
+  cudaFree(h->err); cudaFree(h->stats); cudaFree(h->enc_blob); cudaFree(h->wall_map);
   cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_rew); cudaFree(h->h_done);
   cudaFree(h->h_fin); cudaFree(h->h_rank); cudaFree(h->h_scores); cudaFree(h->h_counts);
   cudaFree(h->small_dev);
@@ -809,5 +837,18 @@ extern "C" int64_t snk_spawn_count(int32_t H, int32_t W, int32_t K) {
 extern "C" int snk_spawn_cells(int32_t H, int32_t W, int32_t K, int32_t* out, int64_t count) {
   if (!out || H < 3 || W < 3 || K < 1 || K > MAX_SNAKE_LENGTH) return fail(SNK_E_INVALID, "bad argument");
   spawn_enumerate(H, W, K, nullptr, out, count);
+  return SNK_OK;
+}
+
+extern "C" int64_t snk_spawn_count_map(int32_t H, int32_t W, int32_t K, const uint8_t* walls_host) {
+  if (!walls_host || H < 3 || W < 3 || K < 1 || K > MAX_SNAKE_LENGTH) { fail(SNK_E_INVALID, "bad spawn table shape"); return -1; }
+  const int64_t n = spawn_enumerate(H, W, K, nullptr, nullptr, 0, SPAWN_TABLE_LIMIT, walls_host);
+  if (n > SPAWN_TABLE_LIMIT) { fail(SNK_E_INVALID, "more than %lld spawn poses", (long long)SPAWN_TABLE_LIMIT); return -1; }
+  return n;
+}
+
+extern "C" int snk_spawn_cells_map(int32_t H, int32_t W, int32_t K, const uint8_t* walls_host, int32_t* out, int64_t count) {
+  if (!out || !walls_host || H < 3 || W < 3 || K < 1 || K > MAX_SNAKE_LENGTH) return fail(SNK_E_INVALID, "bad argument");
+  spawn_enumerate(H, W, K, nullptr, out, count, 0, walls_host);
   return SNK_OK;
 }

@@ -219,8 +219,15 @@ __device__ __noinline__ void reset_env_warp(const KParams& p, uint8_t* rec_base,
   const uint32_t n_cand = d.n_cand, inv_row_words = p.inv_row_words;
   const uint64_t* const spawn = p.spawn;
   SNK_R(0);
-  // make_grid: walled empty box (core/grid_util.py:14-20), one grid row at a time so no division is needed
-  if ((W & 3) == 0 && W >= 8) {          // flat over the grid's 32-bit words; row = word / (W/4) by a multiply-high
+  // make_grid: walled empty box (core/grid_util.py:14-20), one grid row at a time so no division is needed --
+  // or the handle's custom wall layout (snk_create_map), copied word by word from its L2-resident plane
+  if (p.wall_map) {
+    const uint32_t* const wm = p.wall_map;
+    const int HW = d.HW, nfull = HW >> 2;
+    uint32_t* gw = reinterpret_cast<uint32_t*>(r.grid);
+    for (int j = (int)lane; j < nfull; j += 32) gw[j] = __ldg(wm + j);
+    if ((int)lane < (HW & 3)) r.grid[4 * nfull + lane] = reinterpret_cast<const uint8_t*>(wm)[4 * nfull + lane];
+  } else if ((W & 3) == 0 && W >= 8) {          // flat over the grid's 32-bit words; row = word / (W/4) by a multiply-high
     uint32_t* gw = reinterpret_cast<uint32_t*>(r.grid);
     const int wpr = W >> 2, nw = H * wpr;
     for (int j = (int)lane; j < nw; j += 32) {

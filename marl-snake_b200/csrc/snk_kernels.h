@@ -31,6 +31,7 @@ struct KParams {
   uint8_t* recs;               // [N] records, rec_bytes each
   uint8_t* hist;               // [N, ns, fs, ohw_p] channel-bit frames (fs > 1 only)
   const uint64_t* spawn;       // [n_cand] packed spawn poses
+  const uint32_t* wall_map;    // custom wall layout: the H*W cell codes (EMPTY / WALL) a reset starts from, as words; null = walled box
   const int32_t* replay;       // replay draws, all envs back to back
   const int64_t* replay_off;   // [N+1]
   uint32_t* err;               // sticky error bits
@@ -92,7 +93,9 @@ cudaError_t launch_init_records(const Dims& d, uint8_t* recs, cudaStream_t s);
 cudaError_t launch_pack_obs(const uint8_t* obs, uint8_t* bits, size_t n_units, cudaStream_t s);
 
 // host-side spawn table (snk_spawn.cpp)
-int64_t spawn_enumerate(int H, int W, int K, uint64_t* packed_out, int32_t* cells_out, int64_t cap, int64_t limit = 0);
+// walls: [H*W] bytes, nonzero = wall, or null for make_grid's walled box
+int64_t spawn_enumerate(int H, int W, int K, uint64_t* packed_out, int32_t* cells_out, int64_t cap, int64_t limit = 0,
+                        const uint8_t* walls = nullptr);
 constexpr int64_t SPAWN_TABLE_LIMIT = (int64_t)64 << 20;     // poses (512 MB of table); more is refused
 
 }  // namespace snk

@@ -21,8 +21,12 @@ struct Walker {
   std::vector<int> links;      // direction codes (0 UP 1 RIGHT 2 DOWN 3 LEFT) between consecutive cells
   uint64_t* packed; int32_t* cells; int64_t cap; int64_t n = 0;
   int64_t limit = 0;           // > 0: stop enumerating once this many poses were seen (the count explodes with length)
+  const uint8_t* walls = nullptr;   // [H*W], nonzero = not empty; null = the walled box
 
-  bool free_cell(int r, int c) const { return r > 0 && r < H - 1 && c > 0 && c < W - 1; }
+  bool free_cell(int r, int c) const {
+    if (walls) return r >= 0 && r < H && c >= 0 && c < W && walls[r * W + c] == 0;
+    return r > 0 && r < H - 1 && c > 0 && c < W - 1;
+  }
   bool on_path(int cell) const {
     for (int p : path) if (p == cell) return true;
     return false;
@@ -68,9 +72,11 @@ struct Walker {
 
 // Returns the number of poses; fills up to `cap` entries of whichever outputs are non-null.  With limit > 0
 // the walk stops soon after `limit` poses (the return value is then > limit, not the true count).
-int64_t spawn_enumerate(int H, int W, int K, uint64_t* packed_out, int32_t* cells_out, int64_t cap, int64_t limit) {
+int64_t spawn_enumerate(int H, int W, int K, uint64_t* packed_out, int32_t* cells_out, int64_t cap, int64_t limit,
+                        const uint8_t* walls) {
   Walker w{H, W, K, {}, {}, packed_out, cells_out, cap};
   w.limit = limit;
+  w.walls = walls;
   for (int r = 0; r < H; ++r)
     for (int c = 0; c < W; ++c)
       if (w.free_cell(r, c)) { w.path.assign(1, r * W + c); w.links.clear(); w.grow(); }

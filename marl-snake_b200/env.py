@@ -33,8 +33,13 @@ class SnakeBatch:
     def __init__(self, num_envs, height=20, width=20, num_snakes=4, snake_length=3, vision_range=None,
                  frame_stack=1, observer='snake', reward_dict=None, num_fruits=None,
                  max_episode_steps=DEFAULT_MAX_EPISODE_STEPS, device=0, seed=0, rng='philox',
-                 auto_reset=True, env_id_offset=0, done_mode='all', **ignored):
+                 auto_reset=True, env_id_offset=0, done_mode='all', wall_map=None, **ignored):
         reward_dict = DEFAULT_REWARD_DICT if reward_dict is None else reward_dict
+        self.wall_map = None
+        if wall_map is not None:                      # custom wall layout: the map decides the grid shape
+            from .grid_util import as_wall_plane
+            self.wall_map = as_wall_plane(wall_map)
+            height, width = self.wall_map.shape
         if reward_dict.keys() != DEFAULT_REWARD_DICT.keys():                      # snake_env.py:77-80
             raise KeyError(f'reward dict keys must correspond to {DEFAULT_REWARD_DICT.keys()}')
         if observer not in ('snake', 'human'):
@@ -71,7 +76,10 @@ class SnakeBatch:
                         reward_time=float(reward_dict['time']))
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
-            check(lib.snk_create(C.byref(cfg), C.byref(self._h)))
+            if self.wall_map is None:
+                check(lib.snk_create(C.byref(cfg), C.byref(self._h)))
+            else:
+                check(lib.snk_create_map(C.byref(cfg), self.wall_map.ctypes.data_as(C.c_void_p), C.byref(self._h)))
         shape = (C.c_int32 * 4)()
         check(lib.snk_obs_shape(self._h, C.byref(shape)))
         self.obs_shape = tuple(shape)                                  # (ns, oh, ow, 8*fs)
@@ -93,6 +101,9 @@ class SnakeBatch:
                                    self._ep_kills.data_ptr())
         self.observation_space = Box(0, 1, (N,) + self.obs_shape, np.uint8)
         self.action_space = Discrete(len(self.action_dict))
+        self._has_obs = False            # self._obs holds the current observation of every env
+        self._rollout_alive = None       # rollout.collect's (alive, episode age) cache; dropped by any other mutation
+        self._rollout_age = None
 
     # ---- lifecycle ---------------------------------------------------------------------------------
     def close(self):
@@ -129,6 +140,8 @@ class SnakeBatch:
             else:
                 out = self._obs
                 check(lib.snk_reset(self._h, _ptr(mask), _ptr(out), self._stream()))
+                self._has_obs = True
+        self._rollout_alive = None
         return out.clone() if copy else out
 
     def step_bits(self, actions, copy=False, want_info=True):
@@ -161,6 +174,7 @@ class SnakeBatch:
             raise ValueError('actions must be a contiguous uint8 CUDA tensor of shape [num_envs, num_snakes]')
         check(lib.snk_step(self._h, _ptr(actions), _ptr(self._obs if want_obs else None), _ptr(self._rew),
                            _ptr(self._done), C.byref(self._extra) if want_info else None, self._stream()))
+        self._has_obs, self._rollout_alive = self._has_obs and want_obs, None
         info = {}
         if want_info:
             info = dict(finished=self._fin.view(torch.bool), rank=self._rank, episode_scores=self._ep_scores,
@@ -289,6 +303,7 @@ class SnakeBatch:
         view = SnkStateView(**{k: v.data_ptr() for k, v in keep.items()}, max_cells=cells.shape[-1])
         check(lib.snk_set_state(self._h, C.byref(view), _ptr(self._obs), self._stream()))
         torch.cuda.current_stream(self.device).synchronize()      # `keep` must outlive the kernels
+        self._has_obs, self._rollout_alive = True, None
         return self._obs
 
     def save_checkpoint(self):
@@ -302,6 +317,7 @@ class SnakeBatch:
     def load_checkpoint(self, blob):
         blob = np.ascontiguousarray(blob, dtype=np.uint8)
         check(lib.snk_checkpoint_load(self._h, blob.ctypes.data_as(C.c_void_p), blob.size))
+        self._has_obs, self._rollout_alive = False, None
 
     def set_replay(self, draws_per_env):
         """draws_per_env: sequence of N int arrays -- recorded draw outputs in consumption order."""
@@ -382,7 +398,8 @@ class SnakeEnv:
                                  num_fruits=kwargs.pop('num_fruits', None),
                                  max_episode_steps=kwargs.pop('max_episode_steps', DEFAULT_MAX_EPISODE_STEPS),
                                  device=kwargs.pop('device', 0), seed=kwargs.pop('seed', 0),
-                                 rng=kwargs.pop('rng', 'philox'), auto_reset=False, done_mode=self._done_mode)
+                                 rng=kwargs.pop('rng', 'philox'), auto_reset=False, done_mode=self._done_mode,
+                                 wall_map=kwargs.pop('wall_map', None))
         b = self._batch
         self.reward_dict = b.reward_dict
         self.max_episode_steps = b.max_episode_steps
@@ -414,6 +431,9 @@ class SnakeEnv:
         return self
 
     def seed(self, seed=42):
+        """As in the reference (snake_env.py:161-163) this has no effect on the game: there it only creates
+        `self.np_random`, which nothing reads -- spawns and fruits draw from the module-global NumPy generator.  The
+        stream of this environment is fixed by the constructor's `seed=` (Philox key) or by `set_replay`."""
         return [seed]
 
     def close(self):

@@ -98,27 +98,56 @@ class GraphedSteps:
 
 
 @torch.no_grad()
-def collect(batch, q_net, steps, buffer=None, epsilon=0.1, generator=None):
-    """Run `steps` env steps of `batch` (SnakeBatch, auto-reset on) with a shared per-snake Q network
-    (input: float NCHW built from the uint8 NHWC observation, as train_dqn.py:168 does per snake).
-    Only snakes that were alive before the step produce transitions (train_dqn.py:290-298).
-    Returns the number of transitions written; nothing is copied to the host."""
+def collect(batch, q_net, steps, buffer=None, epsilon=0.1, generator=None, early_death=None, max_steps=None,
+            to_input=None):
+    """Run `steps` env steps of `batch` (SnakeBatch, auto-reset on) with a shared per-snake Q network -- the
+    inner loop of the reference trainer (train_dqn.py:277-308) for every environment of the batch at once:
+
+      * one batched forward over all [N*ns] observations (float NCHW built from the uint8 NHWC observation, as
+        train_dqn.py:118,168 does per snake; `to_input` overrides the conversion), epsilon-greedy on the device;
+        snakes that are already dead send action 0 (:281-282);
+      * a transition (obs_i, action_i, r_i, next_obs_i, next_done_i) is pushed for every snake that was alive
+        BEFORE the step and for no other (:290-298), in (env, snake) order; with `early_death=(threshold, penalty)`
+        a snake that dies while its episode is younger than `threshold` steps gets `penalty` added (:293-295);
+      * an episode that ended was reset inside the step (the vector worker's rule, wrappers.py:141-143): its
+        `next_obs` is the first observation of the next episode and all of its snakes are alive again;
+      * with `max_steps`, an episode that reaches that many steps is cut and restarted without a done flag, as the
+        trainer's `step < MAX_STEPS_PER_EPISODE` loop condition does (:275, 270) -- one masked reset launch per step.
+
+    The alive mask and the per-env episode age are read back from the device state (`snk_get_state`) when the batch
+    was touched by anything else since the last call, so consecutive calls continue the same rollout.
+    Returns the number of transitions written (a device scalar); nothing is copied to the host."""
     N, ns = batch.num_envs, batch.num_snakes
-    obs = batch._obs if getattr(batch, '_has_obs', False) else batch.reset()
-    batch._has_obs = True
-    alive = torch.ones((N, ns), dtype=torch.bool, device=obs.device)
+    if not batch._has_obs:
+        batch.reset()
+    if batch._rollout_alive is None:            # first call, or the batch was reset / stepped / restored in between
+        st = batch.get_state()
+        batch._rollout_alive, batch._rollout_age = st['alive'].bool(), st['episode_length']
+    obs = batch._obs
+    alive, age = batch._rollout_alive, batch._rollout_age
     written = torch.zeros((), dtype=torch.int64, device=obs.device)
     for _ in range(steps):
         flat = obs.reshape(N * ns, *obs.shape[2:])
-        q = q_net(flat.permute(0, 3, 1, 2).float())
-        actions = epsilon_greedy(q, epsilon, generator).reshape(N, ns)
+        q = q_net(to_input(flat) if to_input is not None else flat.permute(0, 3, 1, 2).float())
+        actions = epsilon_greedy(q.float(), epsilon, generator).reshape(N, ns)
+        actions = torch.where(alive, actions, torch.zeros_like(actions))
         prev = flat.clone() if buffer is not None else None
         obs, rew, done, info = batch.step(actions)
         if buffer is not None:
             m = alive.reshape(-1)
+            if early_death is not None:
+                threshold, penalty = early_death
+                rew = rew + (done & (age < threshold)[:, None]).to(rew.dtype) * penalty
             buffer.push(prev[m], actions.reshape(-1)[m], rew.reshape(-1)[m],
                         obs.reshape(N * ns, *obs.shape[2:])[m], done.reshape(-1)[m])
             written += m.sum()
-        # a finished env was reset inside the step: all of its snakes are alive again
-        alive = torch.where(info['finished'][:, None], torch.ones_like(done), ~done)
+        # a finished env was reset inside the step: all of its snakes are alive again, its age is 0
+        fin = info['finished'].bool()
+        alive = torch.where(fin[:, None], torch.ones_like(done), ~done)
+        age = torch.where(fin, torch.zeros_like(age), age + 1)
+        if max_steps is not None:
+            cut = age >= max_steps
+            obs = batch.reset(mask=cut)
+            alive, age = alive | cut[:, None], torch.where(cut, torch.zeros_like(age), age)
+    batch._rollout_alive, batch._rollout_age = alive, age
     return written

@@ -51,9 +51,16 @@ DEFAULT_MAX_EPISODE_STEPS = 1e4
 
 
 # --------------------------------------------------------------------------- spawn table
+def spawn_candidates(height, width, length, wall_map=None):
+    """All spawn poses in the reference's enumeration order; wall_map (H x W, nonzero = wall) replaces make_grid's
+    walled box by a custom layout (dfs_sweep_empty takes whatever grid reset() built, snake_env.py:578)."""
+    key = None if wall_map is None else np.ascontiguousarray(np.asarray(wall_map) != 0, dtype=np.uint8).tobytes()
+    return _spawn_candidates(height, width, length, key)
+
+
 @lru_cache(maxsize=None)
-def spawn_candidates(height, width, length):
-    """All spawn poses in the reference's enumeration order.
+def _spawn_candidates(height, width, length, wall_bytes):
+    """
 
     Returns an int array [n_cand, length, 2] of (row, col), head first.
     Follows core/grid_util.py:73-115 on the empty walled grid of make_grid
@@ -62,14 +69,17 @@ def spawn_candidates(height, width, length):
     the cell about to be appended (_head_blocked, :102-110).
     """
     free = np.zeros((height, width), dtype=bool)
-    free[1:height - 1, 1:width - 1] = True
+    if wall_bytes is None:
+        free[1:height - 1, 1:width - 1] = True
+    else:
+        free = np.frombuffer(wall_bytes, dtype=np.uint8).reshape(height, width) == 0
     out = []
 
     def head_boxed(path, extra):
         r0, c0 = path[0]
         for dr, dc in DFS_SHIFTS:
             n = (r0 + dr, c0 + dc)
-            if free[n] and n not in path and n != extra:
+            if 0 <= n[0] < height and 0 <= n[1] < width and free[n] and n not in path and n != extra:
                 return False
         return True
 
@@ -174,7 +184,13 @@ class OracleSnakeEnv:
     """One Snake-v1 environment; same ctor kwargs / reset / step contract as SnakeEnv."""
 
     def __init__(self, height=20, width=20, num_snakes=4, snake_length=3, vision_range=None,
-                 frame_stack=1, observer='snake', draws=None, **kwargs):
+                 frame_stack=1, observer='snake', draws=None, wall_map=None, **kwargs):
+        # wall_map: H x W, nonzero = wall -- reset() starts from this layout instead of make_grid's walled box
+        # (the array make_grid_from_txt returns for an assets/*.txt map, core/grid_util.py:23-33)
+        self.wall_map = None
+        if wall_map is not None:
+            self.wall_map = (np.asarray(wall_map) != 0).astype(np.int64)
+            height, width = self.wall_map.shape
         reward_dict = kwargs.pop('reward_dict', DEFAULT_REWARD)
         if reward_dict.keys() != REWARD_KEYS:                              # snake_env.py:76-80
             raise KeyError(f'reward dict keys must correspond to {REWARD_KEYS}')
@@ -198,10 +214,13 @@ class OracleSnakeEnv:
     def reset(self):
         H, W = self.grid_shape
         ns = self.num_snakes
-        grid = np.zeros((H, W), dtype=np.int64)
-        grid[0, :] = grid[H - 1, :] = WALL
-        grid[:, 0] = grid[:, W - 1] = WALL
-        cands = spawn_candidates(H, W, self.snake_length)
+        if self.wall_map is None:
+            grid = np.zeros((H, W), dtype=np.int64)
+            grid[0, :] = grid[H - 1, :] = WALL
+            grid[:, 0] = grid[:, W - 1] = WALL
+        else:
+            grid = self.wall_map * WALL
+        cands = spawn_candidates(H, W, self.snake_length, self.wall_map)
 
         def no_overlap(pick):                                              # snake_env.py:568-574
             cells = cands[list(pick)].reshape(-1, 2)

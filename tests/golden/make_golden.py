@@ -27,7 +27,42 @@ sys.path.insert(0, '/root/reference/marlenv')
 import gym  # noqa: E402  (the stub)
 import marlenv  # noqa: E402,F401  (registers Snake-v1)
 from marlenv.core.snake import Snake, Direction  # noqa: E402
-from marlenv.core.grid_util import dfs_sweep_empty, make_grid  # noqa: E402
+from marlenv.core.grid_util import dfs_sweep_empty, make_grid, make_grid_from_txt  # noqa: E402
+import marlenv.envs.snake_env as ref_snake_env  # noqa: E402
+
+ASSETS = '/root/reference/marlenv/marlenv/assets'
+
+
+def load_asset_map(name, mapper=None):
+    """A wall layout from the reference's assets, read by the reference's own loader (core/grid_util.py:23-33).
+    The loader splits on '\\n' and so chokes on a final newline; such files are read from a scratch copy with the
+    final newline removed (the map itself is unchanged)."""
+    import tempfile
+    mapper = mapper or {'#': 1, '.': 0}
+    text = open(os.path.join(ASSETS, name)).read().rstrip('\n')
+    with tempfile.NamedTemporaryFile('w', suffix='.txt', delete=False) as fp:
+        fp.write(text)
+    try:
+        return make_grid_from_txt(fp.name, mapper)
+    finally:
+        os.unlink(fp.name)
+
+
+class CustomWalls:
+    """The reference's reset() always builds make_grid's walled box (snake_env.py:133) and has no parameter for a
+    map; while installed, the `make_grid` name that reset() calls returns the custom layout instead.  Nothing else of
+    the reference is touched: dfs_sweep_empty, random_empty_coords and the step rules work on whatever grid they get."""
+
+    def __init__(self, wall_grid):
+        self.grid = None if wall_grid is None else np.asarray(wall_grid)
+
+    def __enter__(self):
+        self._orig = ref_snake_env.make_grid
+        if self.grid is not None:
+            ref_snake_env.make_grid = lambda *a, **k: self.grid.copy()
+
+    def __exit__(self, *exc):
+        ref_snake_env.make_grid = self._orig
 
 DIRS = [Direction.UP, Direction.RIGHT, Direction.DOWN, Direction.LEFT]
 
@@ -104,16 +139,17 @@ def rollout(name, seed, num_envs, steps, env_id='Snake-v1', **kw):
         return
     ns = kw.get('num_snakes', 4)
     n_actions = 5 if kw.get('observer') == 'human' else 3
-    rec = dict(kind='rollout', kwargs=repr(kw), seed=seed)
+    walls = kw.get('wall_map')                      # nested list (H x W, 1 = wall) from load_asset_map, or None
+    ref_kw = {k: v for k, v in kw.items() if k != 'wall_map'}
     per_env = []
     act_rng = np.random.RandomState(seed + 777)
     for e in range(num_envs):
-        env = gym.make(env_id, **kw)
+        env = gym.make(env_id, **ref_kw)
         H, W = env.grid_shape
         np.random.seed(seed + e)
         tap = DrawTap()
         draws, draws_end = [], []
-        with tap:
+        with tap, CustomWalls(walls):
             obs0 = env.reset()
             draws.extend(tap.drain(ns))
             draws_end.append(len(draws))
@@ -386,6 +422,16 @@ def spawn_tables():
         cands = np.asarray(dfs_sweep_empty(grid, k), dtype=np.int16)
         out[f'c_{H}_{W}_{k}'] = cands
         print(f'spawn table {H}x{W} k={k}: {len(cands)} candidates')
+    # spawn tables on the reference's asset maps (custom wall layouts)
+    for name, k, mapper in [('12x12.txt', 4, None), ('20x20_cross.txt', 3, None),
+                            ('40x40_ml2.txt', 3, {'#': 1, '.': 0, 'O': 1})]:
+        grid = load_asset_map(name, mapper)
+        cands = np.asarray(dfs_sweep_empty(grid, k), dtype=np.int16)
+        tag = name.split('.')[0]
+        out[f'map_{tag}__walls'] = (grid != 0).astype(np.uint8)
+        out[f'map_{tag}__k'] = np.array(k)
+        out[f'map_{tag}__cands'] = cands
+        print(f'spawn table on {name} k={k}: {len(cands)} candidates')
     # turn table, probed from the reference's trigonometric _next_direction
     env = gym.make('Snake-v1')
     out['turn'] = np.array([[DIRS.index(env._next_direction(d, a)) for a in range(3)] for d in DIRS],
@@ -417,5 +463,14 @@ if __name__ == '__main__':
             vision_range=2, num_fruits=6, reward_dict=cfg4_rew)
     rollout('roll_cfg4', 1100, 1, 90, height=64, width=64, num_snakes=16, snake_length=5, vision_range=7,
             max_episode_steps=45, reward_dict=cfg4_rew)            # BASELINE cfg4 shape; the cap forces one auto-reset
+    cross = load_asset_map('20x20_cross.txt')
+    rollout('roll_map_cross', 1200, 4, 150, height=20, width=20, num_snakes=4, snake_length=3, vision_range=5,
+            wall_map=cross.tolist())                                   # assets/20x20_cross.txt, the cfg1 shape otherwise
+    small = load_asset_map('12x12.txt')
+    rollout('roll_map_12', 1300, 4, 120, height=12, width=12, num_snakes=3, snake_length=4, frame_stack=2,
+            num_fruits=5, reward_dict=cfg4_rew, wall_map=small.tolist())   # assets/12x12.txt, full-grid observation
+    ml2 = load_asset_map('40x40_ml2.txt', {'#': 1, '.': 0, 'O': 1})
+    rollout('roll_map_ml2', 1400, 2, 100, height=40, width=40, num_snakes=8, snake_length=3, vision_range=4,
+            max_episode_steps=35, num_fruits=10, reward_dict=cfg4_rew, wall_map=ml2.tolist())   # direction-plane record (> 6 snakes)
     rollout('roll_human', 1000, 4, 150, height=12, width=12, num_snakes=3, snake_length=3,
             vision_range=4, observer='human', reward_dict=cfg4_rew)

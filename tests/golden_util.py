@@ -6,7 +6,7 @@ import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 ROLLOUTS = ['roll_cfg1', 'roll_full', 'roll_fs4', 'roll_big', 'roll_single', 'roll_cap',
-            'roll_rect', 'roll_crowd', 'roll_coop', 'roll_human', 'roll_cfg4']
+            'roll_rect', 'roll_crowd', 'roll_coop', 'roll_human', 'roll_cfg4', 'roll_map_cross', 'roll_map_12', 'roll_map_ml2']
 
 
 def unpack_obs(packed):
@@ -55,3 +55,10 @@ def load_spawn_tables():
     z = np.load(os.path.join(GOLDEN_DIR, 'spawn_tables.npz'))
     tables = {tuple(int(x) for x in k.split('_')[1:]): z[k] for k in z.files if k.startswith('c_')}
     return tables, z['turn']
+
+
+def load_map_spawn_tables():
+    """Spawn tables the reference enumerates on its asset maps: name -> (walls uint8 [H, W], snake_length, cands)."""
+    z = np.load(os.path.join(GOLDEN_DIR, 'spawn_tables.npz'))
+    names = sorted({k[len('map_'):].split('__')[0] for k in z.files if k.startswith('map_')})
+    return {n: (z[f'map_{n}__walls'], int(z[f'map_{n}__k']), z[f'map_{n}__cands']) for n in names}

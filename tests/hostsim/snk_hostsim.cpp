@@ -11,7 +11,7 @@
 #include "../../include/snk.h"
 #include "../../marl-snake_b200/csrc/snk_core.cuh"
 
-namespace snk { int64_t spawn_enumerate(int H, int W, int K, uint64_t* packed_out, int32_t* cells_out, int64_t cap, int64_t limit = 0); }
+namespace snk { int64_t spawn_enumerate(int H, int W, int K, uint64_t* packed_out, int32_t* cells_out, int64_t cap, int64_t limit = 0, const uint8_t* walls = nullptr); }
 using namespace snk;
 
 struct HostSim {
@@ -20,6 +20,7 @@ struct HostSim {
   std::vector<uint64_t> spawn;
   std::vector<int32_t> replay;
   std::vector<int64_t> replay_off;
+  std::vector<uint8_t> walls;     // custom wall layout (cell codes EMPTY / WALL), empty = walled box
   uint32_t err = 0;
 };
 
@@ -45,7 +46,7 @@ static void place_fruits(HostSim& h, Rec& r, uint32_t env, int k, int purpose) {
 static void reset_env(HostSim& h, Rec& r, uint32_t env) {
   const Dims& d = h.d;
   const int ns = d.ns, K = d.K, W = d.W;
-  for (int c = 0; c < d.HW; ++c) r.grid[c] = wall_or_empty(c, d.H, d.W);
+  for (int c = 0; c < d.HW; ++c) r.grid[c] = h.walls.empty() ? wall_or_empty(c, d.H, d.W) : h.walls[c];
   std::vector<uint64_t> entry(ns);
   if (d.rng_mode == RNG_REPLAY) {
     for (int i = 0; i < ns; ++i) {
@@ -138,8 +139,12 @@ static void encode_env(HostSim& h, Rec& r, uint32_t env, bool init, uint8_t* obs
 
 extern "C" {
 
-void* hs_create(const snk_config* c) {
+void* hs_create_map(const snk_config* c, const uint8_t* walls);
+void* hs_create(const snk_config* c) { return hs_create_map(c, nullptr); }
+void* hs_create_map(const snk_config* c, const uint8_t* walls) {
   HostSim* h = new HostSim();
+  if (walls) { h->walls.resize((size_t)c->height * c->width); for (size_t i = 0; i < h->walls.size(); ++i) h->walls[i] = walls[i] ? WALL : EMPTY; }
+  const uint8_t* wm = walls ? h->walls.data() : nullptr;
   Dims& d = h->d;
   memset(&d, 0, sizeof d);
   d.N = c->num_envs; d.H = c->height; d.W = c->width; d.ns = c->num_snakes; d.K = c->snake_length;
@@ -152,9 +157,9 @@ void* hs_create(const snk_config* c) {
   d.r_fruit = c->reward_fruit; d.r_kill = c->reward_kill; d.r_lose = c->reward_lose;
   d.r_win = c->reward_win; d.r_time = c->reward_time; d.max_steps = c->max_episode_steps;
   finalize_layout(d);
-  const int64_t n = spawn_enumerate(d.H, d.W, d.K, nullptr, nullptr, 0);
+  const int64_t n = spawn_enumerate(d.H, d.W, d.K, nullptr, nullptr, 0, 0, wm);
   h->spawn.resize((size_t)n);
-  spawn_enumerate(d.H, d.W, d.K, h->spawn.data(), nullptr, n);
+  spawn_enumerate(d.H, d.W, d.K, h->spawn.data(), nullptr, n, 0, wm);
   d.n_cand = (uint32_t)n;
   h->recs.assign((size_t)d.N * d.rec_bytes, 0);
   h->hist.assign((size_t)d.N * d.hist_env_bytes + 16, 0);

@@ -24,8 +24,11 @@ def make_config(num_envs, kw, rng_mode=1, auto_reset=1, seed=0, env_id_offset=0,
     from marl_snake_b200._lib import SnkConfig
     rd = kw.get('reward_dict', {'fruit': 10.0, 'kill': 0.0, 'lose': -0.5, 'win': 0.0, 'time': -0.001})
     ns = kw.get('num_snakes', 4)
-    return SnkConfig(abi_version=1, device=0, num_envs=num_envs, height=kw.get('height', 20),
-                     width=kw.get('width', 20), num_snakes=ns, snake_length=kw.get('snake_length', 3),
+    H, W = kw.get('height', 20), kw.get('width', 20)
+    if kw.get('wall_map') is not None:
+        H, W = np.asarray(kw['wall_map']).shape
+    return SnkConfig(abi_version=1, device=0, num_envs=num_envs, height=H,
+                     width=W, num_snakes=ns, snake_length=kw.get('snake_length', 3),
                      vision_range=int(kw.get('vision_range') or 0), frame_stack=kw.get('frame_stack', 1),
                      num_fruits=kw.get('num_fruits', int(round(ns * 0.8))), auto_reset=auto_reset,
                      done_mode=done_mode, rng_mode=rng_mode, observer=int(kw.get('observer', 'snake') == 'human'),
@@ -39,8 +42,13 @@ class HostSim:
     def __init__(self, num_envs, kw, **cfg_kw):
         self.lib = C.CDLL(build())
         self.lib.hs_create.restype = C.c_void_p
+        self.lib.hs_create_map.restype = C.c_void_p
         self.cfg = make_config(num_envs, kw, **cfg_kw)
-        self.h = C.c_void_p(self.lib.hs_create(C.byref(self.cfg)))
+        if kw.get('wall_map') is not None:
+            walls = np.ascontiguousarray(np.asarray(kw['wall_map']) != 0, dtype=np.uint8)
+            self.h = C.c_void_p(self.lib.hs_create_map(C.byref(self.cfg), walls.ctypes.data_as(C.c_void_p)))
+        else:
+            self.h = C.c_void_p(self.lib.hs_create(C.byref(self.cfg)))
         self.N, self.ns = num_envs, self.cfg.num_snakes
         H, W = self.cfg.height, self.cfg.width
         self.HW = H * W

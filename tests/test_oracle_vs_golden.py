@@ -6,7 +6,7 @@ import sys
 import numpy as np
 import pytest
 
-from golden_util import ROLLOUTS, Rollout, load_scenarios, load_spawn_tables, unpack_obs
+from golden_util import ROLLOUTS, Rollout, load_map_spawn_tables, load_scenarios, load_spawn_tables, unpack_obs
 from oracle.snake_oracle import (CoopOracleSnakeEnv, OracleSnakeEnv, ReplayDraws, RecordingDraws, TURN,
                                  spawn_candidates, competition_rank)
 
@@ -18,6 +18,15 @@ def test_spawn_tables_and_turn_table():
         assert mine.shape == ref.shape, (H, W, k)
         assert np.array_equal(mine, ref), (H, W, k)
     assert np.array_equal(np.asarray(TURN), turn)
+
+
+def test_spawn_tables_on_the_reference_asset_maps():
+    """dfs_sweep_empty on custom wall layouts (assets/12x12.txt, 20x20_cross.txt, 40x40_ml2.txt)."""
+    maps = load_map_spawn_tables()
+    assert set(maps) == {'12x12', '20x20_cross', '40x40_ml2'}
+    for name, (walls, k, ref) in maps.items():
+        mine = spawn_candidates(walls.shape[0], walls.shape[1], k, walls)
+        assert mine.shape == ref.shape and np.array_equal(mine, ref), name
 
 
 @pytest.mark.parametrize('name', ROLLOUTS)
@@ -96,6 +105,11 @@ def _compare_with_live_reference(kw, env_id='Snake-v1', steps=400, n_actions=3, 
         import marlenv  # noqa: F401
         ns = kw['num_snakes']
         acts = np.random.RandomState(5).randint(0, n_actions, size=(steps, ns))
+        walls = kw.get('wall_map')
+        ref_kw = {k: v for k, v in kw.items() if k != 'wall_map'}
+        if walls is not None:     # the reference has no map parameter: its reset() gets the layout from `make_grid`
+            import marlenv.envs.snake_env as ref_snake_env
+            ref_snake_env.make_grid = lambda *a, **k: np.asarray(walls).copy()
 
         def run(make):
             np.random.seed(42)
@@ -111,7 +125,7 @@ def _compare_with_live_reference(kw, env_id='Snake-v1', steps=400, n_actions=3, 
             return out
 
         cls = CoopOracleSnakeEnv if env_id == 'SnakeCoop-v1' else OracleSnakeEnv
-        ref = run(lambda: gym.make(env_id, **kw))
+        ref = run(lambda: gym.make(env_id, **ref_kw))
         mine = run(lambda: cls(**kw))
         assert np.array_equal(ref[0], mine[0])
         for t, (a, b) in enumerate(zip(ref[1:], mine[1:])):
@@ -135,6 +149,18 @@ def _compare_with_live_reference(kw, env_id='Snake-v1', steps=400, n_actions=3, 
 ])
 def test_same_seed_as_live_reference(kw):
     _compare_with_live_reference(kw)
+
+
+@pytest.mark.needs_reference
+@pytest.mark.parametrize('name,kw', [
+    ('12x12', dict(num_snakes=3, snake_length=4, vision_range=3, frame_stack=2)),
+    ('20x20_cross', dict(num_snakes=4, snake_length=3, vision_range=5)),
+])
+def test_custom_wall_map_same_seed_as_live_reference(name, kw):
+    """the oracle on a custom wall layout against the reference whose reset() is handed the same layout."""
+    walls, _, _ = load_map_spawn_tables()[name]
+    _compare_with_live_reference(dict(height=walls.shape[0], width=walls.shape[1], wall_map=walls.astype(np.int64), **kw),
+                                 steps=250)
 
 
 @pytest.mark.needs_reference

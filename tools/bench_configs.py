@@ -172,11 +172,73 @@ def measure_single_env(steps=3000):
                 agent_steps_per_sec=steps * ns / sec)
 
 
+def measure_rollout(num_envs=65536, steps=12, warmup=3, chunk=32768, capacity=1 << 20):
+    """SURVEY N1 at the cfg3 shape: env step + the reference trainer's Q network (3 convs 32/64/64 + dense
+    h*w*64-256-128-3, train_dqn.py:103-131; torch/cuDNN in bf16 -- a library model, not this repo's product) on every
+    snake's observation + epsilon-greedy + packed replay ring, all on the device (`rollout.collect`).  Reports the
+    whole loop and its three legs alone."""
+    import torch.nn as nn
+    from marl_snake_b200 import DeviceReplayBuffer, collect
+    kw = dict(CONFIGS['cfg3'])
+    kw.pop('num_envs')
+    N, ns = num_envs, kw['num_snakes']
+    dev = torch.device('cuda', torch.cuda.current_device())
+    b = SnakeBatch(N, seed=0, device=dev.index, **kw)
+    _, oh, ow, ch = b.obs_shape
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Conv2d(ch, 32, 3, padding=1), nn.ReLU(), nn.Conv2d(32, 64, 3, padding=1), nn.ReLU(),
+                        nn.Conv2d(64, 64, 3, padding=1), nn.ReLU(), nn.Flatten(), nn.Linear(oh * ow * 64, 256), nn.ReLU(),
+                        nn.Linear(256, 128), nn.ReLU(), nn.Linear(128, 3)).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+
+    def to_input(flat):                 # uint8 NHWC -> bf16, already channels_last in memory
+        return flat.permute(0, 3, 1, 2).to(torch.bfloat16)
+
+    def q_net(x):
+        return torch.cat([net(c) for c in x.split(chunk)])
+    buf = DeviceReplayBuffer(capacity, b.obs_shape[1:], dev, pack=b)
+    g = torch.Generator(device=dev).manual_seed(2)
+    collect(b, q_net, warmup, buf, epsilon=0.3, generator=g, to_input=to_input)
+    torch.cuda.synchronize(dev)
+
+    def timed(fn, reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+    t0 = time.perf_counter()
+    ms_loop = timed(lambda: collect(b, q_net, 1, buf, epsilon=0.3, generator=g, to_input=to_input), steps)
+    wall = time.perf_counter() - t0
+    act = torch.randint(0, 3, (N, ns), dtype=torch.uint8, device=dev, generator=g)
+    ms_env = timed(lambda: b.step(act), 50)
+    flat = b._obs.reshape(N * ns, oh, ow, ch)
+    with torch.no_grad():
+        ms_net = timed(lambda: q_net(to_input(flat)), 5)
+    done = torch.zeros(N * ns, dtype=torch.bool, device=dev)
+    rew = torch.zeros(N * ns, dtype=torch.float64, device=dev)
+    ms_push = timed(lambda: buf.push(flat, act.reshape(-1), rew, flat, done), 5)
+    macs = oh * ow * (ch * 32 * 9 + 32 * 64 * 9 + 64 * 64 * 9) + oh * ow * 64 * 256 + 256 * 128 + 128 * 3
+    out = dict(config='n1_rollout', mode='rollout.collect: env step + reference DQN (bf16, cuDNN) + eps-greedy + packed replay ring',
+               shape='cfg3 (20x20, 4 snakes, vision 5, frame_stack 4)', num_envs=N, steps=steps, ms_per_step=ms_loop,
+               agent_steps_per_sec=N * ns / (ms_loop * 1e-3), wall_agent_steps_per_sec=N * ns * steps / wall,
+               legs_ms=dict(env_step=ms_env, q_network_forward=ms_net, replay_push_packed=ms_push),
+               q_network=dict(mflop_per_observation=2 * macs / 1e6, tflops_achieved=2 * macs * N * ns / (ms_net * 1e-3) / 1e12),
+               replay=dict(capacity=capacity, stored='channel bits (snk_pack_obs), 1/8 of NHWC', size=buf.size),
+               device_errors=b.device_errors())
+    b.close()
+    return out
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or ['cfg2', 'cfg3', 'cfg4', 'cfg5_shard', 'cfg5_full']
     for name in which:
         if name == 'cfg1':
             print(json.dumps(measure_single_env()), flush=True)
+            continue
+        if name == 'n1_rollout':
+            print(json.dumps(measure_rollout()), flush=True)
             continue
         print(json.dumps(measure(name)), flush=True)
         if name == 'cfg2' and 'BENCH_STEPS' not in os.environ:
