@@ -512,14 +512,17 @@ class SnakeEnv:
         return fp
 
     def render_fancy(self, cell_size=40, save_path=None):
-        """RGB frame of the current state (host-side visualisation; see render.py)."""
+        """RGB frame of the current state, pixel for pixel the reference's drawing (snake_env.py:165-263; see
+        render.py).  The state -- grid, per-snake body cells, headings -- is exported from the device."""
         from .render import render_fancy
-        st = self._batch.get_state()
-        img = render_fancy(st['grid'][0].cpu().numpy(), st['head'][0].cpu().numpy(), st['dir'][0].cpu().numpy(),
-                           cell_size)
+        longest = max(int(self._batch.get_state()['length'].max()), 2)
+        st = self._batch.get_state(max_cells=longest)
+        img = render_fancy(st['grid'][0].cpu().numpy(), st['cells'][0].cpu().numpy(), st['alive'][0].cpu().numpy(),
+                           st['dir'][0].cpu().numpy(), cell_size)
         if save_path:
             from PIL import Image
             Image.fromarray(img).save(save_path)
+            print(f"Saved fancy render to {save_path}")
         return img
 
 

@@ -108,6 +108,12 @@ class RenderGUI(_Wrapper):
     def close(self):
         if self.video_writer is not None:
             self.video_writer.release()
+        if self.window_initialized:
+            try:
+                import cv2
+                cv2.destroyWindow(self.window_name)
+            except Exception:                      # noqa: BLE001  (headless box / cv2 gone)
+                pass
         super().close()
 
 

@@ -439,7 +439,46 @@ def spawn_tables():
     np.savez_compressed(os.path.join(HERE, 'spawn_tables.npz'), **out)
 
 
+def render_frames():
+    """Pixels of the reference's three drawings -- render_fancy (snake_env.py:165-263), render('rgb_array')
+    (grid_util.py:164-174) and one render('gif') frame (:177-185) -- together with the state they were drawn from."""
+    if ONLY and 'render' not in ONLY:
+        return
+    out, names = {}, []
+    cases = [('r20', dict(height=20, width=20, num_snakes=4, snake_length=5), 30, [0, 7, 19, 33]),
+             ('r12', dict(height=12, width=16, num_snakes=6, snake_length=3, num_fruits=5), 40, [0, 9, 15]),
+             ('r9', dict(height=9, width=9, num_snakes=2, snake_length=3), 17, [0, 4])]
+    for tag, kw, cs, when in cases:
+        env = gym.make('Snake-v1', **kw)
+        np.random.seed(31 + cs)
+        env.reset()
+        rng = np.random.RandomState(cs)
+        H, W = env.grid_shape
+        for t in range(max(when) + 1):
+            if t in when:
+                name = f'{tag}_t{t}'
+                names.append(name)
+                alive, dirs, lens, cells = snake_cells(env, W)
+                out[f'{name}__grid'] = env.grid.astype(np.uint8).copy()
+                out[f'{name}__alive'], out[f'{name}__dir'], out[f'{name}__len'] = alive, dirs, lens
+                out[f'{name}__cells'] = cells
+                out[f'{name}__cell_size'] = np.array(cs)
+                out[f'{name}__fancy'] = np.asarray(env.render_fancy(cell_size=cs))
+                out[f'{name}__rgb'] = np.asarray(env.render('rgb_array'))
+                env.frame_buffer = []
+                env.render('gif')
+                out[f'{name}__gif'] = np.asarray(env.frame_buffer[0])
+            _, _, done, _ = env.step([int(a) for a in rng.randint(0, 3, size=env.num_snakes)])
+            if all(done):
+                env.reset()
+    out['names'] = np.array(names)
+    path = os.path.join(HERE, 'render.npz')
+    np.savez_compressed(path, **out)
+    print(f'render: {len(names)} frames, {os.path.getsize(path) / 1024:.1f} KiB')
+
+
 if __name__ == '__main__':
+    render_frames()
     custom = {'fruit': 1.0, 'kill': 2.0, 'lose': 3.0, 'win': 4.0, 'time': 0.1}
     cfg4_rew = {'fruit': 10.0, 'kill': 1.0, 'lose': -1.0, 'win': 0.1, 'time': -0.001}
     spawn_tables()
