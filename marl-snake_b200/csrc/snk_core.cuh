@@ -38,14 +38,16 @@ constexpr uint32_t SPAWN_ATTEMPT_CAP = 1u << 16;
 // Per-step flag bits kept in the scratch area while a step is resolved.
 enum : uint8_t { ST_WAS_ALIVE = 1, ST_DIED = 2, ST_ATE = 4, ST_WON = 8, ST_EATER = 16 };
 
-struct EnvHdr {            // per-environment scalars inside the record (32 bytes)
-  int32_t alive_counter;   // SnakeEnv.alive_snakes: signed, drifts below the true count (:334-345)
+struct EnvHdr {            // per-environment scalars inside the record (16 bytes)
+  int16_t alive_counter;   // SnakeEnv.alive_snakes: signed, drifts below the true count (:334-345).  A snake dies once
+                           // per episode and is counted at most twice, so the value stays within [-ns, ns]
+  uint8_t hpos;            // frame-stack ring: slot that holds the oldest frame / gets the next one (< fs <= 64)
+  uint8_t pad;
   uint32_t episode_length; // SnakeEnv.episode_length (:392)
   uint32_t event;          // Philox event counter: +1 per step and per explicit reset
   uint32_t cursor;         // replay-stream cursor
-  uint32_t hpos;           // frame-stack ring: slot that holds the oldest frame / gets the next one
-  uint32_t pad[3];
 };
+static_assert(sizeof(EnvHdr) == 16, "EnvHdr is part of the record layout");
 
 // Everything a kernel needs to know about the configuration; passed by value.
 struct Dims {
@@ -57,6 +59,8 @@ struct Dims {
   int32_t dig;                    // 1: body directions live in bits 6..7 of the grid byte (cell codes < 64, i.e.
                                   //    at most 6 snakes) and the record has no direction plane
   int32_t code_mask;              // 63 when dig, else 255: grid byte -> cell code
+  int32_t stat16;                 // 1: the per-snake episode counters (steps, fruits, kills) are uint16 -- they are
+                                  //    bounded by the step cap, which then is <= 65535 (the default is 1e4) -- else uint32
   // record layout (bytes from record start; grid is at 0)
   int32_t off_dirp, off_snk, off_hdr, off_stats, rec_bytes;
   int32_t hist_env_bytes;         // ns*fs*ohw_p, 0 when fs == 1
@@ -83,7 +87,8 @@ inline void finalize_layout(Dims& d) {
   d.off_snk = d.off_dirp + (d.dig ? 0 : round_up((d.HW + 3) / 4, 16));
   d.off_hdr = d.off_snk + round_up(8 * d.ns, 16);
   d.off_stats = d.off_hdr + (int)sizeof(EnvHdr);
-  d.rec_bytes = d.off_stats + round_up(20 * d.ns, 16);
+  d.stat16 = d.max_steps <= 65535.0 ? 1 : 0;
+  d.rec_bytes = d.off_stats + round_up((8 + (d.stat16 ? 6 : 12)) * d.ns, 16);
   d.hist_env_bytes = d.fs > 1 ? d.ns * d.fs * d.ohw_p : 0;
   d.stage_env_bytes = d.ns * d.ohw * d.fs;
   d.obs_env_bytes = d.stage_env_bytes * 8;
@@ -105,10 +110,9 @@ struct Rec {
   uint8_t* alive;
   EnvHdr* hdr;
   double* score;
-  uint32_t* steps;
-  uint32_t* fruits;
-  uint32_t* kills;
+  uint8_t* cnt;              // episode counters [3][ns] (steps, fruits, kills), uint16 or uint32 (Dims::stat16)
 };
+enum : int { CNT_STEPS = 0, CNT_FRUITS = 1, CNT_KILLS = 2 };
 
 SNK_HD Rec rec_view(uint8_t* base, const Dims& d) {
   Rec r;
@@ -121,10 +125,26 @@ SNK_HD Rec rec_view(uint8_t* base, const Dims& d) {
   r.alive = r.dir + d.ns;
   r.hdr = (EnvHdr*)(base + d.off_hdr);
   r.score = (double*)(base + d.off_stats);
-  r.steps = (uint32_t*)(r.score + d.ns);
-  r.fruits = r.steps + d.ns;
-  r.kills = r.fruits + d.ns;
+  r.cnt = (uint8_t*)(r.score + d.ns);
   return r;
+}
+SNK_HD uint32_t cnt_get(const Dims& d, const Rec& r, int field, int i) {
+  const int k = field * d.ns + i;
+  return d.stat16 ? (uint32_t)((const uint16_t*)r.cnt)[k] : ((const uint32_t*)r.cnt)[k];
+}
+SNK_HD void cnt_set(const Dims& d, const Rec& r, int field, int i, uint32_t v) {
+  const int k = field * d.ns + i;
+  if (d.stat16) ((uint16_t*)r.cnt)[k] = (uint16_t)v; else ((uint32_t*)r.cnt)[k] = v;
+}
+// one snake's step: +1 step, +ate fruits, +kl kills
+SNK_HD void cnt_step(const Dims& d, const Rec& r, int i, uint32_t ate, uint32_t kl) {
+  cnt_set(d, r, CNT_STEPS, i, cnt_get(d, r, CNT_STEPS, i) + 1u);
+  if (ate) cnt_set(d, r, CNT_FRUITS, i, cnt_get(d, r, CNT_FRUITS, i) + ate);
+  if (kl) cnt_set(d, r, CNT_KILLS, i, cnt_get(d, r, CNT_KILLS, i) + kl);
+}
+SNK_HD void stats_zero(const Dims& d, const Rec& r, int i) {
+  r.score[i] = 0.0;
+  cnt_set(d, r, CNT_STEPS, i, 0u); cnt_set(d, r, CNT_FRUITS, i, 0u); cnt_set(d, r, CNT_KILLS, i, 0u);
 }
 
 // body-direction plane: 2 bits per cell = the direction the owning snake left the cell in
@@ -351,7 +371,7 @@ SNK_HD StepResult env_step_logic(const Dims& d, uint8_t* rec_base, uint8_t* scr,
 #else
         { volatile double s = r.score[i] + rw; r.score[i] = s; }
 #endif
-        r.steps[i] += 1; r.fruits[i] += ate ? 1u : 0u; r.kills[i] += kl[i];
+        cnt_step(d, r, i, ate ? 1u : 0u, (uint32_t)kl[i]);
         ++n_alive;
       } else {                                             // died this step: erase own cells :560-566
         int c = r.tail[i];

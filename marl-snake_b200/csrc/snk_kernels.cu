@@ -22,6 +22,8 @@
 #include <stdint.h>
 
 #include "snk_core.cuh"
+#include <atomic>
+
 #include "snk_kernels.h"
 
 namespace snk {
@@ -310,13 +312,13 @@ __device__ __noinline__ void reset_env_warp(const KParams& p, uint8_t* rec_base,
     r.len[s] = (uint16_t)K;
     r.dir[s] = (uint8_t)((spawn_link(entry, 1) + 2) & 3);   // coords[0] - coords[1]  core/snake.py:58-61
     r.alive[s] = 1;
-    r.score[s] = 0.0; r.steps[s] = 0; r.fruits[s] = 0; r.kills[s] = 0;
+    stats_zero(d, r, s);
   };
   if (me) write_snake((int)lane);
   __syncwarp();
   SNK_R(3);
   place_fruits_warp(p, rec_base, env_local, d.nfruits, DRAW_RESET_FRUIT);
-  if (lane == 0) { r.hdr->alive_counter = ns; r.hdr->episode_length = 0; }
+  if (lane == 0) { r.hdr->alive_counter = (int16_t)ns; r.hdr->episode_length = 0; }
   __syncwarp();
   SNK_R(4);
 }
@@ -536,7 +538,7 @@ __device__ __forceinline__ GroupOut step_group(const KParams& p, const SH& sh, R
       r.head[i] = (uint16_t)tgt;
       r.grid[tgt] = (uint8_t)(HEAD + tag);
       r.score[i] = __dadd_rn(r.score[i], rw);          // statistics gate on this step's dones  :385-389
-      r.steps[i] += 1; r.fruits[i] += eater ? 1u : 0u; r.kills[i] += (uint32_t)kl;
+      cnt_step(d, r, i, eater ? 1u : 0u, (uint32_t)kl);
     } else if (was_alive) {
       r.alive[i] = 0; r.len[i] = 0; r.dir[i] = (uint8_t)dirv;
     }
@@ -550,7 +552,7 @@ __device__ __forceinline__ GroupOut step_group(const KParams& p, const SH& sh, R
   const bool fin = d.done_mode == 0 ? (capped || n_done == ns) : (capped || n_done > 0);
   __syncwarp();
   if (active) {
-    if (i == 0) { r.hdr->episode_length = ep_len; r.hdr->alive_counter = counter; }
+    if (i == 0) { r.hdr->episode_length = ep_len; r.hdr->alive_counter = (int16_t)counter; }
     p.rew[io] = rw;
     p.done[io] = (capped || !alive_now || (fin && d.done_mode == 1)) ? 1 : 0;
   }
@@ -609,12 +611,13 @@ __device__ __forceinline__ void tile_rules(const KParams& p, const SH& sh, uint8
       if (fin && active) {
         if (p.rank) p.rank[io] = rk;
         if (p.ep_scores) p.ep_scores[io] = my_score;
-        if (p.ep_steps) p.ep_steps[io] = (int32_t)r.steps[i];
-        if (p.ep_fruits) p.ep_fruits[io] = (int32_t)r.fruits[i];
-        if (p.ep_kills) p.ep_kills[io] = (int32_t)r.kills[i];
-        ret = my_score; fr = r.fruits[i]; kl = r.kills[i];
+        fr = cnt_get(d, r, CNT_FRUITS, i); kl = cnt_get(d, r, CNT_KILLS, i);
+        if (p.ep_steps) p.ep_steps[io] = (int32_t)cnt_get(d, r, CNT_STEPS, i);
+        if (p.ep_fruits) p.ep_fruits[io] = (int32_t)fr;
+        if (p.ep_kills) p.ep_kills[io] = (int32_t)kl;
+        ret = my_score;
         if (i == 0) ln = r.hdr->episode_length;
-        r.score[i] = 0.0; r.steps[i] = 0; r.fruits[i] = 0; r.kills[i] = 0;
+        stats_zero(d, r, i);
       }
       for (int o = 16; o; o >>= 1) ret += __shfl_xor_sync(FULL, ret, o);
       fr = __reduce_add_sync(FULL, fr); kl = __reduce_add_sync(FULL, kl); ln = __reduce_add_sync(FULL, ln);
@@ -1378,7 +1381,7 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   if (!kCoop || warp == 0) {
     if ((int)lane < ne && !(s_flag[lane] & F_SKIP)) {
       EnvHdr* h = (EnvHdr*)(s_rec + (size_t)lane * d.rec_bytes + d.off_hdr);
-      h->hpos = (s_flag[lane] & (F_RESET | F_INIT)) ? 0u : (h->hpos + 1u) % (uint32_t)fs;
+      h->hpos = (uint8_t)((s_flag[lane] & (F_RESET | F_INIT)) ? 0u : ((uint32_t)h->hpos + 1u) % (uint32_t)fs);
     }
   }
   if (p.use_tma && (!kCoop || warp == 0)) fence_proxy_async();        // hpos updates -> async proxy
@@ -1450,9 +1453,9 @@ __global__ void snk_set_state_kernel(const Dims d, uint8_t* __restrict__ recs, S
         set_body_dir(d, r, cl[k], dd);
       }
     }
-    r.score[i] = 0.0; r.steps[i] = 0; r.fruits[i] = 0; r.kills[i] = 0;
+    stats_zero(d, r, i);
   }
-  r.hdr->alive_counter = sv.alive_counter[e];
+  r.hdr->alive_counter = (int16_t)sv.alive_counter[e];
   r.hdr->episode_length = (uint32_t)sv.episode_length[e];
   r.hdr->hpos = 0;
 }
@@ -1583,16 +1586,19 @@ template <int kNS, int kW, int kOH, int kOW, int kFS, bool kCoop, int kEnc, int 
 static cudaError_t launch_variant(const KParams& p, int threads, size_t smem_bytes, cudaStream_t stream) {
   // dynamic shared memory opt-in, once per (instance, device) and size: function attributes belong to the device's
   // context.  (Process-wide on purpose: the attribute is a property of the kernel, not of a handle; concurrent first
-  // launches from two threads set the same or a larger value, which is harmless.)
-  static size_t configured[64] = {};
+  // launches from two threads set the same or a larger value, which is harmless; the table itself is atomic.)
+  static std::atomic<size_t> configured[64];
   auto kern = snk_tile_kernel<kNS, kW, kOH, kOW, kFS, kCoop, kEnc, kVar>;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  if (dev < 0 || dev >= 64 || smem_bytes > configured[dev]) {
+  if (dev < 0 || dev >= 64 || smem_bytes > configured[dev].load(std::memory_order_acquire)) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) configured[dev] = smem_bytes;
+    if (dev >= 0 && dev < 64) {          // keep the maximum: a concurrent first launch may have stored a larger size
+      size_t seen = configured[dev].load(std::memory_order_relaxed);
+      while (seen < smem_bytes && !configured[dev].compare_exchange_weak(seen, smem_bytes, std::memory_order_release)) {}
+    }
   }
   const int envs_per_cta = (kCoop ? 1 : threads / 32) * p.E;
   const int grid = (p.d.N + envs_per_cta - 1) / envs_per_cta;

@@ -93,10 +93,10 @@ static void reset_env(HostSim& h, Rec& r, uint32_t env) {
     r.len[s] = (uint16_t)K;
     r.dir[s] = (uint8_t)((spawn_link(entry[s], 1) + 2) & 3);
     r.alive[s] = 1;
-    r.score[s] = 0.0; r.steps[s] = 0; r.fruits[s] = 0; r.kills[s] = 0;
+    stats_zero(d, r, s);
   }
   place_fruits(h, r, env, d.nfruits, DRAW_RESET_FRUIT);
-  r.hdr->alive_counter = ns;
+  r.hdr->alive_counter = (int16_t)ns;
   r.hdr->episode_length = 0;
 }
 
@@ -127,7 +127,7 @@ static void encode_env(HostSim& h, Rec& r, uint32_t env, bool init, uint8_t* obs
       else for (int f = 0; f < fs; ++f) { stg[(size_t)cell * fs + f] = (uint8_t)bits; hrow[(size_t)f * d.ohw_p + cell] = (uint8_t)bits; }
     }
   }
-  if (fs > 1) r.hdr->hpos = init ? 0u : (r.hdr->hpos + 1u) % (uint32_t)fs;
+  if (fs > 1) r.hdr->hpos = (uint8_t)(init ? 0u : ((uint32_t)r.hdr->hpos + 1u) % (uint32_t)fs);
   if (obs)
     for (int u = 0; u < d.stage_env_bytes; ++u) {
       const uint32_t b = stage[u];
@@ -207,11 +207,11 @@ void hs_step(void* p, const uint8_t* actions, uint8_t* obs, double* rew, uint8_t
         const size_t o = (size_t)e * ns + i;
         if (rank) rank[o] = competition_rank(r.score, ns, i);
         if (ep_scores) ep_scores[o] = r.score[i];
-        if (ep_steps) ep_steps[o] = (int32_t)r.steps[i];
-        if (ep_fruits) ep_fruits[o] = (int32_t)r.fruits[i];
-        if (ep_kills) ep_kills[o] = (int32_t)r.kills[i];
+        if (ep_steps) ep_steps[o] = (int32_t)cnt_get(d, r, CNT_STEPS, i);
+        if (ep_fruits) ep_fruits[o] = (int32_t)cnt_get(d, r, CNT_FRUITS, i);
+        if (ep_kills) ep_kills[o] = (int32_t)cnt_get(d, r, CNT_KILLS, i);
       }
-      for (int i = 0; i < ns; ++i) { r.score[i] = 0.0; r.steps[i] = 0; r.fruits[i] = 0; r.kills[i] = 0; }
+      for (int i = 0; i < ns; ++i) stats_zero(d, r, i);
       do_reset = d.auto_reset != 0;
     }
     if (res.fruit_taken) place_fruits(*h, r, (uint32_t)e, res.fruit_taken, DRAW_STEP_FRUIT);
@@ -252,9 +252,9 @@ void hs_set_state(void* p, const uint8_t* grid, const uint8_t* alive, const uint
           set_body_dir(d, r, cl[k], diff == -d.W ? 0 : diff == 1 ? 1 : diff == d.W ? 2 : 3);
         }
       }
-      r.score[i] = 0.0; r.steps[i] = 0; r.fruits[i] = 0; r.kills[i] = 0;
+      stats_zero(d, r, i);
     }
-    r.hdr->alive_counter = counter[e];
+    r.hdr->alive_counter = (int16_t)counter[e];
     r.hdr->episode_length = (uint32_t)ep_len[e];
     r.hdr->hpos = 0;
     encode_env(*h, r, (uint32_t)e, true, obs ? obs + (size_t)e * d.obs_env_bytes : nullptr);
