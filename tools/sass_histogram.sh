@@ -1,0 +1,11 @@
+#!/bin/bash
+# SASS opcode histogram of the in-tree libsnk.so (cuobjdump runs without a GPU): bash tools/sass_histogram.sh > profiles/<tag>_sass_opcodes.txt
+so=${1:-marl-snake_b200/libsnk.so}
+echo "# cuobjdump -sass $so  (sm_100a), opcode counts over all kernels; $(date -u +%F)"
+echo "# kernels:"; cuobjdump -sass $so | grep -oE "Function : [A-Za-z0-9_]+" | sed 's/Function : //' | c++filt | sed 's/(.*//' | sort | uniq -c | sed 's/^/#   /'
+echo "# proof points: UBLKCP = cp.async.bulk (TMA 1-D bulk copies), SYNCS = mbarrier, MATCH = match.any, REDUX/VOTE = warp votes,"
+echo "#   DMUL/DADD without DFMA = float64 reward in the reference's order, no LDL/STL = no local memory"
+for op in UBLKCP SYNCS MATCH VOTE REDUX DMUL DADD DFMA LDL STL UTCHMMA UTCQMMA; do
+  printf "# %-8s %s\n" $op $(cuobjdump -sass $so | grep -cE "^\s+/\*[0-9a-f]{4}\*/\s+(@!?U?P[0-9T] )?$op(\.|\s|;)")
+done
+cuobjdump -sass $so | grep -oE "^\s+/\*[0-9a-f]{4}\*/\s+(@!?U?P[0-9T] )?[A-Z][A-Z0-9_.]+" | awk '{print $NF}' | sed 's/\..*//' | sort | uniq -c | sort -rn
