@@ -16,7 +16,8 @@ SNK_XFER_RAW, SNK_XFER_PACKED = 0, 1
 DEV_ERRORS = {1: 'action outside {0,1,2}', 2: 'replay stream exhausted',
               4: 'replayed draw out of range / replayed spawn overlaps', 8: 'spawn sampling gave up',
               16: 'internal bounds check failed (debug build)',
-              32: "a record tile's bulk copy timed out; the tile was skipped"}
+              32: "a record tile's bulk copy timed out; the tile was skipped",
+              64: 'set_state: grid is not walls + fruits + live snakes, or too many fruit cells'}
 STAT_NAMES = ('episodes', 'return_sum', 'episode_steps_sum', 'fruits_sum', 'kills_sum', 'deaths',
               'env_steps', 'reserved')
 

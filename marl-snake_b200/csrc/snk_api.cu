@@ -59,6 +59,7 @@ struct snk_env {
   uint8_t* hist = nullptr;
   uint64_t* spawn = nullptr;
   uint32_t* wall_map = nullptr;                  // custom wall layout (snk_create_map): H*W cell codes, padded to words
+  uint8_t* base_grid = nullptr;                  // compact records: the wall layout, one copy per environment of a tile
   int32_t* replay = nullptr;
   int64_t* replay_off = nullptr;
   uint32_t* err = nullptr;
@@ -98,7 +99,7 @@ static KParams base_params(const snk_env* h) {
   KParams p;
   memset(&p, 0, sizeof p);
   p.d = h->d;
-  p.recs = h->recs; p.hist = h->hist; p.spawn = h->spawn; p.wall_map = h->wall_map;
+  p.recs = h->recs; p.hist = h->hist; p.spawn = h->spawn; p.wall_map = h->wall_map; p.base_grid = h->base_grid;
   p.replay = h->replay; p.replay_off = h->replay_off;
   p.err = h->err; p.stats = h->stats;
   p.E = h->tile_envs;
@@ -149,6 +150,7 @@ static int create_impl(const snk_config* c, const uint8_t* walls_host, snk_env**
   d.auto_reset = c->auto_reset ? 1 : 0; d.done_mode = c->done_mode ? 1 : 0; d.rng_mode = c->rng_mode;
   d.observer = c->observer;
   d.dig = default_dig(d.ns);
+  d.compact = 1;                      // decided with the tile mode below
   d.seed_lo = (uint32_t)c->seed; d.seed_hi = (uint32_t)(c->seed >> 32);
   d.env_off_lo = (uint32_t)c->env_id_offset; d.env_off_hi = (uint32_t)(c->env_id_offset >> 32);
   d.r_fruit = c->reward_fruit; d.r_kill = c->reward_kill; d.r_lose = c->reward_lose;
@@ -191,8 +193,21 @@ static int create_impl(const snk_config* c, const uint8_t* walls_host, snk_env**
   const int64_t tiles_full = ((int64_t)d.N + EPW_full - 1) / EPW_full;
   // Measured on the B200 (profiles/README.md, tools/sweep_tiles*.sh): warp-private tiles win once the batch
   // is several waves deep; below that, and for large records or frame stacks, the CTA-cooperative mode does.
+  // With compact records (profiles/r02_ab_compact*.txt) warp-private tiles already win from ~6 000 tiles on:
+  // 65 536 envs of the cfg5 shape 0.057 ms against 0.061 ms cooperative, 131 072 envs 0.097 against 0.114 ms.
   int coop = env_int("SNK_COOP", -1);
-  if (coop < 0) coop = (tiles_full < 148 * 192 || (size_t)EPW_full * d.rec_bytes > 8 * 1024 || d.fs > 1) ? 1 : 0;
+  if (coop < 0) coop = (tiles_full < 148 * 40 || (size_t)EPW_full * d.rec_bytes > 8 * 1024 || d.fs > 1) ? 1 : 0;
+  // Compact records (the grid is rebuilt in shared memory from walls + fruit slots + bodies instead of being read
+  // from and written to HBM) save 2 * H * W bytes per env-step and cost the rule warp a walk along every live body.
+  // That pays wherever bytes bound the step: warp-private tiles (cfg5 0.855 -> 0.769 ms), frame stacks (cfg3 0.207 ->
+  // 0.202 ms) and large grids (cfg4 0.124 -> 0.121 ms); a cooperative tile of a small grid is bound by the latency of
+  // its single rule warp, and there the walk costs more than the bytes (131 072-env shard 0.114 -> 0.118 ms, cfg2
+  // 0.0187 -> 0.0208 ms).  SNK_COMPACT=0/1 (or the older SNK_NO_COMPACT=1) forces the layout.
+  {
+    int compact = env_int("SNK_COMPACT", -1);
+    if (compact < 0) compact = default_compact() ? ((!coop || d.fs > 1 || d.HW >= 1024) ? 1 : 0) : 0;
+    if (!compact) { d.compact = 0; d.dig = default_dig(d.ns); finalize_layout(d); }
+  }
   // A coop tile may hold fewer environments than the rule warp has lane groups: shorter per-CTA latency
   // (the rule phase of one warp, then the tile's encode) and more rule warps in flight.  Shrink until a
   // tile's observation block is <= 32 KB, and further while the launch would not fill every SM 16 times.
@@ -244,7 +259,7 @@ static int create_impl(const snk_config* c, const uint8_t* walls_host, snk_env**
   DeviceGuard guard(c->device);
   if (guard.err != cudaSuccess) { delete h; return fail(SNK_E_CUDA, "cudaSetDevice(%d): %s", c->device, cudaGetErrorString(guard.err)); }
 #define CUH(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { int rc = fail(SNK_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); snk_destroy(h); return rc; } } while (0)
-  CUH(cudaMalloc(&h->recs, (size_t)d.N * d.rec_bytes));
+  CUH(cudaMalloc(&h->recs, (size_t)d.N * d.hbm_rec_bytes));
   if (d.hist_env_bytes) CUH(cudaMalloc(&h->hist, (size_t)d.N * d.hist_env_bytes));
   CUH(cudaMalloc(&h->spawn, table.size() * sizeof(uint64_t)));
   CUH(cudaMalloc(&h->err, sizeof(uint32_t)));
@@ -254,6 +269,16 @@ static int create_impl(const snk_config* c, const uint8_t* walls_host, snk_env**
   if (wm) {
     CUH(cudaMalloc(&h->wall_map, walls.size()));
     CUH(cudaMemcpy(h->wall_map, walls.data(), walls.size(), cudaMemcpyHostToDevice));
+  }
+  if (d.compact) {
+    // the grid every record implies starts from the wall layout: make_grid's walled box (core/grid_util.py:14-20) or
+    // the custom map; as many copies as the widest tile has environments, so ONE bulk copy paints a tile's grids
+    const int copies = h->tile_envs > h->many_tile_envs ? h->tile_envs : h->many_tile_envs;
+    std::vector<uint8_t> tpl((size_t)copies * d.off_c0, 0);
+    for (int i = 0; i < d.HW; ++i) tpl[i] = wm ? wm[i] : wall_or_empty(i, d.H, d.W);
+    for (int k = 1; k < copies; ++k) memcpy(tpl.data() + (size_t)k * d.off_c0, tpl.data(), (size_t)d.off_c0);
+    CUH(cudaMalloc(&h->base_grid, tpl.size()));
+    CUH(cudaMemcpy(h->base_grid, tpl.data(), tpl.size(), cudaMemcpyHostToDevice));
   }
   {
     size_t tab_off = 0, lutb_off = 0;
@@ -295,7 +320,7 @@ extern "C" int snk_destroy(snk_env* h) {
   if (!h) return SNK_OK;
   DeviceGuard guard(h->device);
   cudaFree(h->recs); cudaFree(h->hist); cudaFree(h->spawn); cudaFree(h->replay); cudaFree(h->replay_off);
-  cudaFree(h->err); cudaFree(h->stats); cudaFree(h->enc_blob); cudaFree(h->wall_map);
+  cudaFree(h->err); cudaFree(h->stats); cudaFree(h->enc_blob); cudaFree(h->wall_map); cudaFree(h->base_grid);
   cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_rew); cudaFree(h->h_done);
   cudaFree(h->h_fin); cudaFree(h->h_rank); cudaFree(h->h_scores); cudaFree(h->h_counts);
   cudaFree(h->small_dev);
@@ -323,7 +348,7 @@ extern "C" size_t snk_algorithmic_bytes_per_env_step(const snk_env* h) {
   const Dims& d = h->d;
   // state record read + write, frame history (read fs-1 rows, write 1), observation write,
   // actions in, rewards (f64) and dones out.
-  size_t b = 2 * (size_t)d.rec_bytes + (size_t)d.obs_env_bytes + (size_t)d.ns * (1 + 8 + 1);
+  size_t b = 2 * (size_t)d.hbm_rec_bytes + (size_t)d.obs_env_bytes + (size_t)d.ns * (1 + 8 + 1);
   if (d.fs > 1) b += (size_t)d.ns * d.fs * d.ohw;
   return b;
 }
@@ -708,7 +733,7 @@ extern "C" int snk_get_state(snk_env* h, const snk_state_view* out, void* stream
   if (!h || !out) return fail(SNK_E_INVALID, "null argument");
   if (out->cells && out->max_cells < 1) return fail(SNK_E_INVALID, "max_cells must be >= 1 when cells is given");
   ON_DEVICE(h);
-  CU(launch_get_state(h->d, h->recs, to_view(out), (cudaStream_t)stream));
+  CU(launch_get_state(h->d, h->recs, h->base_grid, to_view(out), (cudaStream_t)stream));
   note_user_stream(h, (cudaStream_t)stream);
   return SNK_OK;
 }
@@ -719,7 +744,7 @@ extern "C" int snk_set_state(snk_env* h, const snk_state_view* in, uint8_t* obs_
     return fail(SNK_E_INVALID, "set_state needs grid, alive, dir, cells, length, alive_counter, episode_length");
   if (obs_dev && ((uintptr_t)obs_dev & 7)) return fail(SNK_E_INVALID, "obs must be 8-byte aligned");
   ON_DEVICE(h);
-  CU(launch_set_state(h->d, h->recs, to_view(in), (cudaStream_t)stream));
+  CU(launch_set_state(h->d, h->recs, h->base_grid, h->err, to_view(in), (cudaStream_t)stream));
   KParams p = base_params(h);
   p.mode = MODE_ENCODE; p.obs = obs_dev;
   p.vec16 = check_vec16(h, obs_dev);
@@ -732,11 +757,11 @@ extern "C" int snk_set_state(snk_env* h, const snk_state_view* in, uint8_t* obs_
 // ---- exact checkpoint: the raw records (grid, snakes, counters, Philox event, replay cursor, statistics),
 // the frame histories and the rollout statistics vector, byte for byte
 static const uint64_t CKPT_MAGIC = 0x0031544B434B4E53ull;     // "SNKCKT1"
-struct CkptHeader { uint64_t magic; int32_t N, H, W, ns, K, V, fs, dig, rec_bytes, hist_env_bytes; double env_steps; };
+struct CkptHeader { uint64_t magic; int32_t N, H, W, ns, K, V, fs, dig, rec_bytes, hist_env_bytes; double env_steps; };   // rec_bytes: per env in HBM
 
 extern "C" size_t snk_checkpoint_bytes(const snk_env* h) {
   if (!h) return 0;
-  return sizeof(CkptHeader) + (size_t)h->d.N * ((size_t)h->d.rec_bytes + (size_t)h->d.hist_env_bytes) + STAT_COUNT * sizeof(double);
+  return sizeof(CkptHeader) + (size_t)h->d.N * ((size_t)h->d.hbm_rec_bytes + (size_t)h->d.hist_env_bytes) + STAT_COUNT * sizeof(double);
 }
 
 extern "C" int snk_checkpoint_save(snk_env* h, void* blob_host, size_t bytes) {
@@ -746,9 +771,9 @@ extern "C" int snk_checkpoint_save(snk_env* h, void* blob_host, size_t bytes) {
   CU(cudaDeviceSynchronize());
   const Dims& d = h->d;
   uint8_t* out = (uint8_t*)blob_host;
-  CkptHeader hd = {CKPT_MAGIC, d.N, d.H, d.W, d.ns, d.K, d.V, d.fs, d.dig, d.rec_bytes, d.hist_env_bytes, 0.0};
+  CkptHeader hd = {CKPT_MAGIC, d.N, d.H, d.W, d.ns, d.K, d.V, d.fs, d.dig | (d.compact << 1), d.hbm_rec_bytes, d.hist_env_bytes, 0.0};
   memcpy(out, &hd, sizeof hd); out += sizeof hd;
-  CU(cudaMemcpy(out, h->recs, (size_t)d.N * d.rec_bytes, cudaMemcpyDeviceToHost)); out += (size_t)d.N * d.rec_bytes;
+  CU(cudaMemcpy(out, h->recs, (size_t)d.N * d.hbm_rec_bytes, cudaMemcpyDeviceToHost)); out += (size_t)d.N * d.hbm_rec_bytes;
   if (d.hist_env_bytes) { CU(cudaMemcpy(out, h->hist, (size_t)d.N * d.hist_env_bytes, cudaMemcpyDeviceToHost)); out += (size_t)d.N * d.hist_env_bytes; }
   CU(cudaMemcpy(out, h->stats, STAT_COUNT * sizeof(double), cudaMemcpyDeviceToHost));
   return SNK_OK;
@@ -762,11 +787,11 @@ extern "C" int snk_checkpoint_load(snk_env* h, const void* blob_host, size_t byt
   CkptHeader hd;
   memcpy(&hd, in, sizeof hd); in += sizeof hd;
   if (hd.magic != CKPT_MAGIC || hd.N != d.N || hd.H != d.H || hd.W != d.W || hd.ns != d.ns || hd.K != d.K || hd.V != d.V ||
-      hd.fs != d.fs || hd.dig != d.dig || hd.rec_bytes != d.rec_bytes || hd.hist_env_bytes != d.hist_env_bytes)
+      hd.fs != d.fs || hd.dig != (d.dig | (d.compact << 1)) || hd.rec_bytes != d.hbm_rec_bytes || hd.hist_env_bytes != d.hist_env_bytes)
     return fail(SNK_E_INVALID, "checkpoint was written by a handle of a different shape");
   ON_DEVICE(h);
   CU(cudaDeviceSynchronize());
-  CU(cudaMemcpy(h->recs, in, (size_t)d.N * d.rec_bytes, cudaMemcpyHostToDevice)); in += (size_t)d.N * d.rec_bytes;
+  CU(cudaMemcpy(h->recs, in, (size_t)d.N * d.hbm_rec_bytes, cudaMemcpyHostToDevice)); in += (size_t)d.N * d.hbm_rec_bytes;
   if (d.hist_env_bytes) { CU(cudaMemcpy(h->hist, in, (size_t)d.N * d.hist_env_bytes, cudaMemcpyHostToDevice)); in += (size_t)d.N * d.hist_env_bytes; }
   CU(cudaMemcpy(h->stats, in, STAT_COUNT * sizeof(double), cudaMemcpyHostToDevice));
   h->was_reset = true;
@@ -790,7 +815,8 @@ extern "C" int snk_set_replay(snk_env* h, const int32_t* draws_host, const int64
   }
   CU(cudaMemcpy(h->replay_off, offsets_host, ((size_t)N + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
   // cursors live in the records: zero them
-  CU(cudaMemset2D(h->recs + h->d.off_hdr + offsetof(EnvHdr, cursor), (size_t)h->d.rec_bytes, 0, sizeof(uint32_t), (size_t)N));
+  CU(cudaMemset2D(h->recs + h->d.hbm_c0 + (h->d.off_hdr - h->d.off_c0) + offsetof(EnvHdr, cursor), (size_t)h->d.hbm_rec_bytes, 0,
+                  sizeof(uint32_t), (size_t)N));
   return SNK_OK;
 }
 
@@ -798,7 +824,8 @@ extern "C" int snk_replay_cursors(snk_env* h, int32_t* cursors_host) {
   if (!h || !cursors_host) return fail(SNK_E_INVALID, "null argument");
   ON_DEVICE(h);
   CU(cudaDeviceSynchronize());
-  CU(cudaMemcpy2D(cursors_host, sizeof(int32_t), h->recs + h->d.off_hdr + offsetof(EnvHdr, cursor), (size_t)h->d.rec_bytes,
+  CU(cudaMemcpy2D(cursors_host, sizeof(int32_t), h->recs + h->d.hbm_c0 + (h->d.off_hdr - h->d.off_c0) + offsetof(EnvHdr, cursor),
+                  (size_t)h->d.hbm_rec_bytes,
                   sizeof(int32_t), (size_t)h->d.N, cudaMemcpyDeviceToHost));
   return SNK_OK;
 }

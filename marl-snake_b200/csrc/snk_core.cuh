@@ -25,7 +25,9 @@ enum : int { EMPTY = 0, WALL = 1, FRUIT = 2, HEAD = 3, BODY = 4, TAIL = 5 };
 enum : int { RNG_PHILOX = 0, RNG_REPLAY = 1 };
 enum : uint32_t { ERR_BAD_ACTION = 1, ERR_REPLAY_UNDERRUN = 2, ERR_REPLAY_RANGE = 4, ERR_SPAWN_GIVEUP = 8,
                   ERR_INTERNAL = 16,       // a bounds / alignment check of the debug build (-DSNK_DEBUG_CHECKS) failed
-                  ERR_TMA_TIMEOUT = 32 };  // a record tile's bulk copy did not land within two seconds; tile skipped
+                  ERR_TMA_TIMEOUT = 32,    // a record tile's bulk copy did not land within two seconds; tile skipped
+                  ERR_STATE = 64 };        // compact records: set_state grid is not walls + fruits + live snakes, or more
+                                           // fruit cells than the record has slots for
 enum : int { DRAW_STEP_FRUIT = 0, DRAW_SPAWN = 1, DRAW_RESET_FRUIT = 2 };
 enum : int { STAT_EPISODES = 0, STAT_RETURN, STAT_EP_STEPS, STAT_FRUITS, STAT_KILLS, STAT_DEATHS,
              STAT_ENV_STEPS, STAT_COUNT = 8 };
@@ -61,8 +63,17 @@ struct Dims {
   int32_t code_mask;              // 63 when dig, else 255: grid byte -> cell code
   int32_t stat16;                 // 1: the per-snake episode counters (steps, fruits, kills) are uint16 -- they are
                                   //    bounded by the step cap, which then is <= 65535 (the default is 1e4) -- else uint32
-  // record layout (bytes from record start; grid is at 0)
-  int32_t off_dirp, off_snk, off_hdr, off_stats, rec_bytes;
+  int32_t compact;                // 1: the record kept in HBM is the working record WITHOUT its grid: the grid is a function
+                                  //    of the rest (wall layout + fruit cells + the live snakes' bodies, which the direction
+                                  //    plane spells out from tail to head) and is rebuilt in shared memory when a tile is
+                                  //    loaded.  Implies the direction plane (dig == 0) and a fruit slot list in the record.
+  int32_t fcap;                   // compact: fruit slots per environment (uint16 cell + 1, 0 = free)
+  // working-record layout (bytes from the record start; grid is at 0).  rec_bytes is the working record; the part from
+  // off_c0 on ("c-part": plane, snake table, header, statistics, fruit slots) is what a compact handle keeps in HBM
+  int32_t off_dirp, off_snk, off_hdr, off_stats, off_fruit, rec_bytes;
+  int32_t off_c0;                 // start of the c-part inside the working record (= round_up(HW, 16))
+  int32_t hbm_rec_bytes;          // bytes per environment in HBM: rec_bytes, or rec_bytes - off_c0 when compact
+  int32_t hbm_c0;                 // offset of the c-part inside the HBM record: off_c0, or 0 when compact
   int32_t hist_env_bytes;         // ns*fs*ohw_p, 0 when fs == 1
   int32_t stage_env_bytes;        // ns*ohw*fs  (staging area per env, output order)
   int32_t obs_env_bytes;          // ns*ohw*fs*8
@@ -82,13 +93,22 @@ inline void finalize_layout(Dims& d) {
   if (d.V > 0) { d.oh = d.ow = 2 * d.V + 1; } else { d.oh = d.H; d.ow = d.W; }
   d.ohw = d.oh * d.ow;
   d.ohw_p = round_up(d.ohw, 16);
+  if (d.compact) d.dig = 0;
   d.code_mask = d.dig ? 63 : 255;
   d.off_dirp = round_up(d.HW, 16);
+  d.off_c0 = d.off_dirp;
   d.off_snk = d.off_dirp + (d.dig ? 0 : round_up((d.HW + 3) / 4, 16));
   d.off_hdr = d.off_snk + round_up(8 * d.ns, 16);
   d.off_stats = d.off_hdr + (int)sizeof(EnvHdr);
   d.stat16 = d.max_steps <= 65535.0 ? 1 : 0;
-  d.rec_bytes = d.off_stats + round_up((8 + (d.stat16 ? 6 : 12)) * d.ns, 16);
+  d.off_fruit = d.off_stats + round_up((8 + (d.stat16 ? 6 : 12)) * d.ns, 16);
+  // A step can add a fruit without removing one (two heads meeting on a fruit: both die, the fruit stays and one more
+  // is drawn, C3) -- at most once per two deaths, so nfruits + ns / 2 cells bound an episode; ns more for set_state
+  d.fcap = d.compact ? round_up(d.nfruits + d.ns, 8) : 0;
+  if (d.fcap > 32) d.fcap = 32;                 // one warp lane per slot (nfruits <= 32)
+  d.rec_bytes = d.off_fruit + round_up(2 * d.fcap, 16);
+  d.hbm_rec_bytes = d.compact ? d.rec_bytes - d.off_c0 : d.rec_bytes;
+  d.hbm_c0 = d.compact ? 0 : d.off_c0;
   d.hist_env_bytes = d.fs > 1 ? d.ns * d.fs * d.ohw_p : 0;
   d.stage_env_bytes = d.ns * d.ohw * d.fs;
   d.obs_env_bytes = d.stage_env_bytes * 8;
@@ -111,12 +131,16 @@ struct Rec {
   EnvHdr* hdr;
   double* score;
   uint8_t* cnt;              // episode counters [3][ns] (steps, fruits, kills), uint16 or uint32 (Dims::stat16)
+  uint16_t* fruit;           // compact: fcap fruit slots, cell + 1 or 0
 };
 enum : int { CNT_STEPS = 0, CNT_FRUITS = 1, CNT_KILLS = 2 };
 
-SNK_HD Rec rec_view(uint8_t* base, const Dims& d) {
+// g: the grid, c: the c-part (working-record offsets minus off_c0).  A contiguous working record has c == g + off_c0;
+// a compact handle keeps the two in separate shared-memory areas (and only the c-part in HBM).
+SNK_HD Rec rec_view2(uint8_t* g, uint8_t* c, const Dims& d) {
   Rec r;
-  r.grid = base;
+  uint8_t* base = c - d.off_c0;
+  r.grid = g;
   r.dirp = base + d.off_dirp;
   r.head = (uint16_t*)(base + d.off_snk);
   r.tail = r.head + d.ns;
@@ -126,8 +150,10 @@ SNK_HD Rec rec_view(uint8_t* base, const Dims& d) {
   r.hdr = (EnvHdr*)(base + d.off_hdr);
   r.score = (double*)(base + d.off_stats);
   r.cnt = (uint8_t*)(r.score + d.ns);
+  r.fruit = (uint16_t*)(base + d.off_fruit);
   return r;
 }
+SNK_HD Rec rec_view(uint8_t* base, const Dims& d) { return rec_view2(base, base + d.off_c0, d); }
 SNK_HD uint32_t cnt_get(const Dims& d, const Rec& r, int field, int i) {
   const int k = field * d.ns + i;
   return d.stat16 ? (uint32_t)((const uint16_t*)r.cnt)[k] : ((const uint32_t*)r.cnt)[k];
@@ -159,6 +185,11 @@ SNK_HD int dir_delta(int dir, int W) { return dir == 0 ? -W : dir == 1 ? 1 : dir
 // With at most 6 snakes every cell code (type + 10*owner <= 55) fits 6 bits, so the 2-bit direction of a
 // BODY / TAIL cell rides in bits 6..7 of its grid byte and the plane is dropped from the record ("dig").
 // EMPTY / WALL / FRUIT / HEAD bytes carry no direction bits, so an empty cell is still exactly 0.
+// SNK_NO_COMPACT=1 keeps the whole working record (grid included) in HBM -- the round-1 layout, kept for A/B runs.
+inline int default_compact() {
+  const char* off = getenv("SNK_NO_COMPACT");
+  return (off && *off == '1') ? 0 : 1;
+}
 inline int default_dig(int ns) {
   const char* off = getenv("SNK_NO_DIG");
   return (10 * (ns - 1) + 5 < 64 && !(off && *off == '1')) ? 1 : 0;

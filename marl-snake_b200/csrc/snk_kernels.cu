@@ -104,9 +104,10 @@ __device__ __forceinline__ uint32_t warp_inclusive_sum(uint32_t v, uint32_t lane
 // memory, and every byte store into the grid would force its pointer fields to be reloaded from there.)
 // (Likewise every configuration value is copied into a local first: `p` arrives as a generic reference here, and
 // a field read after a shared-memory store would be reloaded through a generic load -- 1 to 2 us per reset.)
-__device__ __noinline__ void place_fruits_warp(const KParams& p, uint8_t* rec_base, uint32_t env_local, int k, int purpose) {
+// g: the environment's grid, vb: its virtual record base (c-part address minus off_c0; == g for a contiguous record).
+__device__ __noinline__ void place_fruits_warp(const KParams& p, uint8_t* g, uint8_t* vb, uint32_t env_local, int k, int purpose) {
   const Dims& d = p.d;
-  const Rec r = rec_view(rec_base, d);
+  const Rec r = rec_view2(g, vb + d.off_c0, d);
   const uint32_t FULL = 0xffffffffu;
   const uint32_t lane = lane_id();
   const int HW = d.HW, rng_mode = d.rng_mode;
@@ -200,6 +201,20 @@ __device__ __noinline__ void place_fruits_warp(const KParams& p, uint8_t* rec_ba
   __syncwarp();
   SNK_ASSERT(p, mycell < HW);
   if (mycell >= 0) r.grid[mycell] = (uint8_t)FRUIT;
+  if (d.compact) {
+    // the new fruit cells also go into the record's slot list (duplicate draws collapse to one cell, one slot):
+    // the a-th distinct new cell takes the a-th free slot
+    const int fcap = d.fcap;
+    const uint32_t dup = __match_any_sync(FULL, mycell);
+    const bool adds = mycell >= 0 && (__ffs(dup) - 1) == (int)lane;
+    const uint32_t adders = __ballot_sync(FULL, adds);
+    const uint32_t freem = __ballot_sync(FULL, (int)lane < fcap && r.fruit[lane] == 0);
+    if (adds) {
+      const uint32_t slot = __fns(freem, 0, __popc(adders & ((1u << lane) - 1u)) + 1);
+      if (slot < 32u) r.fruit[slot] = (uint16_t)(mycell + 1);
+      else atomicOr(p.err, ERR_STATE);
+    }
+  }
   __syncwarp();
 }
 
@@ -212,15 +227,16 @@ __device__ __forceinline__ void dirp_set_atomic(uint8_t* dirp, int c, int v) {
 }
 
 // SnakeEnv.reset for one environment record in shared memory      envs/snake_env.py:131-159, 576-596
-__device__ __noinline__ void reset_env_warp(const KParams& p, uint8_t* rec_base, uint32_t env_local) {
+__device__ __noinline__ void reset_env_warp(const KParams& p, uint8_t* g, uint8_t* vb, uint32_t env_local) {
   const Dims& d = p.d;
-  const Rec r = rec_view(rec_base, d);
+  const Rec r = rec_view2(g, vb + d.off_c0, d);
   const uint32_t lane = lane_id();
   // values read inside loops live in registers (see place_fruits_warp); what a rare branch reads once stays in `p`
   const int ns = d.ns, K = d.K, W = d.W, H = d.H, rng_mode = d.rng_mode;
   const uint32_t n_cand = d.n_cand, inv_row_words = p.inv_row_words;
   const uint64_t* const spawn = p.spawn;
   SNK_R(0);
+  if (d.compact && (int)lane < d.fcap) r.fruit[lane] = 0;
   // make_grid: walled empty box (core/grid_util.py:14-20), one grid row at a time so no division is needed --
   // or the handle's custom wall layout (snk_create_map), copied word by word from its L2-resident plane
   if (p.wall_map) {
@@ -317,7 +333,7 @@ __device__ __noinline__ void reset_env_warp(const KParams& p, uint8_t* rec_base,
   if (me) write_snake((int)lane);
   __syncwarp();
   SNK_R(3);
-  place_fruits_warp(p, rec_base, env_local, d.nfruits, DRAW_RESET_FRUIT);
+  place_fruits_warp(p, g, vb, env_local, d.nfruits, DRAW_RESET_FRUIT);
   if (lane == 0) { r.hdr->alive_counter = (int16_t)ns; r.hdr->episode_length = 0; }
   __syncwarp();
   SNK_R(4);
@@ -465,6 +481,12 @@ __device__ __forceinline__ GroupOut step_group(const KParams& p, const SH& sh, R
   bool died = was_alive && (n > 1 || lethal);
   const bool credit = died && first && (kind == BODY || kind == HEAD);     // owner paid once per cell (C2)
   const bool eater = was_alive && !died && kind == FRUIT;
+  if (d.compact && eater) {                           // the eaten fruit leaves the record's slot list
+    const int fcap = d.fcap;
+#pragma unroll 1
+    for (int j = 0; j < fcap; ++j)
+      if (r.fruit[j] == (uint16_t)(tgt + 1u)) { r.fruit[j] = 0; break; }
+  }
   const int fruit_taken = __popc(__ballot_sync(FULL, was_alive && first && kind == FRUIT) & gmask);   // (C3)
   int counter = r.hdr->alive_counter - __popc(__ballot_sync(FULL, died) & gmask);        // :334
 
@@ -563,10 +585,56 @@ __device__ __forceinline__ GroupOut step_group(const KParams& p, const SH& sh, R
   return out;
 }
 
+// Where a tile's environments live in shared memory: grid of environment q at g + q * gs, its virtual record base
+// (c-part address minus off_c0) at vb + q * cs.  Contiguous working records: g == vb, gs == cs == rec_bytes.
+// Compact handle: the grids (rebuilt, never stored) in one block, the c-parts (the HBM records) behind it.
+struct TilePtr {
+  uint8_t* g; uint8_t* vb; int gs, cs;
+  __device__ __forceinline__ uint8_t* G(int q) const { return g + (size_t)q * gs; }
+  __device__ __forceinline__ uint8_t* VB(int q) const { return vb + (size_t)q * cs; }
+};
+
+// Compact records: the grids of the tile arrived as copies of the handle's wall layout; put the fruit cells and the
+// live snakes' bodies on them.  Lanes = (environment, snake) as in the rule phase.  A body is walked from its tail
+// along the direction plane (each cell's entry points toward the head)      inverse of core/snake.py:86-94
+template <class SH>
+__device__ __forceinline__ void expand_tile(const KParams& p, const SH& sh, const TilePtr& tp, int ne) {
+  const Dims& d = p.d;
+  const int lane = (int)lane_id();
+  const int ns = sh.ns(), G = sh.group(), W = sh.W();
+  const int g = lane / G, i = lane - g * G;
+  if (g < ne) {
+    const Rec r = rec_view2(tp.G(g), tp.VB(g) + d.off_c0, d);
+    const int fcap = d.fcap;
+    for (int j = i; j < fcap; j += G) {
+      const uint32_t s = r.fruit[j];
+      if (s) { SNK_ASSERT(p, s <= (uint32_t)d.HW); r.grid[s - 1u] = (uint8_t)FRUIT; }
+    }
+  }
+  __syncwarp();          // a snake never lies on a fruit cell, but keep the two passes ordered anyway
+  if (g < ne && i < ns) {
+    const Rec r = rec_view2(tp.G(g), tp.VB(g) + d.off_c0, d);
+    if (r.alive[i]) {
+      const int hd = r.head[i], tag = 10 * i;
+      int c = r.tail[i];
+      uint8_t code = (uint8_t)(TAIL + tag);
+#pragma unroll 1
+      for (int guard = 0; guard < d.HW && c != hd; ++guard) {
+        SNK_ASSERT(p, (unsigned)c < (unsigned)d.HW);
+        r.grid[c] = code;
+        code = (uint8_t)(BODY + tag);
+        c += dir_delta(dirp_get(r.dirp, c), W);
+      }
+      r.grid[hd] = (uint8_t)(HEAD + tag);
+    }
+  }
+  __syncwarp();
+}
+
 // ---- one warp: rules + terminal info + rollout statistics + rare events for a tile ----------------
 // Leaves per-environment flags in s_flag[] (F_RESET / F_INIT / F_SKIP).
 template <class SH>
-__device__ __forceinline__ void tile_rules(const KParams& p, const SH& sh, uint8_t* s_rec, int e0, int ne,
+__device__ __forceinline__ void tile_rules(const KParams& p, const SH& sh, const TilePtr& tp, int e0, int ne,
                                            uint8_t* s_flag, uint32_t action, int t) {
   const Dims& d = p.d;
   const uint32_t FULL = 0xffffffffu;
@@ -579,7 +647,7 @@ __device__ __forceinline__ void tile_rules(const KParams& p, const SH& sh, uint8
   const bool env_ok = g < ne;
   const bool active = env_ok && i < ns;
   const int e = e0 + g;
-  Rec r = rec_view(s_rec + (size_t)(env_ok ? g : 0) * d.rec_bytes, d);
+  Rec r = rec_view2(tp.G(env_ok ? g : 0), tp.VB(env_ok ? g : 0) + d.off_c0, d);
   // outputs of step t of a multi-step launch (snk_step_many) land t * [N, ns] (t * [N] for `finished`) further on
   const size_t io = (size_t)t * d.N * ns + (size_t)e * ns + i;
   const size_t ie = (size_t)t * d.N + e;
@@ -649,9 +717,8 @@ __device__ __forceinline__ void tile_rules(const KParams& p, const SH& sh, uint8
     const int q = src / G;
     const int qf = __shfl_sync(FULL, fruit, src);
     const int qflag = __shfl_sync(FULL, (int)flag, src);
-    uint8_t* rq = s_rec + (size_t)q * d.rec_bytes;
-    if (qf) place_fruits_warp(p, rq, (uint32_t)(e0 + q), qf, DRAW_STEP_FRUIT);
-    if (qflag & F_RESET) reset_env_warp(p, rq, (uint32_t)(e0 + q));
+    if (qf) place_fruits_warp(p, tp.G(q), tp.VB(q), (uint32_t)(e0 + q), qf, DRAW_STEP_FRUIT);
+    if (qflag & F_RESET) reset_env_warp(p, tp.G(q), tp.VB(q), (uint32_t)(e0 + q));
   }
   __syncwarp();
 }
@@ -678,7 +745,7 @@ __device__ __forceinline__ uint32_t window_mask(int V, int oh, int ow, int H, in
 // -> LUT row -> one 128-bit streaming store.  A viewer block of ohw*8 bytes is only 8-byte aligned
 // when ohw is odd, so units are laid out from the address parity and the end units may be half units.
 template <class SH>
-__device__ __forceinline__ void encode_viewer_fs1(const KParams& p, const SH& sh, const uint8_t* base,
+__device__ __forceinline__ void encode_viewer_fs1(const KParams& p, const SH& sh, const uint8_t* base, const uint8_t* vb,
                                                   uint32_t grid32, int v, uint8_t* outv, uint32_t lut32,
                                                   uint8_t* bitsv, uint32_t lutb32) {
   const Dims& d = p.d;
@@ -687,7 +754,7 @@ __device__ __forceinline__ void encode_viewer_fs1(const KParams& p, const SH& sh
   const int H = d.H, V = d.V;
   const uint8_t* grid = base;
   int r0, c0;
-  viewer_origin(d, base, ns, W, V, v, r0, c0);
+  viewer_origin(d, vb, ns, W, V, v, r0, c0);
   const int shift = (int)((reinterpret_cast<uintptr_t>(outv) >> 3) & 1);
   const int units = (ohw + shift + 1) >> 1;
   if (p.use_tab) {
@@ -965,7 +1032,7 @@ __device__ __forceinline__ void encode_viewer_direct(const SH& sh, uint32_t grid
 // with flat 128-bit stores.  The frame history lives in HBM as one byte per window cell per stored frame,
 // rows of a ring (hist layout); each step reads fs-1 rows and writes one.
 template <class SH, int kFS, bool kBits>
-__device__ __forceinline__ void encode_env_stacked(const KParams& p, const SH& sh, const uint8_t* base, int e,
+__device__ __forceinline__ void encode_env_stacked(const KParams& p, const SH& sh, const uint8_t* base, const uint8_t* vb, int e,
                                                    int qflag, uint8_t* s_stage, uint32_t lut32, const uint8_t* s_lut,
                                                    const uint8_t* s_hist) {
   const Dims& d = p.d;
@@ -980,13 +1047,13 @@ __device__ __forceinline__ void encode_env_stacked(const KParams& p, const SH& s
   const uint8_t* grid = base;
   const uint32_t grid32 = (uint32_t)__cvta_generic_to_shared(grid);
   const bool init = (qflag & (F_RESET | F_INIT)) != 0;
-  const int hpos = (int)((const EnvHdr*)(base + d.off_hdr))->hpos;
+  const int hpos = (int)((const EnvHdr*)(vb + d.off_hdr))->hpos;
   // The environment's whole history block (ns x fs rows) was staged into shared memory by the same bulk copy
   // barrier as its record, so the kept frames cost no HBM round trip here; only the new row goes out.
 #pragma unroll 1
   for (int v = 0; v < ns; ++v) {
     int r0, c0;
-    viewer_origin(d, base, ns, W, V, v, r0, c0);
+    viewer_origin(d, vb, ns, W, V, v, r0, c0);
     uint8_t* stg = s_stage + (size_t)v * ohw * fs;
     uint8_t* hrow = p.hist + (size_t)e * d.hist_env_bytes + (size_t)(v * fs) * d.ohw_p;
     const uint8_t* srow = s_hist + (size_t)(v * fs) * d.ohw_p;                  // the same rows, staged
@@ -1153,13 +1220,21 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   uint32_t* s_view = reinterpret_cast<uint32_t*>(s_flag + 48);         // one packed word per (environment, viewer) lane
   uint8_t* s_lut = smem + (size_t)ntiles * tile_bytes + (size_t)nwarps * stage_bytes + (size_t)ntiles * TILE_AUX_BYTES;
   uint8_t* s_pad = s_lut + p.enc_blob_bytes + 16;                       // ENC_PAD: zero-bordered planes of the tile's grids
+  // compact handle: [EPW grids (wall layout copies, then rebuilt)][EPW c-parts = the HBM records]; otherwise EPW
+  // contiguous working records
+  TilePtr tp;
+  tp.g = s_rec;
+  if (d.compact) { tp.gs = d.off_c0; tp.cs = d.hbm_rec_bytes; tp.vb = s_rec + (size_t)EPW * d.off_c0 - d.off_c0; }
+  else { tp.gs = tp.cs = d.rec_bytes; tp.vb = s_rec; }
+  uint8_t* const s_c = tp.vb + d.off_c0 - d.hbm_c0;                     // first byte of the tile as it lies in HBM
 
   // ---- stage the tile's records: HBM -> shared.  One bulk asynchronous copy (TMA) issued by the tile's
   //      elected thread and awaited on an mbarrier, or 128-bit coalesced loads (p.use_tma == 0).
   const bool elected = kCoop ? tid == 0 : lane == 0;
-  const uint32_t rec32 = (uint32_t)__cvta_generic_to_shared(s_rec);
+  const uint32_t rec32 = (uint32_t)__cvta_generic_to_shared(s_c);
   const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(s_flag) + 32u;     // flags: 32 B, mbarrier: 8 B
-  const uint32_t tile_load_bytes = (uint32_t)ne * (uint32_t)d.rec_bytes;
+  const uint32_t tile_load_bytes = (uint32_t)ne * (uint32_t)d.hbm_rec_bytes;
+  const uint32_t grid_load_bytes = d.compact ? (uint32_t)ne * (uint32_t)d.off_c0 : 0u;   // wall-layout copies (L2-resident)
   const uint32_t hist_load_bytes = (fs > 1 && p.mode == MODE_STEP) ? (uint32_t)ne * (uint32_t)d.hist_env_bytes : 0u;
   // The encode tables ride on the same barrier when the tile's elected thread can speak for every reader
   // of s_lut (coop CTA, or a single-warp CTA); otherwise the CTA copies them with 128-bit loads below.
@@ -1168,18 +1243,24 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
     if (elected) {
       mbar_init(mbar, 1);
       if (ne > 0) {
-        mbar_expect_tx(mbar, tile_load_bytes + hist_load_bytes + (blob_by_tma ? (uint32_t)p.enc_copy_bytes : 0u));
-        bulk_load(rec32, p.recs + (size_t)e0 * d.rec_bytes, tile_load_bytes, mbar);
+        mbar_expect_tx(mbar, tile_load_bytes + grid_load_bytes + hist_load_bytes + (blob_by_tma ? (uint32_t)p.enc_copy_bytes : 0u));
+        bulk_load(rec32, p.recs + (size_t)e0 * d.hbm_rec_bytes, tile_load_bytes, mbar);
+        if (grid_load_bytes) bulk_load((uint32_t)__cvta_generic_to_shared(s_rec), p.base_grid, grid_load_bytes, mbar);
         if (hist_load_bytes) bulk_load((uint32_t)__cvta_generic_to_shared(s_hist), p.hist + (size_t)e0 * d.hist_env_bytes, hist_load_bytes, mbar);
         if (blob_by_tma) bulk_load((uint32_t)__cvta_generic_to_shared(s_lut), p.enc_blob, (uint32_t)p.enc_copy_bytes, mbar);
       }
     }
   } else {
-    const uint4* src = reinterpret_cast<const uint4*>(p.recs + (size_t)e0 * d.rec_bytes);
-    uint4* dst = reinterpret_cast<uint4*>(s_rec);
-    const int n16 = ne * (d.rec_bytes >> 4);
+    const uint4* src = reinterpret_cast<const uint4*>(p.recs + (size_t)e0 * d.hbm_rec_bytes);
+    uint4* dst = reinterpret_cast<uint4*>(s_c);
+    const int n16 = ne * (d.hbm_rec_bytes >> 4);
     if (kCoop) { for (int k = tid; k < n16; k += nt) dst[k] = __ldcs(src + k); }
     else { for (int k = (int)lane; k < n16; k += 32) dst[k] = __ldcs(src + k); }
+    const uint4* gsrc = reinterpret_cast<const uint4*>(p.base_grid);
+    uint4* gdst = reinterpret_cast<uint4*>(s_rec);
+    const int g16 = (int)(grid_load_bytes >> 4);
+    if (kCoop) { for (int k = tid; k < g16; k += nt) gdst[k] = __ldg(gsrc + k); }
+    else { for (int k = (int)lane; k < g16; k += 32) gdst[k] = __ldg(gsrc + k); }
     const uint4* hsrc = reinterpret_cast<const uint4*>(p.hist + (size_t)e0 * d.hist_env_bytes);
     uint4* hdst = reinterpret_cast<uint4*>(s_hist);
     const int h16 = (int)(hist_load_bytes >> 4);
@@ -1243,16 +1324,17 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
       const int g = (int)lane / G, i = (int)lane - g * G;
       action = (g < ne && i < ns) ? __ldg(p.actions + ((size_t)t * d.N + e0 + g) * ns + i) : 0u;
     }
-    if (ne > 0) tile_rules(p, sh, s_rec, e0, ne, s_flag, action, t);
+    if (d.compact && t == 0 && ne > 0) expand_tile(p, sh, tp, ne);
+    if (ne > 0) tile_rules(p, sh, tp, e0, ne, s_flag, action, t);
     if (kEnc == ENC_REG && ne > 0) {           // crop origin + out-of-grid rows / columns of every viewer of the tile
       const int g = (int)lane / G, i = (int)lane - g * G;
-      if (g < ne && i < ns) s_view[lane] = make_viewer_word(p, sh, s_rec + (size_t)g * d.rec_bytes, i);
+      if (g < ne && i < ns) s_view[lane] = make_viewer_word(p, sh, tp.VB(g), i);
     }
     if (kEnc == ENC_PAD && ne > 0) {           // crop origin of every viewer inside its padded plane
       const int g = (int)lane / G, i = (int)lane - g * G;
       if (g < ne && i < ns) {
         int r0, c0;
-        viewer_origin(d, s_rec + (size_t)g * d.rec_bytes, ns, sh.W(), d.V, i, r0, c0);
+        viewer_origin(d, tp.VB(g), ns, sh.W(), d.V, i, r0, c0);
         s_view[lane] = (uint32_t)((r0 + d.V) * sh.pad_pitch() + c0 + sh.pad_left());
       }
     }
@@ -1269,11 +1351,11 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
     //      asynchronously under the encode; its issuer waits for the shared-memory reads before exiting.
     if (last) {
       if (p.use_tma) {
-        if (elected) bulk_store(p.recs + (size_t)e0 * d.rec_bytes, rec32, tile_load_bytes);
+        if (elected) bulk_store(p.recs + (size_t)e0 * d.hbm_rec_bytes, rec32, tile_load_bytes);
       } else {
-        uint4* dst = reinterpret_cast<uint4*>(p.recs + (size_t)e0 * d.rec_bytes);
-        const uint4* src = reinterpret_cast<const uint4*>(s_rec);
-        const int n16 = ne * (d.rec_bytes >> 4);
+        uint4* dst = reinterpret_cast<uint4*>(p.recs + (size_t)e0 * d.hbm_rec_bytes);
+        const uint4* src = reinterpret_cast<const uint4*>(s_c);
+        const int n16 = ne * (d.hbm_rec_bytes >> 4);
         if (kCoop) { for (int k = tid; k < n16; k += nt) dst[k] = src[k]; }
         else { for (int k = (int)lane; k < n16; k += 32) dst[k] = src[k]; }
       }
@@ -1292,7 +1374,7 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
           const int q = (int)__umulhi((uint32_t)idx, (uint32_t)p.inv_grid_words);
           const int j = idx - q * nw;
           const int rr = kW ? j / wpr : (int)__umulhi((uint32_t)j, (uint32_t)p.inv_row_words);
-          const uint32_t w = reinterpret_cast<const uint32_t*>(s_rec + (size_t)q * d.rec_bytes)[j];
+          const uint32_t w = reinterpret_cast<const uint32_t*>(tp.G(q))[j];
           uint32_t* dst = reinterpret_cast<uint32_t*>(s_pad + (size_t)q * d.pad_env_bytes + d.V * sh.pad_pitch() + sh.pad_left());
           dst[rr * P4 + (j - rr * wpr)] = w & cm4;
         }
@@ -1324,19 +1406,19 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
         for (int pv = wfirst; pv < ne * ns; pv += wstep) {
           const int q = pv / ns, v = pv - q * ns;
           if (s_flag[q] & F_SKIP) continue;
-          const uint8_t* base = s_rec + (size_t)q * d.rec_bytes;
+          const uint8_t* base = tp.G(q);
           const uint32_t grid32 = (uint32_t)__cvta_generic_to_shared(base);
           uint8_t* outv = obs_t ? obs_t + ((size_t)(e0 + q) * ns + v) * (size_t)ohw * 8 : nullptr;
           uint8_t* bitsv = bits_t ? bits_t + ((size_t)(e0 + q) * ns + v) * (size_t)ohw : nullptr;
           if (kEnc == ENC_REG) encode_viewer_reg(p, sh, grid32, s_view[q * G + v], cw, v, outv, lut32, bitsv, lutb32);
           else if (kEnc == ENC_DIRECT) encode_viewer_direct(sh, grid32, v, outv, lut32, (uint32_t)d.code_mask, bitsv, lutb32);
-          else encode_viewer_fs1(p, sh, base, grid32, v, outv, lut32, bitsv, lutb32);
+          else encode_viewer_fs1(p, sh, base, tp.VB(q), grid32, v, outv, lut32, bitsv, lutb32);
         }
       } else {
 #pragma unroll 1
         for (int q = 0; q < ne; ++q) {
           if (s_flag[q] & F_SKIP) continue;
-          const uint8_t* base = s_rec + (size_t)q * d.rec_bytes;
+          const uint8_t* base = tp.G(q);
           const uint32_t grid32 = (uint32_t)__cvta_generic_to_shared(base);
           uint8_t* outq = obs_t ? obs_t + (size_t)(e0 + q) * ns * (size_t)ohw * 8 : nullptr;
           uint8_t* bitsq = bits_t ? bits_t + (size_t)(e0 + q) * ns * (size_t)ohw : nullptr;
@@ -1346,7 +1428,7 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
             uint8_t* bitsv = bitsq ? bitsq + (size_t)v * ohw : nullptr;
             if (kEnc == ENC_REG) encode_viewer_reg(p, sh, grid32, s_view[q * G + v], cw, v, outv, lut32, bitsv, lutb32);
             else if (kEnc == ENC_DIRECT) encode_viewer_direct(sh, grid32, v, outv, lut32, (uint32_t)d.code_mask, bitsv, lutb32);
-            else encode_viewer_fs1(p, sh, base, grid32, v, outv, lut32, bitsv, lutb32);
+            else encode_viewer_fs1(p, sh, base, tp.VB(q), grid32, v, outv, lut32, bitsv, lutb32);
           }
         }
       }
@@ -1374,13 +1456,13 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   for (int q = wfirst; q < ne; q += wstep) {
     const int qflag = s_flag[q];
     if (qflag & F_SKIP) continue;
-    encode_env_stacked<Shape<kNS, kW, kOH, kOW, kFS>, kFS, kBits>(p, sh, s_rec + (size_t)q * d.rec_bytes, e0 + q, qflag,
+    encode_env_stacked<Shape<kNS, kW, kOH, kOW, kFS>, kFS, kBits>(p, sh, tp.G(q), tp.VB(q), e0 + q, qflag,
                                                            s_stage, lut32, s_lut, s_hist + (size_t)q * d.hist_env_bytes);
   }
   if (kCoop) __syncthreads(); else __syncwarp();
   if (!kCoop || warp == 0) {
     if ((int)lane < ne && !(s_flag[lane] & F_SKIP)) {
-      EnvHdr* h = (EnvHdr*)(s_rec + (size_t)lane * d.rec_bytes + d.off_hdr);
+      EnvHdr* h = (EnvHdr*)(tp.VB((int)lane) + d.off_hdr);
       h->hpos = (uint8_t)((s_flag[lane] & (F_RESET | F_INIT)) ? 0u : ((uint32_t)h->hpos + 1u) % (uint32_t)fs);
     }
   }
@@ -1389,24 +1471,43 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   // ---- write the records back: shared -> HBM
   if (p.use_tma) {
     if (elected) {
-      bulk_store(p.recs + (size_t)e0 * d.rec_bytes, rec32, tile_load_bytes);
+      bulk_store(p.recs + (size_t)e0 * d.hbm_rec_bytes, rec32, tile_load_bytes);
       bulk_store_wait_read();
     }
   } else {
-    uint4* dst = reinterpret_cast<uint4*>(p.recs + (size_t)e0 * d.rec_bytes);
-    const uint4* src = reinterpret_cast<const uint4*>(s_rec);
-    const int n16 = ne * (d.rec_bytes >> 4);
+    uint4* dst = reinterpret_cast<uint4*>(p.recs + (size_t)e0 * d.hbm_rec_bytes);
+    const uint4* src = reinterpret_cast<const uint4*>(s_c);
+    const int n16 = ne * (d.hbm_rec_bytes >> 4);
     if (kCoop) { for (int k = tid; k < n16; k += nt) dst[k] = src[k]; }
     else { for (int k = (int)lane; k < n16; k += 32) dst[k] = src[k]; }
   }
 }
 
 // ---- state export / import (parity + checkpoint interface; thread per environment) ----------------
-__global__ void snk_get_state_kernel(const Dims d, const uint8_t* __restrict__ recs, StateView sv) {
+// Compact handles keep no grid in HBM: `base_grid` is the handle's wall layout, the caller's array receives the rebuilt
+// grid (walls + fruit slots + live bodies walked from the tail).  r.grid is never dereferenced for them.
+__global__ void snk_get_state_kernel(const Dims d, const uint8_t* __restrict__ recs, const uint8_t* __restrict__ base_grid,
+                                     StateView sv) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.N) return;
-  Rec r = rec_view(const_cast<uint8_t*>(recs) + (size_t)e * d.rec_bytes, d);
-  if (sv.grid) for (int c = 0; c < d.HW; ++c) sv.grid[(size_t)e * d.HW + c] = (uint8_t)cell_code(d, r.grid[c]);
+  uint8_t* hb = const_cast<uint8_t*>(recs) + (size_t)e * d.hbm_rec_bytes;
+  Rec r = rec_view2(hb, hb + d.hbm_c0, d);
+  if (sv.grid && !d.compact) for (int c = 0; c < d.HW; ++c) sv.grid[(size_t)e * d.HW + c] = (uint8_t)cell_code(d, r.grid[c]);
+  if (sv.grid && d.compact) {
+    uint8_t* out = sv.grid + (size_t)e * d.HW;
+    for (int c = 0; c < d.HW; ++c) out[c] = base_grid[c];
+    for (int j = 0; j < d.fcap; ++j) if (r.fruit[j]) out[r.fruit[j] - 1] = (uint8_t)FRUIT;
+    for (int i = 0; i < d.ns; ++i) {
+      if (!r.alive[i]) continue;
+      int c = r.tail[i];
+      uint8_t code = (uint8_t)(TAIL + 10 * i);
+      for (int guard = 0; guard < d.HW && c != r.head[i]; ++guard) {
+        out[c] = code; code = (uint8_t)(BODY + 10 * i);
+        c += dir_delta(dirp_get(r.dirp, c), d.W);
+      }
+      out[r.head[i]] = (uint8_t)(HEAD + 10 * i);
+    }
+  }
   if (sv.alive_counter) sv.alive_counter[e] = r.hdr->alive_counter;
   if (sv.episode_length) sv.episode_length[e] = (int32_t)r.hdr->episode_length;
   for (int i = 0; i < d.ns; ++i) {
@@ -1431,11 +1532,39 @@ __global__ void snk_get_state_kernel(const Dims d, const uint8_t* __restrict__ r
   }
 }
 
-__global__ void snk_set_state_kernel(const Dims d, uint8_t* __restrict__ recs, StateView sv) {
+__global__ void snk_set_state_kernel(const Dims d, uint8_t* __restrict__ recs, const uint8_t* __restrict__ base_grid,
+                                     uint32_t* __restrict__ err, StateView sv) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.N) return;
-  Rec r = rec_view(recs + (size_t)e * d.rec_bytes, d);
-  for (int c = 0; c < d.HW; ++c) r.grid[c] = sv.grid[(size_t)e * d.HW + c];
+  uint8_t* hb = recs + (size_t)e * d.hbm_rec_bytes;
+  Rec r = rec_view2(hb, hb + d.hbm_c0, d);
+  if (!d.compact) for (int c = 0; c < d.HW; ++c) r.grid[c] = sv.grid[(size_t)e * d.HW + c];
+  if (d.compact) {
+    // the record stores the fruit cells and the bodies; whatever else the caller's grid holds must be what they imply
+    const uint8_t* in = sv.grid + (size_t)e * d.HW;
+    int nf = 0;
+    bool bad = false;
+    for (int j = 0; j < d.fcap; ++j) r.fruit[j] = 0;
+    for (int c = 0; c < d.HW; ++c) {
+      const uint32_t code = in[c], kind = code % 10u;
+      if (code == (uint32_t)FRUIT) { if (nf < d.fcap) r.fruit[nf] = (uint16_t)(c + 1); ++nf; }
+      else if (kind < (uint32_t)HEAD) bad |= code != base_grid[c];                 // EMPTY / WALL: the handle's layout
+    }
+    bad |= nf > d.fcap;
+    for (int i = 0; i < d.ns && !bad; ++i) {                                      // every live body cell carries its code
+      const size_t o = (size_t)e * d.ns + i;
+      const int len = sv.alive[o] ? sv.length[o] : 0;
+      for (int k = 0; k < len; ++k) {
+        const int c = sv.cells[o * sv.max_cells + k];
+        bad |= (unsigned)c >= (unsigned)d.HW || in[c] != (k == 0 ? HEAD : k == len - 1 ? TAIL : BODY) + 10 * i;
+      }
+    }
+    int body = 0, want = 0;
+    for (int c = 0; c < d.HW; ++c) body += (in[c] % 10u) >= (uint32_t)HEAD;
+    for (int i = 0; i < d.ns; ++i) want += sv.alive[(size_t)e * d.ns + i] ? sv.length[(size_t)e * d.ns + i] : 0;
+    bad |= body != want;                                                          // no stray body cells either
+    if (bad) atomicOr(err, ERR_STATE);
+  }
   for (int i = 0; i < d.ns; ++i) {
     const size_t o = (size_t)e * d.ns + i;
     const int32_t* cl = sv.cells + o * sv.max_cells;
@@ -1483,7 +1612,7 @@ __global__ void __launch_bounds__(256) snk_pack_obs_kernel(const uint8_t* __rest
 }
 
 __global__ void snk_init_records_kernel(const Dims d, uint8_t* __restrict__ recs) {
-  const size_t n = (size_t)d.N * d.rec_bytes / 16;
+  const size_t n = (size_t)d.N * d.hbm_rec_bytes / 16;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     reinterpret_cast<uint4*>(recs)[i] = make_uint4(0, 0, 0, 0);
 }
@@ -1655,12 +1784,12 @@ cudaError_t launch_tile_kernel(const KParams& p, int threads, size_t smem_bytes,
   }
 }
 
-cudaError_t launch_get_state(const Dims& d, const uint8_t* recs, const StateView& sv, cudaStream_t s) {
-  snk_get_state_kernel<<<(d.N + 127) / 128, 128, 0, s>>>(d, recs, sv);
+cudaError_t launch_get_state(const Dims& d, const uint8_t* recs, const uint8_t* base_grid, const StateView& sv, cudaStream_t s) {
+  snk_get_state_kernel<<<(d.N + 127) / 128, 128, 0, s>>>(d, recs, base_grid, sv);
   return cudaGetLastError();
 }
-cudaError_t launch_set_state(const Dims& d, uint8_t* recs, const StateView& sv, cudaStream_t s) {
-  snk_set_state_kernel<<<(d.N + 127) / 128, 128, 0, s>>>(d, recs, sv);
+cudaError_t launch_set_state(const Dims& d, uint8_t* recs, const uint8_t* base_grid, uint32_t* err, const StateView& sv, cudaStream_t s) {
+  snk_set_state_kernel<<<(d.N + 127) / 128, 128, 0, s>>>(d, recs, base_grid, err, sv);
   return cudaGetLastError();
 }
 cudaError_t launch_pack_obs(const uint8_t* obs, uint8_t* bits, size_t n_units, cudaStream_t s) {

@@ -32,6 +32,8 @@ struct KParams {
   uint8_t* hist;               // [N, ns, fs, ohw_p] channel-bit frames (fs > 1 only)
   const uint64_t* spawn;       // [n_cand] packed spawn poses
   const uint32_t* wall_map;    // custom wall layout: the H*W cell codes (EMPTY / WALL) a reset starts from, as words; null = walled box
+  const uint8_t* base_grid;    // compact handles: the wall layout (walled box or custom map), off_c0 bytes per copy, as many
+                               //   copies back to back as a tile has environments -- one bulk copy paints a tile's grids
   const int32_t* replay;       // replay draws, all envs back to back
   const int64_t* replay_off;   // [N+1]
   uint32_t* err;               // sticky error bits
@@ -86,8 +88,8 @@ size_t pad_plane_bytes(const Dims& d, int tile_envs);     // ENC_PAD: padded pla
 size_t encode_blob_bytes(const Dims& d, size_t* tab_off, size_t* lutb_off);
 void encode_blob_fill(const Dims& d, uint8_t* out);
 cudaError_t launch_tile_kernel(const KParams& p, int threads, size_t smem_bytes, cudaStream_t stream);
-cudaError_t launch_get_state(const Dims& d, const uint8_t* recs, const StateView& sv, cudaStream_t s);
-cudaError_t launch_set_state(const Dims& d, uint8_t* recs, const StateView& sv, cudaStream_t s);
+cudaError_t launch_get_state(const Dims& d, const uint8_t* recs, const uint8_t* base_grid, const StateView& sv, cudaStream_t s);
+cudaError_t launch_set_state(const Dims& d, uint8_t* recs, const uint8_t* base_grid, uint32_t* err, const StateView& sv, cudaStream_t s);
 cudaError_t launch_init_records(const Dims& d, uint8_t* recs, cudaStream_t s);
 // obs: n_units * 8 bytes of 0/1 (16-byte aligned) -> bits: n_units bytes, bit c = byte c of the unit
 cudaError_t launch_pack_obs(const uint8_t* obs, uint8_t* bits, size_t n_units, cudaStream_t s);

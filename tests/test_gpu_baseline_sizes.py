@@ -96,13 +96,15 @@ REPLAY_KW = dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range
 REPLAY_N, REPLAY_T, REPLAY_BASE = 1024, 512, 4000
 
 
+@pytest.mark.parametrize('compact', ['0', '1'])
 @pytest.mark.parametrize('coop', ['0', '1'])
-def test_gpu_replay_at_scale(monkeypatch, coop):
+def test_gpu_replay_at_scale(monkeypatch, coop, compact):
     """1 024 envs x 512 steps of the cfg1/cfg5 shape in replay mode against the oracle's recorded
     trajectories, in both tile modes."""
     from replay_scale_util import check_replay_at_scale, oracle_trajectories
     envs = oracle_trajectories(REPLAY_KW, REPLAY_N, REPLAY_T, REPLAY_BASE)
     monkeypatch.setenv('SNK_COOP', coop)
+    monkeypatch.setenv('SNK_COMPACT', compact)             # both record layouts (HBM record with / without the grid)
     be = GpuBackend(REPLAY_N, REPLAY_KW, rng_mode=1, auto_reset=1)
     episodes = check_replay_at_scale(be, envs, REPLAY_T, unpack_obs)
     assert episodes > 4 * REPLAY_N                       # mean episode ~70 steps: every env restarts several times

@@ -11,9 +11,16 @@ from parity_util import check_against_oracle_philox, check_rollout_replay, check
 
 pytestmark = pytest.mark.gpu
 
+# Record layout in HBM: '1' = compact (no grid; rebuilt in shared memory from walls + fruit slots + bodies), '0' = the
+# whole working record.  By default the library picks per handle (compact for warp-private tiles, frame stacks and
+# large grids), so tests that mean to cover a layout force it.
+both_layouts = pytest.mark.parametrize('compact', ['0', '1'])
 
+
+@both_layouts
 @pytest.mark.parametrize('name', ROLLOUTS)
-def test_gpu_rollout_replay(name):
+def test_gpu_rollout_replay(monkeypatch, name, compact):
+    monkeypatch.setenv('SNK_COMPACT', compact)
     g = Rollout(name)
     be = GpuBackend(g.num_envs, g.kwargs, rng_mode=1, auto_reset=1, done_mode=g.done_mode)
     check_rollout_replay(be, g)
@@ -21,8 +28,10 @@ def test_gpu_rollout_replay(name):
     be.close()
 
 
+@both_layouts
 @pytest.mark.parametrize('sc', load_scenarios(), ids=lambda s: s.name)
-def test_gpu_scenarios(sc):
+def test_gpu_scenarios(monkeypatch, sc, compact):
+    monkeypatch.setenv('SNK_COMPACT', compact)
     kw = dict(height=sc.H, width=sc.W, num_snakes=sc.num_snakes, snake_length=2, **sc.kwargs)
     be = GpuBackend(1, kw, rng_mode=1, auto_reset=0)
     check_scenario(be, sc)
@@ -307,6 +316,7 @@ def test_gpu_rollout_stats():
     assert float(t[0]) == eps
 
 
+@both_layouts
 @pytest.mark.parametrize('coop', ['0', '1', '1-small'])
 @pytest.mark.parametrize('kw,N', [
     (dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5), 2051),
@@ -319,12 +329,13 @@ def test_gpu_rollout_stats():
     (dict(height=26, width=26, num_snakes=25, snake_length=2, num_fruits=30), 9),       # max snakes, full-grid obs
     (dict(height=9, width=9, num_snakes=1, snake_length=3, vision_range=2), 700),      # 32 envs per warp
 ])
-def test_gpu_tile_modes(monkeypatch, coop, kw, N):
+def test_gpu_tile_modes(monkeypatch, coop, kw, N, compact):
     """Both tile modes (warp-private tiles / CTA-cooperative tile; '1-small' = one environment per
     cooperative tile with 64 threads) against the host build of the rule source; by default the mode and the
     tile size are chosen from the batch size, so each is forced here."""
     from hostsim_util import HostSim
     monkeypatch.setenv('SNK_COOP', coop[0])
+    monkeypatch.setenv('SNK_COMPACT', compact)
     if coop == '1-small':
         monkeypatch.setenv('SNK_THREADS', '64')
         monkeypatch.setenv('SNK_TILE_ENVS', '1')
@@ -346,7 +357,9 @@ def test_gpu_tile_modes(monkeypatch, coop, kw, N):
 
 
 @pytest.mark.parametrize('knob', ['SNK_TMA=0', 'SNK_ENC_LEGACY=1', 'SNK_NO_TABLE=1', 'SNK_TMA=0,SNK_COOP=0', 'SNK_NO_DIG=1',
-                                  'SNK_NO_DIG=1,SNK_COOP=0'])
+                                  'SNK_NO_DIG=1,SNK_COOP=0', 'SNK_NO_COMPACT=1', 'SNK_COMPACT=0,SNK_COOP=0',
+                                  'SNK_COMPACT=1,SNK_COOP=1', 'SNK_COMPACT=1,SNK_TMA=0', 'SNK_COMPACT=1,SNK_TMA=0,SNK_COOP=0',
+                                  'SNK_COMPACT=0,SNK_TMA=0', 'SNK_COMPACT=1,SNK_ENC_LEGACY=1'])
 @pytest.mark.parametrize('kw,N', [
     (dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5), 1500),
     (dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5, frame_stack=4), 300),
@@ -429,12 +442,15 @@ FUZZ_SEED = int(__import__('os').environ.get('SNK_FUZZ_SEED', 20240611))
 
 
 @pytest.mark.parametrize('case', range(FUZZ_CASES))
-def test_gpu_fuzz_shapes(case):
+def test_gpu_fuzz_shapes(monkeypatch, case):
     """Seeded random shapes (grid 6..40, 1..12 snakes, length 2..6, vision None..8, frame_stack 1..5, fruit
     counts 0..32, step caps, both done rules and observers, odd batch sizes) against the host build of the rule
     source in Philox mode: every output of every step bit-exact."""
     from hostsim_util import HostSim
     kw, done_mode, N = _fuzz_configs(FUZZ_CASES, FUZZ_SEED)[case]
+    monkeypatch.setenv('SNK_COMPACT', str(case & 1))         # both record layouts ...
+    if case & 2:
+        monkeypatch.setenv('SNK_COOP', '0')                  # ... and warp-private tiles for half of the cases
     ns = kw['num_snakes']
     hs = HostSim(N, kw, rng_mode=0, auto_reset=1, seed=1000 + case, done_mode=done_mode)
     be = GpuBackend(N, kw, rng_mode=0, auto_reset=1, seed=1000 + case, done_mode=done_mode)
@@ -772,12 +788,14 @@ def test_gpu_step_host_info_matches_device_path(N):
     assert seen >= N * 2                                   # the step cap ended every env at least twice
 
 
+@both_layouts
 @pytest.mark.parametrize('kw', [dict(num_snakes=4, vision_range=5), dict(num_snakes=3, vision_range=3, frame_stack=4),
                                 dict(num_snakes=9, height=16, width=16, vision_range=2, max_episode_steps=15)])
-def test_gpu_exact_checkpoint_resume(kw):
+def test_gpu_exact_checkpoint_resume(monkeypatch, kw, compact):
     """snk_checkpoint_save / _load: a second batch continues bit for bit -- grid, frame history, episode
     statistics, Philox position and rollout statistics included."""
     from marl_snake_b200 import SnakeBatch, SnkError
+    monkeypatch.setenv('SNK_COMPACT', compact)
     N, ns = 700, kw['num_snakes']
     a, b = SnakeBatch(N, seed=44, **kw), SnakeBatch(N, seed=44, **kw)
     a.reset()
@@ -804,11 +822,17 @@ def test_gpu_exact_checkpoint_resume(kw):
     other = SnakeBatch(N + 1, seed=44, **kw)
     with pytest.raises(SnkError):
         other.load_checkpoint(blob)
+    monkeypatch.setenv('SNK_COMPACT', '1' if compact == '0' else '0')      # the other record layout: refused as well
+    other = SnakeBatch(N, seed=44, **kw)
+    with pytest.raises(SnkError):
+        other.load_checkpoint(blob)
 
 
-def test_gpu_state_roundtrip():
+@both_layouts
+def test_gpu_state_roundtrip(monkeypatch, compact):
     """get_state -> set_state on a second batch reproduces the trajectory (checkpoint / restore)."""
     from marl_snake_b200 import SnakeBatch
+    monkeypatch.setenv('SNK_COMPACT', compact)
     N, ns = 200, 4
     kw = dict(num_snakes=ns, vision_range=5, seed=17)
     a, b = SnakeBatch(N, **kw), SnakeBatch(N, seed=999, num_snakes=ns, vision_range=5)
@@ -831,6 +855,15 @@ def test_gpu_state_roundtrip():
     quiet = (~ia['finished']) & (a.get_state()['grid'] == b.get_state()['grid']).all(2).all(1)
     assert int(quiet.sum()) > N // 2
     assert torch.equal(oa[quiet], ob[quiet])
+    assert b.device_errors() == 0
+    # A compact record stores fruit cells and bodies only: a grid that is anything but walls + fruits + the given bodies
+    # cannot be represented and raises the sticky SNK_DEV_STATE bit (the full layout takes the grid as it is).
+    grid = st['grid'].cpu().numpy().copy()
+    stray = np.argwhere(grid[0] == 0)[0]
+    grid[0][tuple(stray)] = 4                                  # a BODY cell of snake 0 that no body accounts for
+    b.set_state(grid, st['alive'].cpu().numpy(), st['dir'].cpu().numpy(), st['length'].cpu().numpy(),
+                st['cells'].clamp(min=0).cpu().numpy(), st['alive_counter'].cpu().numpy(), st['episode_length'].cpu().numpy())
+    assert b.device_errors(clear=True) == (64 if compact == '1' else 0)
 
 
 BITS_CASES = [

@@ -61,16 +61,18 @@ def cross_map():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('compact', ['0', '1'])
 @pytest.mark.parametrize('coop', ['0', '1'])
 @pytest.mark.parametrize('kw,N,steps', [
     (dict(num_snakes=4, snake_length=3, vision_range=4), 40, 120),
     (dict(num_snakes=3, snake_length=4, frame_stack=2, num_fruits=6), 17, 90),
     (dict(num_snakes=8, snake_length=2, vision_range=3, max_episode_steps=40), 9, 90),     # direction-plane record
 ])
-def test_gpu_wall_map_philox_matches_oracle(monkeypatch, coop, kw, N, steps):
+def test_gpu_wall_map_philox_matches_oracle(monkeypatch, coop, kw, N, steps, compact):
     from gpu_backend import GpuBackend
     from parity_util import check_against_oracle_philox
     monkeypatch.setenv('SNK_COOP', coop)
+    monkeypatch.setenv('SNK_COMPACT', compact)
     walls = cross_map()
     kw = dict(height=walls.shape[0], width=walls.shape[1], wall_map=walls, **kw)
     be = check_against_oracle_philox(GpuBackend, kw, num_envs=N, steps=steps, seed=77, env_id_offset=11)

@@ -35,6 +35,7 @@ CONFIGS = {
     'cfg5_256k': dict(num_envs=262144, vision_range=5, **BASE),
     'cfg5_512k': dict(num_envs=524288, vision_range=5, **BASE),
     'cfg5_full': dict(num_envs=1048576, vision_range=5, **BASE),
+    'cfg5_n': dict(num_envs=int(os.environ.get('BENCH_N', 65536)), vision_range=5, **BASE),     # size sweeps
 }
 DEFAULT_STEPS = {'cfg2': 2000}
 
