@@ -83,7 +83,7 @@ struct snk_env {
   WidenPool* pool = nullptr;
   cudaEvent_t chunk_ev[XFER_MAX_CHUNKS] = {};
   int n_chunk_ev = 0;
-  int force_generic = 0, coop = 0, lut_dual = 0, use_tma = 0, enc_flavour = 0, pdl = 1;
+  int force_generic = 0, coop = 0, lut_dual = 0, use_tma = 0, enc_flavour = 0, pdl = 1, bigreg = 0;
   bool was_reset = false;
 };
 
@@ -106,7 +106,7 @@ static KParams base_params(const snk_env* h) {
   p.force_generic = h->force_generic;
   p.enc_blob = h->enc_blob; p.enc_blob_bytes = h->enc_blob_bytes; p.enc_tab_off = h->enc_tab_off; p.use_tab = h->use_tab;
   p.enc_lutb_off = h->enc_lutb_off;
-  p.lut_dual = h->lut_dual; p.coop = h->coop; p.use_tma = h->use_tma; p.pdl = h->pdl;
+  p.lut_dual = h->lut_dual; p.coop = h->coop; p.use_tma = h->use_tma; p.pdl = h->pdl; p.bigreg = h->bigreg;
   p.T = 1;
   p.enc_flavour = h->enc_flavour;
   p.enc_copy_bytes = (h->enc_flavour == ENC_LEGACY) ? h->enc_blob_bytes : h->enc_tab_off;     // LUT only
@@ -210,12 +210,14 @@ static int create_impl(const snk_config* c, const uint8_t* walls_host, snk_env**
   }
   // A coop tile may hold fewer environments than the rule warp has lane groups: shorter per-CTA latency
   // (the rule phase of one warp, then the tile's encode) and more rule warps in flight.  Shrink until a
-  // tile's observation block is <= 32 KB, and further while the launch would not fill every SM 16 times.
+  // tile's observation block is <= 64 KB (32 KB with a frame stack, where a warp encodes a whole environment), and
+  // further while the launch would not fill every SM 16 times.  (cfg4, 28.8 KB per environment: two environments per
+  // tile -- a full rule warp -- 0.108 ms against 0.121 ms with one, profiles/r02_ab_tiles.txt.)
   int EPW = env_int("SNK_TILE_ENVS", 0);
   if (EPW <= 0) {
     EPW = EPW_full;
     if (coop) {
-      while (EPW > 1 && (size_t)EPW * d.obs_env_bytes > 32 * 1024) EPW >>= 1;
+      while (EPW > 1 && (size_t)EPW * d.obs_env_bytes > (size_t)(d.fs > 1 ? 32 : 64) * 1024) EPW >>= 1;
       while (EPW > 1 && ((int64_t)d.N + EPW - 1) / EPW < 148 * 16) EPW >>= 1;
     }
   }
@@ -226,7 +228,9 @@ static int create_impl(const snk_config* c, const uint8_t* walls_host, snk_env**
   // frame_stack > 1 encodes one environment per warp, so more warps than environments would idle
   // (the padded-plane encode wants an even number of warps: with an odd window a warp then only ever sees viewer
   // blocks of one address parity and keeps one set of cell offsets in registers)
-  int threads = env_int("SNK_THREADS", !coop ? 32 : d.fs > 1 ? 32 * (EPW < 8 ? EPW : 8)
+  // (warp-private tiles: four warps per CTA share the encode tables and the per-CTA shared-memory overhead -- half
+  // a percent over single-warp CTAs at every batch size measured, profiles/r02_ab_tiles.txt)
+  int threads = env_int("SNK_THREADS", !coop ? 128 : d.fs > 1 ? 32 * (EPW < 8 ? EPW : 8)
                                        : encode_flavour(d, true) == ENC_PAD ? 128 : 96);
   const int max_threads = coop ? SNK_MAX_THREADS_COOP : SNK_MAX_THREADS;
   if (threads < 32 || threads > max_threads || (threads & 31)) { delete h; return fail(SNK_E_INVALID, "SNK_THREADS must be a multiple of 32 in 32..%d", max_threads); }
@@ -249,6 +253,11 @@ static int create_impl(const snk_config* c, const uint8_t* walls_host, snk_env**
   h->force_generic = env_int("SNK_FORCE_GENERIC", 0);
   h->use_tma = env_int("SNK_TMA", 1);
   h->pdl = env_int("SNK_PDL", 1);
+  {
+    // the uncapped-register instance of the warp-private kernel once the batch is many waves deep
+    const int64_t tiles = ((int64_t)d.N + EPW - 1) / EPW;
+    h->bigreg = (!coop && tiles >= (int64_t)env_int("SNK_BIGREG_TILES", 24576)) ? 1 : 0;
+  }
   h->smem_bytes = tile_smem_bytes(d, threads / 32, coop != 0, EPW);
   if (h->smem_bytes > 227 * 1024) {
     const size_t need = h->smem_bytes;

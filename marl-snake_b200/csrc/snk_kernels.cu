@@ -1182,10 +1182,14 @@ __device__ __forceinline__ void encode_env_stacked(const KParams& p, const SH& s
 // kVar: 0 the plain step (NHWC observation, one step per launch) -- the lean instance every benchmark line runs;
 //       1 channel-bit output as well / instead (snk_step_bits); 2 several steps per launch (snk_step_many), any output.
 //       The variants only differ in code that is compiled out of variant 0, which keeps its register count.
+//       3 the plain step again, compiled without a register cap (88 registers instead of 64): fewer resident warps, more
+//         loads in flight per warp -- 2 % faster once the batch is many waves deep (cfg5: 0.756 against 0.772 ms), 3.5 %
+//         slower on a 131 072-env shard (profiles/r02_ab_tiles3.txt); the launch picks by batch size (KParams::bigreg).
+// Warp-private instances of variants 0 and 1 are capped at 64 registers (eight 128-thread CTAs per SM).
 template <int kNS, int kW, int kOH, int kOW, int kFS, bool kCoop, int kEnc, int kVar>
-__global__ void __launch_bounds__(kCoop ? SNK_MAX_THREADS_COOP : SNK_MAX_THREADS)
+__global__ void __launch_bounds__(kCoop ? SNK_MAX_THREADS_COOP : SNK_MAX_THREADS, (!kCoop && kVar <= 1) ? 8 : (!kCoop && kVar == 3) ? 1 : 0)
 snk_tile_kernel(const __grid_constant__ KParams p) {
-  constexpr bool kBits = kVar >= 1, kMulti = kVar == 2;
+  constexpr bool kBits = kVar == 1 || kVar == 2, kMulti = kVar == 2;
   uint8_t* const bits_out = kBits ? p.bits : nullptr;
   extern __shared__ __align__(16) uint8_t smem[];
   const Dims& d = p.d;
@@ -1748,6 +1752,9 @@ template <int kNS, int kW, int kOH, int kOW, int kFS, bool kCoop, int kEnc>
 static cudaError_t launch_instance(const KParams& p, int threads, size_t smem_bytes, cudaStream_t stream) {
   if (p.T > 1) return launch_variant<kNS, kW, kOH, kOW, kFS, kCoop, kEnc, 2>(p, threads, smem_bytes, stream);
   if (p.bits) return launch_variant<kNS, kW, kOH, kOW, kFS, kCoop, kEnc, 1>(p, threads, smem_bytes, stream);
+  if constexpr (!kCoop) {
+    if (p.bigreg) return launch_variant<kNS, kW, kOH, kOW, kFS, kCoop, kEnc, 3>(p, threads, smem_bytes, stream);
+  }
   return launch_variant<kNS, kW, kOH, kOW, kFS, kCoop, kEnc, 0>(p, threads, smem_bytes, stream);
 }
 
