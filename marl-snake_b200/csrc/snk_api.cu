@@ -75,7 +75,8 @@ struct snk_env {
   uint8_t* h_fin = nullptr; int32_t* h_rank = nullptr; double* h_scores = nullptr; int32_t* h_counts = nullptr;   // [3][N, ns]
   // few environments: every output of a host-buffer step lives in ONE device block mirrored by ONE pinned host
   // block, so the step costs one copy in, one launch, one copy out (the latency-bound drop-in mode)
-  uint8_t* small_dev = nullptr; uint8_t* small_host = nullptr;
+  uint8_t* small_dev = nullptr; uint8_t* small_host = nullptr; uint8_t* small_map = nullptr;
+  int small_zero_copy = 1;
   cudaStream_t own_stream = nullptr;
   // packed host transport (snk_hostxfer.cpp): device channel-bit mirror, pinned staging, widening pool
   int xfer_mode = XFER_RAW, xfer_threads = 0;
@@ -253,6 +254,7 @@ static int create_impl(const snk_config* c, const uint8_t* walls_host, snk_env**
   h->force_generic = env_int("SNK_FORCE_GENERIC", 0);
   h->use_tma = env_int("SNK_TMA", 1);
   h->pdl = env_int("SNK_PDL", 1);
+  h->small_zero_copy = env_int("SNK_SMALL_ZEROCOPY", 1);
   {
     // the uncapped-register instance of the warp-private kernel once the batch is many waves deep
     const int64_t tiles = ((int64_t)d.N + EPW - 1) / EPW;
@@ -279,10 +281,11 @@ static int create_impl(const snk_config* c, const uint8_t* walls_host, snk_env**
     CUH(cudaMalloc(&h->wall_map, walls.size()));
     CUH(cudaMemcpy(h->wall_map, walls.data(), walls.size(), cudaMemcpyHostToDevice));
   }
-  if (d.compact) {
-    // the grid every record implies starts from the wall layout: make_grid's walled box (core/grid_util.py:14-20) or
-    // the custom map; as many copies as the widest tile has environments, so ONE bulk copy paints a tile's grids
-    const int copies = h->tile_envs > h->many_tile_envs ? h->tile_envs : h->many_tile_envs;
+  {
+    // the wall layout every reset starts from: make_grid's walled box (core/grid_util.py:14-20) or the custom map,
+    // padded to 16 bytes.  Compact records: it is also what the grid every record implies starts from -- as many
+    // copies as the widest tile has environments, so ONE bulk copy paints a tile's grids
+    const int copies = !d.compact ? 1 : h->tile_envs > h->many_tile_envs ? h->tile_envs : h->many_tile_envs;
     std::vector<uint8_t> tpl((size_t)copies * d.off_c0, 0);
     for (int i = 0; i < d.HW; ++i) tpl[i] = wm ? wm[i] : wall_or_empty(i, d.H, d.W);
     for (int k = 1; k < copies; ++k) memcpy(tpl.data() + (size_t)k * d.off_c0, tpl.data(), (size_t)d.off_c0);
@@ -574,13 +577,24 @@ static int step_host_small(snk_env* h, const SmallLayout& L, const uint8_t* acti
   const Dims& d = h->d;
   const size_t nn = (size_t)d.N * d.ns;
   cudaStream_t s = h->own_stream;
-  if (!h->small_dev) CU(cudaMalloc(&h->small_dev, L.total));
-  if (!h->small_host) CU(cudaMallocHost(&h->small_host, L.total));
-  uint8_t* dv = h->small_dev;
+  // Zero-copy (default): the block is pinned host memory mapped into the device's address space; the kernel reads
+  // the actions from it and writes every output to it over PCIe, so a step is one launch and one synchronise --
+  // no copy commands at all (a few KB per step; SNK_SMALL_ZEROCOPY=0 restores copy in / launch / copy out).
+  const bool zero_copy = h->small_zero_copy != 0;
+  if (!h->small_host) {
+    if (zero_copy) {
+      CU(cudaHostAlloc((void**)&h->small_host, L.total, cudaHostAllocMapped));
+      CU(cudaHostGetDevicePointer((void**)&h->small_map, h->small_host, 0));
+    } else {
+      CU(cudaMallocHost(&h->small_host, L.total));
+    }
+  }
+  if (!zero_copy && !h->small_dev) CU(cudaMalloc(&h->small_dev, L.total));
+  uint8_t* dv = zero_copy ? h->small_map : h->small_dev;
   uint8_t* hv = h->small_host;
   memcpy(hv + L.act, actions_host, nn);
   { int rc0 = own_stream_after_user_work(h); if (rc0) return rc0; }
-  CU(cudaMemcpyAsync(dv + L.act, hv + L.act, nn, cudaMemcpyHostToDevice, s));
+  if (!zero_copy) CU(cudaMemcpyAsync(dv + L.act, hv + L.act, nn, cudaMemcpyHostToDevice, s));
   snk_step_extra xd;
   memset(&xd, 0, sizeof xd);
   if (xh) {
@@ -590,7 +604,7 @@ static int step_host_small(snk_env* h, const SmallLayout& L, const uint8_t* acti
   int rc = step_impl(h, dv + L.act, obs_host ? dv + L.obs : nullptr, nullptr, (double*)(dv + L.rew), dv + L.done, xh ? &xd : nullptr, s);
   if (rc) return rc;
   const size_t lo = obs_host ? L.obs : L.rew, hi = xh ? L.total : L.fin;
-  CU(cudaMemcpyAsync(hv + lo, dv + lo, hi - lo, cudaMemcpyDeviceToHost, s));
+  if (!zero_copy) CU(cudaMemcpyAsync(hv + lo, dv + lo, hi - lo, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   if (obs_host) memcpy(obs_host, hv + L.obs, (size_t)d.N * d.obs_env_bytes);
   memcpy(rewards_host, hv + L.rew, nn * sizeof(double));

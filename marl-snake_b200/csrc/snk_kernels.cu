@@ -119,12 +119,39 @@ __device__ __noinline__ void place_fruits_warp(const KParams& p, uint8_t* g, uin
     if (4 * w + 4 > HW) x |= 0xFFFFFFFFu << (8 * (HW - 4 * w));           // bytes past the grid are not cells
     return zero_bytes(x);
   };
+  // Lane ranges that are whole 16-byte units (cw a multiple of 4; cfg5: one unit per lane, cfg4: eight) are scanned
+  // four words per load: a quarter of the dependent shared-memory round trips in the count pass and in the walk.
+  const bool vec = (cw & 3) == 0;
+  const int c4 = cw >> 2;
+  const uint4* gw4 = reinterpret_cast<const uint4*>(r.grid);
+  auto load_zeros4 = [&](int u) -> uint4 {                                // zero-byte flags of words 4u .. 4u + 3
+    const int lim = HW - 16 * u;                                          // grid bytes left from this unit on
+    if (lim <= 0) return make_uint4(0u, 0u, 0u, 0u);
+    uint4 x = gw4[u];                                                     // the grid area is padded to 16 bytes
+    if (lim < 16) {
+      x.x |= lim >= 4 ? 0u : 0xFFFFFFFFu << (8 * lim);
+      x.y |= lim >= 8 ? 0u : lim <= 4 ? 0xFFFFFFFFu : 0xFFFFFFFFu << (8 * (lim - 4));
+      x.z |= lim >= 12 ? 0u : lim <= 8 ? 0xFFFFFFFFu : 0xFFFFFFFFu << (8 * (lim - 8));
+      x.w |= lim <= 12 ? 0xFFFFFFFFu : 0xFFFFFFFFu << (8 * (lim - 12));
+    }
+    return make_uint4(zero_bytes(x.x), zero_bytes(x.y), zero_bytes(x.z), zero_bytes(x.w));
+  };
   uint32_t cnt = 0;
-  const int rot = (int)lane % cw;                                        // rotate: lanes start in different banks
-  for (int j = 0; j < cw; ++j) {
-    int jj = j + rot;
-    jj -= (jj >= cw) ? cw : 0;
-    cnt += (uint32_t)__popc(load_zeros((int)lane * cw + jj));
+  if (vec) {
+    const int rot = (int)lane % c4;                                      // rotate: a quarter-warp's loads hit distinct banks
+    for (int j = 0; j < c4; ++j) {
+      int jj = j + rot;
+      jj -= (jj >= c4) ? c4 : 0;
+      const uint4 z = load_zeros4((int)lane * c4 + jj);
+      cnt += (uint32_t)(__popc(z.x) + __popc(z.y) + __popc(z.z) + __popc(z.w));
+    }
+  } else {
+    const int rot = (int)lane % cw;                                      // rotate: lanes start in different banks
+    for (int j = 0; j < cw; ++j) {
+      int jj = j + rot;
+      jj -= (jj >= cw) ? cw : 0;
+      cnt += (uint32_t)__popc(load_zeros((int)lane * cw + jj));
+    }
   }
   const uint32_t incl = warp_inclusive_sum(cnt, lane);
   const int n_empty = (int)__shfl_sync(FULL, incl, 31);
@@ -160,7 +187,23 @@ __device__ __noinline__ void place_fruits_warp(const KParams& p, uint8_t* g, uin
     }
     const int owner = lo;                                                 // first lane whose prefix exceeds the rank
     uint32_t rr = key - __shfl_sync(FULL, incl - cnt, owner);             // rank inside the owner's word range
-    if (rank >= 0) {
+    if (rank >= 0 && vec) {
+#pragma unroll 1
+      for (int t = 0; t < c4; ++t) {
+        const uint4 z4 = load_zeros4(owner * c4 + t);
+        const uint32_t p0 = (uint32_t)__popc(z4.x), p1 = p0 + (uint32_t)__popc(z4.y), p2 = p1 + (uint32_t)__popc(z4.z);
+        const uint32_t c = p2 + (uint32_t)__popc(z4.w);
+        if (rr < c) {
+          const int k = (int)(p0 <= rr) + (int)(p1 <= rr) + (int)(p2 <= rr);          // word of the unit
+          const uint32_t z = k == 0 ? z4.x : k == 1 ? z4.y : k == 2 ? z4.z : z4.w;
+          rr -= k == 0 ? 0u : k == 1 ? p0 : k == 2 ? p1 : p2;
+          const uint32_t c0 = (z >> 7) & 1u, c1 = c0 + ((z >> 15) & 1u), c2 = c1 + ((z >> 23) & 1u);
+          mycell = 4 * (4 * (owner * c4 + t) + k) + (int)((c0 <= rr) + (c1 <= rr) + (c2 <= rr));
+          break;
+        }
+        rr -= c;
+      }
+    } else if (rank >= 0) {
 #pragma unroll 1
       for (int t = 0; t < cw; ++t) {
         const uint32_t z = load_zeros(owner * cw + t);
@@ -239,7 +282,21 @@ __device__ __noinline__ void reset_env_warp(const KParams& p, uint8_t* g, uint8_
   if (d.compact && (int)lane < d.fcap) r.fruit[lane] = 0;
   // make_grid: walled empty box (core/grid_util.py:14-20), one grid row at a time so no division is needed --
   // or the handle's custom wall layout (snk_create_map), copied word by word from its L2-resident plane
-  if (p.wall_map) {
+  if (p.base_grid) {                   // the handle's wall layout (walled box or custom map), 16 bytes per lane and trip
+    const uint4* const tpl = reinterpret_cast<const uint4*>(p.base_grid);
+    uint4* g4 = reinterpret_cast<uint4*>(r.grid);
+    const int n16 = d.off_c0 >> 4;
+    for (int j = (int)lane; j < n16; j += 128) {            // four L2 loads in flight per lane
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      const uint4 a = __ldg(tpl + j);
+      const uint4 b = j + 32 < n16 ? __ldg(tpl + j + 32) : z, c = j + 64 < n16 ? __ldg(tpl + j + 64) : z;
+      const uint4 e = j + 96 < n16 ? __ldg(tpl + j + 96) : z;
+      g4[j] = a;
+      if (j + 32 < n16) g4[j + 32] = b;
+      if (j + 64 < n16) g4[j + 64] = c;
+      if (j + 96 < n16) g4[j + 96] = e;
+    }
+  } else if (p.wall_map) {
     const uint32_t* const wm = p.wall_map;
     const int HW = d.HW, nfull = HW >> 2;
     uint32_t* gw = reinterpret_cast<uint32_t*>(r.grid);

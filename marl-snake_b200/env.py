@@ -425,6 +425,9 @@ class SnakeEnv:
         self._xh = SnkStepExtra(self._h_fin.ctypes.data, self._h_rank.ctypes.data, self._h_scores.ctypes.data,
                                 self._h_counts[0].ctypes.data, self._h_counts[1].ctypes.data,
                                 self._h_counts[2].ctypes.data)
+        # the buffers never move: their addresses (and the handle) are converted for ctypes once, not on every step
+        self._step_args = (self._batch._h,) + tuple(x.ctypes.data_as(C.c_void_p) for x in
+                                                    (self._h_act, self._h_obs, self._h_rew, self._h_done)) + (C.byref(self._xh),)
 
     @property
     def unwrapped(self):
@@ -464,16 +467,14 @@ class SnakeEnv:
                     raise KeyError(ac)                                                    # snake_env.py:606
                 ac = 0
             self._h_act[0, i] = int(ac)
-        p = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
-        check(lib.snk_step_host_info(self._batch._h, p(self._h_act), p(self._h_obs), p(self._h_rew), p(self._h_done),
-                                     C.byref(self._xh)))
+        check(lib.snk_step_host_info(*self._step_args))
         info = {}
         if self._h_fin[0]:
             info['rank'] = [int(r) for r in self._h_rank[0]]
             info['episode_scores'] = self._h_scores[0].copy()
             for k, name in enumerate(('episode_steps', 'episode_fruits', 'episode_kills')):
                 info[name] = self._h_counts[k, 0].astype(np.float64)
-        return (self._h_obs[0].copy(), [float(r) for r in self._h_rew[0]], [bool(d) for d in self._h_done[0]], info)
+        return (self._h_obs[0].copy(), self._h_rew[0].tolist(), self._h_done[0].astype(bool).tolist(), info)
 
     @property
     def grid(self):

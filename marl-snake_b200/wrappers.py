@@ -148,6 +148,9 @@ class VectorSnakeEnv:
             self._xh = SnkStepExtra(self._h_fin.ctypes.data, self._h_rank.ctypes.data, self._h_scores.ctypes.data,
                                     self._h_counts[0].ctypes.data, self._h_counts[1].ctypes.data,
                                     self._h_counts[2].ctypes.data)
+            # the buffers never move: convert their addresses for ctypes once, not on every step
+            self._step_args = (b._h,) + tuple(x.ctypes.data_as(C.c_void_p) for x in
+                                              (self._h_act, self._h_obs, self._h_rew, self._h_done)) + (C.byref(self._xh),)
 
     def _squeeze(self, x):
         return x[:, 0] if self.num_snakes == 1 else x
@@ -183,9 +186,7 @@ class VectorSnakeEnv:
         elif self.batch.observer == 'human':
             a = np.where((a < 0) | (a > 4), 0, a)
         self._h_act[...] = a
-        p = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
-        check(lib.snk_step_host_info(self.batch._h, p(self._h_act), p(self._h_obs), p(self._h_rew), p(self._h_done),
-                                     C.byref(self._xh)))
+        check(lib.snk_step_host_info(*self._step_args))
         infos = [{} for _ in range(self.num_envs)]
         if self.num_snakes > 1 and self._h_fin.any():
             for e in np.nonzero(self._h_fin)[0]:
