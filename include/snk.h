@@ -58,7 +58,7 @@ enum {
   SNK_DEV_TMA_TIMEOUT = 32,      /* a record tile's bulk copy did not complete within 2 s; that tile was not stepped */
   SNK_DEV_STATE = 64             /* snk_set_state: the grid is not the handle's walls + fruit cells + the live snakes'
                                     bodies (the resident record stores only those), or it holds more fruit cells than
-                                    the record has slots (num_fruits + num_snakes, rounded up to 8, at most 32)       */
+                                    the record has slots (num_fruits + num_snakes, rounded up to 8)       */
 };
 
 enum { SNK_RNG_PHILOX = 0, SNK_RNG_REPLAY = 1 };

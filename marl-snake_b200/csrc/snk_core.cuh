@@ -104,8 +104,7 @@ inline void finalize_layout(Dims& d) {
   d.off_fruit = d.off_stats + round_up((8 + (d.stat16 ? 6 : 12)) * d.ns, 16);
   // A step can add a fruit without removing one (two heads meeting on a fruit: both die, the fruit stays and one more
   // is drawn, C3) -- at most once per two deaths, so nfruits + ns / 2 cells bound an episode; ns more for set_state
-  d.fcap = d.compact ? round_up(d.nfruits + d.ns, 8) : 0;
-  if (d.fcap > 32) d.fcap = 32;                 // one warp lane per slot (nfruits <= 32)
+  d.fcap = d.compact ? round_up(d.nfruits + d.ns, 8) : 0;      // <= 32 + 25 -> at most 64: two slots per warp lane
   d.rec_bytes = d.off_fruit + round_up(2 * d.fcap, 16);
   d.hbm_rec_bytes = d.compact ? d.rec_bytes - d.off_c0 : d.rec_bytes;
   d.hbm_c0 = d.compact ? 0 : d.off_c0;

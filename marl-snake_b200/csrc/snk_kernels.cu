@@ -41,9 +41,10 @@ __device__ const uint8_t* dbg_hist_lo; __device__ const uint8_t* dbg_hist_hi;
 __device__ const uint8_t* dbg_bits_lo; __device__ const uint8_t* dbg_bits_hi;
 __device__ uint32_t* dbg_err;
 __device__ __forceinline__ void dbg_arm(const KParams& p) {        // every thread writes the same values
-  dbg_obs_lo = p.obs; dbg_obs_hi = p.obs ? p.obs + (size_t)p.d.N * p.d.obs_env_bytes : nullptr;
+  const size_t blocks = (p.T > 1 && p.obs_every_step) ? (size_t)p.T : 1;      // snk_step_many: one block per step
+  dbg_obs_lo = p.obs; dbg_obs_hi = p.obs ? p.obs + blocks * p.d.N * p.d.obs_env_bytes : nullptr;
   dbg_hist_lo = p.hist; dbg_hist_hi = p.hist ? p.hist + (size_t)p.d.N * p.d.hist_env_bytes : nullptr;
-  dbg_bits_lo = p.bits; dbg_bits_hi = p.bits ? p.bits + (size_t)p.d.N * p.d.stage_env_bytes : nullptr;
+  dbg_bits_lo = p.bits; dbg_bits_hi = p.bits ? p.bits + blocks * p.d.N * p.d.stage_env_bytes : nullptr;
   dbg_err = p.err;
 }
 __device__ __forceinline__ void dbg_store(const void* q, size_t n, const uint8_t* lo, const uint8_t* hi) {
@@ -251,10 +252,13 @@ __device__ __noinline__ void place_fruits_warp(const KParams& p, uint8_t* g, uin
     const uint32_t dup = __match_any_sync(FULL, mycell);
     const bool adds = mycell >= 0 && (__ffs(dup) - 1) == (int)lane;
     const uint32_t adders = __ballot_sync(FULL, adds);
-    const uint32_t freem = __ballot_sync(FULL, (int)lane < fcap && r.fruit[lane] == 0);
+    const uint32_t free_lo = __ballot_sync(FULL, (int)lane < fcap && r.fruit[lane] == 0);              // slots 0..31
+    const uint32_t free_hi = __ballot_sync(FULL, (int)lane + 32 < fcap && r.fruit[lane + 32] == 0);    // slots 32..63
     if (adds) {
-      const uint32_t slot = __fns(freem, 0, __popc(adders & ((1u << lane) - 1u)) + 1);
-      if (slot < 32u) r.fruit[slot] = (uint16_t)(mycell + 1);
+      const int a = __popc(adders & ((1u << lane) - 1u)), nlo = __popc(free_lo);
+      uint32_t slot = a < nlo ? __fns(free_lo, 0, a + 1) : __fns(free_hi, 0, a - nlo + 1);     // 0xffffffff: none left
+      if (a >= nlo && slot < 32u) slot += 32u;
+      if (slot < (uint32_t)fcap) r.fruit[slot] = (uint16_t)(mycell + 1);
       else atomicOr(p.err, ERR_STATE);
     }
   }
@@ -279,7 +283,7 @@ __device__ __noinline__ void reset_env_warp(const KParams& p, uint8_t* g, uint8_
   const uint32_t n_cand = d.n_cand, inv_row_words = p.inv_row_words;
   const uint64_t* const spawn = p.spawn;
   SNK_R(0);
-  if (d.compact && (int)lane < d.fcap) r.fruit[lane] = 0;
+  if (d.compact) for (int j = (int)lane; j < d.fcap; j += 32) r.fruit[j] = 0;
   // make_grid: walled empty box (core/grid_util.py:14-20), one grid row at a time so no division is needed --
   // or the handle's custom wall layout (snk_create_map), copied word by word from its L2-resident plane
   if (p.base_grid) {                   // the handle's wall layout (walled box or custom map), 16 bytes per lane and trip
@@ -1250,13 +1254,13 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   uint8_t* const bits_out = kBits ? p.bits : nullptr;
   extern __shared__ __align__(16) uint8_t smem[];
   const Dims& d = p.d;
-#ifdef SNK_DEBUG_CHECKS
-  dbg_arm(p);
-#endif
   const Shape<kNS, kW, kOH, kOW, kFS> sh(d);
   // Programmatic dependent launch: nothing above touches global memory.  Wait for the grid this one depends on (the
   // previous step; a no-op for an ordinary launch), then let the next step's CTAs be scheduled behind this grid's.
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef SNK_DEBUG_CHECKS
+  dbg_arm(p);       // after the wait: the bounds are device globals, and the previous step (maybe of another handle) still runs before it
+#endif
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   SNK_T(t_start);
   const int tid = threadIdx.x, nt = blockDim.x;

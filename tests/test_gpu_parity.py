@@ -328,6 +328,9 @@ def test_gpu_rollout_stats():
     (dict(height=30, width=30, num_snakes=20, snake_length=3, vision_range=4), 21),   # one env per warp, dual LUT
     (dict(height=26, width=26, num_snakes=25, snake_length=2, num_fruits=30), 9),       # max snakes, full-grid obs
     (dict(height=9, width=9, num_snakes=1, snake_length=3, vision_range=2), 700),      # 32 envs per warp
+    # 32 fruits and 12 snakes: head-on meetings on fruit cells push the fruit count past num_fruits (C3) -- more than
+    # 32 fruit slots in a compact record
+    (dict(height=24, width=34, num_snakes=12, snake_length=3, vision_range=4, num_fruits=32, max_episode_steps=12), 130),
 ])
 def test_gpu_tile_modes(monkeypatch, coop, kw, N, compact):
     """Both tile modes (warp-private tiles / CTA-cooperative tile; '1-small' = one environment per

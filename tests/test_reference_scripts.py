@@ -39,7 +39,8 @@ def test_harness_on_the_unmodified_reference(scenario, tmp_path):
 @pytest.mark.parametrize('scenario', SCENARIOS)
 def test_reference_scripts_run_on_the_cuda_path(scenario, tmp_path):
     out = run('ours', scenario, tmp_path)
-    assert any(s.endswith('libsnk.so') for s in out['native_so']), out
+    lib_name = os.path.basename(os.environ.get('SNK_LIB_PATH', 'libsnk.so'))      # e.g. libsnk_dbg.so, the debug-checks build
+    assert any(s.endswith(lib_name) for s in out['native_so']), out
     if scenario == 'test_env':
         assert out['gui_calls'].get('imshow', 0) == out['steps']       # one window frame per env step (RenderGUI)
     if scenario == 'train_dqn':
