@@ -232,7 +232,7 @@ static int create_impl(const snk_config* c, const uint8_t* walls_host, snk_env**
   // (warp-private tiles: four warps per CTA share the encode tables and the per-CTA shared-memory overhead -- half
   // a percent over single-warp CTAs at every batch size measured, profiles/r02_ab_tiles.txt)
   int threads = env_int("SNK_THREADS", !coop ? 128 : d.fs > 1 ? 32 * (EPW < 8 ? EPW : 8)
-                                       : encode_flavour(d, true) == ENC_PAD ? 128 : 96);
+                                       : encode_flavour(d, true) == ENC_PAD ? 128 : 64);    // 64: cfg2 0.0177 ms against 0.0199 at 96 (r02_ab_coop_threads.txt)
   const int max_threads = coop ? SNK_MAX_THREADS_COOP : SNK_MAX_THREADS;
   if (threads < 32 || threads > max_threads || (threads & 31)) { delete h; return fail(SNK_E_INVALID, "SNK_THREADS must be a multiple of 32 in 32..%d", max_threads); }
   // large grids: fewer environments per tile until two CTAs fit an SM, then fewer warps if it still does not fit
