@@ -96,6 +96,26 @@ __device__ __forceinline__ uint32_t warp_inclusive_sum(uint32_t v, uint32_t lane
   return v;
 }
 
+// Compact records: the new fruit cells of a placement also go into the record's slot list (duplicate draws collapse to
+// one cell, one slot): the a-th distinct new cell takes the a-th free slot.  Out of line on purpose -- inlined into
+// place_fruits_warp its live values raised the register count of every kernel instance.
+__device__ __noinline__ void fruit_slots_add(uint16_t* fruit, int fcap, int mycell, uint32_t* err) {
+  const uint32_t FULL = 0xffffffffu;
+  const uint32_t lane = lane_id();
+  const uint32_t dup = __match_any_sync(FULL, mycell);
+  const bool adds = mycell >= 0 && (__ffs(dup) - 1) == (int)lane;
+  const uint32_t adders = __ballot_sync(FULL, adds);
+  const uint32_t free_lo = __ballot_sync(FULL, (int)lane < fcap && fruit[lane] == 0);              // slots 0..31
+  const uint32_t free_hi = __ballot_sync(FULL, (int)lane + 32 < fcap && fruit[lane + 32] == 0);    // slots 32..63
+  if (adds) {
+    const int a = __popc(adders & ((1u << lane) - 1u)), nlo = __popc(free_lo);
+    uint32_t slot = a < nlo ? __fns(free_lo, 0, a + 1) : __fns(free_hi, 0, a - nlo + 1);     // 0xffffffff: none left
+    if (a >= nlo && slot < 32u) slot += 32u;
+    if (slot < (uint32_t)fcap) fruit[slot] = (uint16_t)(mycell + 1);
+    else atomicOr(err, ERR_STATE);
+  }
+}
+
 // Place k fruits on the k drawn ranks of the row-major empty-cell list (all ranks refer to the
 // grid as it is before any of them is placed; duplicates collapse)    core/grid_util.py:126-133
 // The grid is scanned as 32-bit words (four cells): lane l owns the contiguous word range
@@ -120,39 +140,15 @@ __device__ __noinline__ void place_fruits_warp(const KParams& p, uint8_t* g, uin
     if (4 * w + 4 > HW) x |= 0xFFFFFFFFu << (8 * (HW - 4 * w));           // bytes past the grid are not cells
     return zero_bytes(x);
   };
-  // Lane ranges that are whole 16-byte units (cw a multiple of 4; cfg5: one unit per lane, cfg4: eight) are scanned
-  // four words per load: a quarter of the dependent shared-memory round trips in the count pass and in the walk.
-  const bool vec = (cw & 3) == 0;
-  const int c4 = cw >> 2;
-  const uint4* gw4 = reinterpret_cast<const uint4*>(r.grid);
-  auto load_zeros4 = [&](int u) -> uint4 {                                // zero-byte flags of words 4u .. 4u + 3
-    const int lim = HW - 16 * u;                                          // grid bytes left from this unit on
-    if (lim <= 0) return make_uint4(0u, 0u, 0u, 0u);
-    uint4 x = gw4[u];                                                     // the grid area is padded to 16 bytes
-    if (lim < 16) {
-      x.x |= lim >= 4 ? 0u : 0xFFFFFFFFu << (8 * lim);
-      x.y |= lim >= 8 ? 0u : lim <= 4 ? 0xFFFFFFFFu : 0xFFFFFFFFu << (8 * (lim - 4));
-      x.z |= lim >= 12 ? 0u : lim <= 8 ? 0xFFFFFFFFu : 0xFFFFFFFFu << (8 * (lim - 8));
-      x.w |= lim <= 12 ? 0xFFFFFFFFu : 0xFFFFFFFFu << (8 * (lim - 12));
-    }
-    return make_uint4(zero_bytes(x.x), zero_bytes(x.y), zero_bytes(x.z), zero_bytes(x.w));
-  };
+  // (A four-words-per-load variant of this scan and of the walk below cut the fruit seeding of a cfg4 reset from 7.0
+  //  to 4.6 us, but its live values raised the register count of every kernel instance -- cfg2 48 -> 62, cfg4 64 -> 78,
+  //  cfg5 88 -> 94 -- and the step times did not improve: removed again, profiles/README.md.)
   uint32_t cnt = 0;
-  if (vec) {
-    const int rot = (int)lane % c4;                                      // rotate: a quarter-warp's loads hit distinct banks
-    for (int j = 0; j < c4; ++j) {
-      int jj = j + rot;
-      jj -= (jj >= c4) ? c4 : 0;
-      const uint4 z = load_zeros4((int)lane * c4 + jj);
-      cnt += (uint32_t)(__popc(z.x) + __popc(z.y) + __popc(z.z) + __popc(z.w));
-    }
-  } else {
-    const int rot = (int)lane % cw;                                      // rotate: lanes start in different banks
-    for (int j = 0; j < cw; ++j) {
-      int jj = j + rot;
-      jj -= (jj >= cw) ? cw : 0;
-      cnt += (uint32_t)__popc(load_zeros((int)lane * cw + jj));
-    }
+  const int rot = (int)lane % cw;                                        // rotate: lanes start in different banks
+  for (int j = 0; j < cw; ++j) {
+    int jj = j + rot;
+    jj -= (jj >= cw) ? cw : 0;
+    cnt += (uint32_t)__popc(load_zeros((int)lane * cw + jj));
   }
   const uint32_t incl = warp_inclusive_sum(cnt, lane);
   const int n_empty = (int)__shfl_sync(FULL, incl, 31);
@@ -188,23 +184,7 @@ __device__ __noinline__ void place_fruits_warp(const KParams& p, uint8_t* g, uin
     }
     const int owner = lo;                                                 // first lane whose prefix exceeds the rank
     uint32_t rr = key - __shfl_sync(FULL, incl - cnt, owner);             // rank inside the owner's word range
-    if (rank >= 0 && vec) {
-#pragma unroll 1
-      for (int t = 0; t < c4; ++t) {
-        const uint4 z4 = load_zeros4(owner * c4 + t);
-        const uint32_t p0 = (uint32_t)__popc(z4.x), p1 = p0 + (uint32_t)__popc(z4.y), p2 = p1 + (uint32_t)__popc(z4.z);
-        const uint32_t c = p2 + (uint32_t)__popc(z4.w);
-        if (rr < c) {
-          const int k = (int)(p0 <= rr) + (int)(p1 <= rr) + (int)(p2 <= rr);          // word of the unit
-          const uint32_t z = k == 0 ? z4.x : k == 1 ? z4.y : k == 2 ? z4.z : z4.w;
-          rr -= k == 0 ? 0u : k == 1 ? p0 : k == 2 ? p1 : p2;
-          const uint32_t c0 = (z >> 7) & 1u, c1 = c0 + ((z >> 15) & 1u), c2 = c1 + ((z >> 23) & 1u);
-          mycell = 4 * (4 * (owner * c4 + t) + k) + (int)((c0 <= rr) + (c1 <= rr) + (c2 <= rr));
-          break;
-        }
-        rr -= c;
-      }
-    } else if (rank >= 0) {
+    if (rank >= 0) {
 #pragma unroll 1
       for (int t = 0; t < cw; ++t) {
         const uint32_t z = load_zeros(owner * cw + t);
@@ -245,23 +225,7 @@ __device__ __noinline__ void place_fruits_warp(const KParams& p, uint8_t* g, uin
   __syncwarp();
   SNK_ASSERT(p, mycell < HW);
   if (mycell >= 0) r.grid[mycell] = (uint8_t)FRUIT;
-  if (d.compact) {
-    // the new fruit cells also go into the record's slot list (duplicate draws collapse to one cell, one slot):
-    // the a-th distinct new cell takes the a-th free slot
-    const int fcap = d.fcap;
-    const uint32_t dup = __match_any_sync(FULL, mycell);
-    const bool adds = mycell >= 0 && (__ffs(dup) - 1) == (int)lane;
-    const uint32_t adders = __ballot_sync(FULL, adds);
-    const uint32_t free_lo = __ballot_sync(FULL, (int)lane < fcap && r.fruit[lane] == 0);              // slots 0..31
-    const uint32_t free_hi = __ballot_sync(FULL, (int)lane + 32 < fcap && r.fruit[lane + 32] == 0);    // slots 32..63
-    if (adds) {
-      const int a = __popc(adders & ((1u << lane) - 1u)), nlo = __popc(free_lo);
-      uint32_t slot = a < nlo ? __fns(free_lo, 0, a + 1) : __fns(free_hi, 0, a - nlo + 1);     // 0xffffffff: none left
-      if (a >= nlo && slot < 32u) slot += 32u;
-      if (slot < (uint32_t)fcap) r.fruit[slot] = (uint16_t)(mycell + 1);
-      else atomicOr(p.err, ERR_STATE);
-    }
-  }
+  if (d.compact) fruit_slots_add(r.fruit, d.fcap, mycell, p.err);
   __syncwarp();
 }
 
@@ -286,21 +250,7 @@ __device__ __noinline__ void reset_env_warp(const KParams& p, uint8_t* g, uint8_
   if (d.compact) for (int j = (int)lane; j < d.fcap; j += 32) r.fruit[j] = 0;
   // make_grid: walled empty box (core/grid_util.py:14-20), one grid row at a time so no division is needed --
   // or the handle's custom wall layout (snk_create_map), copied word by word from its L2-resident plane
-  if (p.base_grid) {                   // the handle's wall layout (walled box or custom map), 16 bytes per lane and trip
-    const uint4* const tpl = reinterpret_cast<const uint4*>(p.base_grid);
-    uint4* g4 = reinterpret_cast<uint4*>(r.grid);
-    const int n16 = d.off_c0 >> 4;
-    for (int j = (int)lane; j < n16; j += 128) {            // four L2 loads in flight per lane
-      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-      const uint4 a = __ldg(tpl + j);
-      const uint4 b = j + 32 < n16 ? __ldg(tpl + j + 32) : z, c = j + 64 < n16 ? __ldg(tpl + j + 64) : z;
-      const uint4 e = j + 96 < n16 ? __ldg(tpl + j + 96) : z;
-      g4[j] = a;
-      if (j + 32 < n16) g4[j + 32] = b;
-      if (j + 64 < n16) g4[j + 64] = c;
-      if (j + 96 < n16) g4[j + 96] = e;
-    }
-  } else if (p.wall_map) {
+  if (p.wall_map) {
     const uint32_t* const wm = p.wall_map;
     const int HW = d.HW, nfull = HW >> 2;
     uint32_t* gw = reinterpret_cast<uint32_t*>(r.grid);
