@@ -213,10 +213,15 @@ int snk_widen_bits_host(const uint8_t* bits_host, uint8_t* obs_host, size_t n_un
 
 /* ---- parity / checkpoint interface ---------------------------------------------------------- */
 
+/* The reference's env.grid / env.snakes[i] of every environment.  A handle with compact records (the default for
+ * warp-private tiles, frame stacks and large grids) keeps no grid in device memory: the grid
+ * returned here is rebuilt from the handle's wall layout, the record's fruit cells and the bodies -- which is exactly
+ * what the reference's grid holds after every step (snake_env.py:546-566 never leaves anything else behind). */
 int snk_get_state(snk_env* env, const snk_state_view* out, void* stream);
 /* Needs grid, alive, dir, cells(+max_cells), length, alive_counter, episode_length. Rebuilds the
  * body-direction plane, zeroes episode statistics, fills every frame-stack slot with the encoding
- * of the given grid.  obs_dev (may be NULL) receives that stacked observation. */
+ * of the given grid.  obs_dev (may be NULL) receives that stacked observation.  Compact records take the fruit cells
+ * from `grid` and check the rest of it against the wall layout and the given bodies (SNK_DEV_STATE otherwise). */
 int snk_set_state(snk_env* env, const snk_state_view* in, uint8_t* obs_dev, void* stream);
 
 /* Exact checkpoint / resume of a shard (the reference never saves env state; its trainers checkpoint only
