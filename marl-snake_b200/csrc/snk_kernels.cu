@@ -1,20 +1,23 @@
 // snk_kernels.cu -- sm_100a kernels of the batched Snake-v1 step path.
 //
-// A WARP owns a tile of 32/G consecutive environments, G = num_snakes rounded up to a power of two:
-// lane = (environment in tile, snake).  The tile's records (grid, body-direction plane, snake table,
-// counters, episode statistics) are contiguous in HBM; the warp stages them into its private slice of
-// shared memory with 128-bit coalesced loads, steps them there and writes them back the same way.
-// After the CTA-wide lookup-table build there is no block barrier: warps are independent, so one
-// warp's rule phase overlaps the other warps' observation stores.
+// A TILE is up to 32/G consecutive environments, G = num_snakes rounded up to a power of two, so that in the rule
+// phase lane = (environment in tile, snake).  The tile's records are contiguous in HBM; one elected thread stages them
+// into shared memory with a 1-D bulk copy (cp.async.bulk + mbarrier), the tile is stepped there and written back the
+// same way.  Two tile modes: warp-private (every warp owns a tile, no block barrier after the table copy: one warp's
+// rule phase overlaps the other warps' observation stores) and CTA-cooperative (one tile per CTA, warp 0 runs the
+// rules, then all warps share the tile's viewers).  Two record layouts: the whole working record in HBM, or the
+// compact one without the grid, which is then rebuilt in shared memory (expand_tile) from the handle's wall layout,
+// the record's fruit slots and the bodies spelled out by the direction plane.
 //
 //   rules    lanes = snakes: turn, head advance, __match_any_sync on target cells (head-on and arrival
-//            order), ballots for deaths / fruit cells / alive set, shuffles for kill attribution and the
-//            tail-growth rule, float64 reward, clear-then-write grid update      (step_group)
-//   rare     whole warp per environment: fruit respawn = k-th empty cell by ballot/popc rank-select;
+//            order), ballots for deaths / fruit cells / alive set, shared-memory scatter for kill credit, one more
+//            match for the tail-growth rule, float64 reward, clear-then-write grid update      (step_group)
+//   rare     whole warp per environment: fruit respawn = k-th empty cell by word-wise rank-select;
 //            auto-reset = spawn picks + paint-and-vote overlap test + fruit seeding
 //   encode   whole warp per (environment, viewer): two crop cells per lane -> LUT -> one 128-bit
-//            streaming store (frame_stack 1); channel-bit frames staged in output order and expanded
-//            with flat 128-bit stores (frame_stack > 1)
+//            streaming store (frame_stack 1; register / direct / padded-plane / table flavours); channel-bit frames
+//            staged in output order and expanded with flat 128-bit stores (frame_stack > 1); optionally the channel
+//            bits themselves instead of / beside the NHWC bytes
 //
 // Reference: SnakeEnv.step / reset / _encode (envs/snake_env.py:301-414, 131-159, 474-519) and the
 // vector worker's auto-reset (wrappers.py:138-146).
