@@ -8,4 +8,11 @@ echo "#   DMUL/DADD without DFMA = float64 reward in the reference's order, no L
 for op in UBLKCP SYNCS MATCH VOTE REDUX DMUL DADD DFMA LDL STL UTCHMMA UTCQMMA; do
   printf "# %-8s %s\n" $op $(cuobjdump -sass $so | grep -cE "^\s+/\*[0-9a-f]{4}\*/\s+(@!?U?P[0-9T] )?$op(\.|\s|;)")
 done
+echo "# per benchmarked instance (cuobjdump -res-usage: registers, stack) and its local-memory instructions:"
+for inst in "Li4ELi20ELi11ELi11ELi1ELb0ELi1ELi3E cfg5_bench_line" "Li4ELi20ELi11ELi11ELi1ELb0ELi1ELi0E cfg5_shard" "Li4ELi20ELi20ELi20ELi1ELb1ELi2ELi0E cfg2" "Li4ELi20ELi11ELi11ELi4ELb1ELi0ELi0E cfg3" "Li16ELi64ELi15ELi15ELi1ELb1ELi3ELi0E cfg4"; do
+  set -- $inst
+  res=$(cuobjdump -res-usage $so 2>/dev/null | grep -A1 "$1" | grep -oE "REG:[0-9]+ STACK:[0-9]+")
+  loc=$(cuobjdump -sass -fun "_ZN3snk15snk_tile_kernelI${1}EvNS_7KParamsE" $so 2>/dev/null | grep -cE "\b(LDL|STL)\b")
+  printf "#   %-16s %-22s LDL+STL %s\n" $2 "$res" $loc
+done
 cuobjdump -sass $so | grep -oE "^\s+/\*[0-9a-f]{4}\*/\s+(@!?U?P[0-9T] )?[A-Z][A-Z0-9_.]+" | awk '{print $NF}' | sed 's/\..*//' | sort | uniq -c | sort -rn
