@@ -112,8 +112,10 @@ def reference_arm(args):
         'impl': 'reference', 'metric': 'agent_steps_per_sec', 'value': val, 'unit': 'agent-steps/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'envs_per_gpu': pool.procs, 'global_envs': pool.procs,
-                   'env_steps_per_bench_step': chunk},
+        # the arm's config: the same workload; each bench step is a bounded SAMPLE of it (one env per host core)
+        'config': {'workload': WORKLOAD, 'envs_per_gpu': args.envs_per_gpu, 'global_envs': args.envs_per_gpu * args.gpus,
+                   'parallelism': f'env-shard x{args.gpus}',
+                   'sample_envs': pool.procs, 'env_steps_per_bench_step': chunk},
         'cpu_baseline': {'value': val, 'unit': 'agent-steps/s', 'cores': pool.procs, 'kind': kind, 'sample': sample},
         'e2e': {'value': val, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}
