@@ -197,7 +197,11 @@ static int create_impl(const snk_config* c, const uint8_t* walls_host, snk_env**
   // With compact records (profiles/r02_ab_compact*.txt) warp-private tiles already win from ~6 000 tiles on:
   // 65 536 envs of the cfg5 shape 0.057 ms against 0.061 ms cooperative, 131 072 envs 0.097 against 0.114 ms.
   int coop = env_int("SNK_COOP", -1);
-  if (coop < 0) coop = (tiles_full < 148 * 40 || (size_t)EPW_full * d.rec_bytes > 8 * 1024 || d.fs > 1) ? 1 : 0;
+  // Windows of 128..255 cells have their fast encode (padded planes) only in cooperative tiles: a 32x32 / 8-snake /
+  // vision-7 batch runs 0.101 ms cooperative against 0.119 ms warp-private at 32 768 envs, 0.70 against 0.78 ms at
+  // 262 144 (profiles/r02_ab_shapes.txt).
+  if (coop < 0) coop = (tiles_full < 148 * 40 || (size_t)EPW_full * d.rec_bytes > 8 * 1024 || d.fs > 1 ||
+                        encode_flavour(d, true) == ENC_PAD) ? 1 : 0;
   // Compact records (the grid is rebuilt in shared memory from walls + fruit slots + bodies instead of being read
   // from and written to HBM) save 2 * H * W bytes per env-step and cost the rule warp a walk along every live body.
   // That pays wherever bytes bound the step: warp-private tiles (cfg5 0.855 -> 0.769 ms), frame stacks (cfg3 0.207 ->

@@ -36,6 +36,10 @@ CONFIGS = {
     'cfg5_512k': dict(num_envs=524288, vision_range=5, **BASE),
     'cfg5_full': dict(num_envs=1048576, vision_range=5, **BASE),
     'cfg5_n': dict(num_envs=int(os.environ.get('BENCH_N', 65536)), vision_range=5, **BASE),     # size sweeps
+    # other tile geometries (32 / 16 / 4 environments per tile), for the tile-mode heuristics
+    'solo_n': dict(num_envs=int(os.environ.get('BENCH_N', 65536)), height=9, width=9, num_snakes=1, snake_length=3, vision_range=2),
+    'duo_n': dict(num_envs=int(os.environ.get('BENCH_N', 65536)), height=12, width=12, num_snakes=2, snake_length=3),
+    'wide8_n': dict(num_envs=int(os.environ.get('BENCH_N', 65536)), height=32, width=32, num_snakes=8, snake_length=4, vision_range=7),
 }
 DEFAULT_STEPS = {'cfg2': 2000}
 
