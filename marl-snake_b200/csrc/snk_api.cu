@@ -84,7 +84,8 @@ struct snk_env {
   WidenPool* pool = nullptr;
   cudaEvent_t chunk_ev[XFER_MAX_CHUNKS] = {};
   int n_chunk_ev = 0;
-  int force_generic = 0, coop = 0, lut_dual = 0, use_tma = 0, enc_flavour = 0, pdl = 1, bigreg = 0;
+  int force_generic = 0, coop = 0, lut_dual = 0, use_tma = 0, enc_flavour = 0, pdl = 1, bigreg = 0, l2_keep = 0;
+  float l2_keep_frac = 1.0f;
   bool was_reset = false;
 };
 
@@ -107,7 +108,7 @@ static KParams base_params(const snk_env* h) {
   p.force_generic = h->force_generic;
   p.enc_blob = h->enc_blob; p.enc_blob_bytes = h->enc_blob_bytes; p.enc_tab_off = h->enc_tab_off; p.use_tab = h->use_tab;
   p.enc_lutb_off = h->enc_lutb_off;
-  p.lut_dual = h->lut_dual; p.coop = h->coop; p.use_tma = h->use_tma; p.pdl = h->pdl; p.bigreg = h->bigreg;
+  p.lut_dual = h->lut_dual; p.coop = h->coop; p.use_tma = h->use_tma; p.pdl = h->pdl; p.bigreg = h->bigreg; p.l2_keep = h->l2_keep; p.l2_keep_frac = h->l2_keep_frac;
   p.T = 1;
   p.enc_flavour = h->enc_flavour;
   p.enc_copy_bytes = (h->enc_flavour == ENC_LEGACY) ? h->enc_blob_bytes : h->enc_tab_off;     // LUT only
@@ -259,6 +260,8 @@ static int create_impl(const snk_config* c, const uint8_t* walls_host, snk_env**
   h->use_tma = env_int("SNK_TMA", 1);
   h->pdl = env_int("SNK_PDL", 1);
   h->small_zero_copy = env_int("SNK_SMALL_ZEROCOPY", 1);
+  h->l2_keep = env_int("SNK_L2_KEEP", d.fs > 1 ? 1 : 0);
+  h->l2_keep_frac = (float)env_int("SNK_L2_KEEP_PCT", 100) / 100.0f;
   {
     // the uncapped-register instance of the warp-private kernel once the batch is many waves deep
     const int64_t tiles = ((int64_t)d.N + EPW - 1) / EPW;

@@ -448,6 +448,24 @@ __device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
     }
   }
 }
+// L2 eviction priority for the record tiles (SNK_L2_KEEP): the records are re-read every step while the observation
+// block streams through once, so the record lines are asked to stay (evict_last) under the evict-first observation stores.
+// Measured (profiles/r02_ab_l2keep*.txt): cfg3 0.2028 -> 0.1960 ms (its 16 MB of records then never leave the L2), cfg5
+// unchanged (252 MB of records against 126 MB of L2), cfg4 and the cfg5 shard 1.5-2 % slower; on by default with a
+// frame stack only.  The same hint on the frame-history load did not pay (0.1987 ms).
+__device__ __forceinline__ uint64_t l2_policy_evict_last(float fraction) {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, %1;" : "=l"(pol) : "f"(fraction));
+  return pol;
+}
+__device__ __forceinline__ void bulk_load_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_store_hint(void* dst, uint32_t src, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src), "r"(bytes), "l"(pol) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
@@ -1262,7 +1280,8 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
       mbar_init(mbar, 1);
       if (ne > 0) {
         mbar_expect_tx(mbar, tile_load_bytes + grid_load_bytes + hist_load_bytes + (blob_by_tma ? (uint32_t)p.enc_copy_bytes : 0u));
-        bulk_load(rec32, p.recs + (size_t)e0 * d.hbm_rec_bytes, tile_load_bytes, mbar);
+        if (p.l2_keep) bulk_load_hint(rec32, p.recs + (size_t)e0 * d.hbm_rec_bytes, tile_load_bytes, mbar, l2_policy_evict_last(p.l2_keep_frac));
+        else bulk_load(rec32, p.recs + (size_t)e0 * d.hbm_rec_bytes, tile_load_bytes, mbar);
         if (grid_load_bytes) bulk_load((uint32_t)__cvta_generic_to_shared(s_rec), p.base_grid, grid_load_bytes, mbar);
         if (hist_load_bytes) bulk_load((uint32_t)__cvta_generic_to_shared(s_hist), p.hist + (size_t)e0 * d.hist_env_bytes, hist_load_bytes, mbar);
         if (blob_by_tma) bulk_load((uint32_t)__cvta_generic_to_shared(s_lut), p.enc_blob, (uint32_t)p.enc_copy_bytes, mbar);
@@ -1369,7 +1388,10 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
     //      asynchronously under the encode; its issuer waits for the shared-memory reads before exiting.
     if (last) {
       if (p.use_tma) {
-        if (elected) bulk_store(p.recs + (size_t)e0 * d.hbm_rec_bytes, rec32, tile_load_bytes);
+        if (elected) {
+          if (p.l2_keep) bulk_store_hint(p.recs + (size_t)e0 * d.hbm_rec_bytes, rec32, tile_load_bytes, l2_policy_evict_last(p.l2_keep_frac));
+          else bulk_store(p.recs + (size_t)e0 * d.hbm_rec_bytes, rec32, tile_load_bytes);
+        }
       } else {
         uint4* dst = reinterpret_cast<uint4*>(p.recs + (size_t)e0 * d.hbm_rec_bytes);
         const uint4* src = reinterpret_cast<const uint4*>(s_c);
@@ -1489,7 +1511,8 @@ snk_tile_kernel(const __grid_constant__ KParams p) {
   // ---- write the records back: shared -> HBM
   if (p.use_tma) {
     if (elected) {
-      bulk_store(p.recs + (size_t)e0 * d.hbm_rec_bytes, rec32, tile_load_bytes);
+      if (p.l2_keep) bulk_store_hint(p.recs + (size_t)e0 * d.hbm_rec_bytes, rec32, tile_load_bytes, l2_policy_evict_last(p.l2_keep_frac));
+      else bulk_store(p.recs + (size_t)e0 * d.hbm_rec_bytes, rec32, tile_load_bytes);
       bulk_store_wait_read();
     }
   } else {

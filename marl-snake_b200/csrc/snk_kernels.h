@@ -70,6 +70,8 @@ struct KParams {
   uint32_t inv_grid_words;     // ENC_PAD: ceil(2^32 / (H*W/4)) and ceil(2^32 / (W/4)): exact division of word indices
   uint32_t inv_row_words;      //          below 2^16 by a multiply-high
   int32_t pdl;                 // launch with programmatic stream serialization (SNK_PDL=0 switches it off)
+  int32_t l2_keep;             // record tiles are loaded and stored with an L2 evict_last hint (SNK_L2_KEEP)
+  float l2_keep_frac;          //   fraction of those lines the policy applies to
   int32_t bigreg;              // warp-private tiles, batch many waves deep: run the instance compiled without a register cap
   int32_t T;                   // steps per launch (snk_step_many; frame_stack 1).  actions / rewards / dones / extras are
   int32_t obs_every_step;      //   [T, ...]; obs / bits are [T, ...] when obs_every_step, else the last step's block only

@@ -362,7 +362,8 @@ def test_gpu_tile_modes(monkeypatch, coop, kw, N, compact):
 @pytest.mark.parametrize('knob', ['SNK_TMA=0', 'SNK_ENC_LEGACY=1', 'SNK_NO_TABLE=1', 'SNK_TMA=0,SNK_COOP=0', 'SNK_NO_DIG=1',
                                   'SNK_NO_DIG=1,SNK_COOP=0', 'SNK_NO_COMPACT=1', 'SNK_COMPACT=0,SNK_COOP=0',
                                   'SNK_COMPACT=1,SNK_COOP=1', 'SNK_COMPACT=1,SNK_TMA=0', 'SNK_COMPACT=1,SNK_TMA=0,SNK_COOP=0',
-                                  'SNK_COMPACT=0,SNK_TMA=0', 'SNK_COMPACT=1,SNK_ENC_LEGACY=1', 'SNK_BIGREG_TILES=1,SNK_COOP=0'])
+                                  'SNK_COMPACT=0,SNK_TMA=0', 'SNK_COMPACT=1,SNK_ENC_LEGACY=1', 'SNK_BIGREG_TILES=1,SNK_COOP=0',
+                                  'SNK_L2_KEEP=1', 'SNK_L2_KEEP=0', 'SNK_L2_KEEP=1,SNK_COOP=0'])
 @pytest.mark.parametrize('kw,N', [
     (dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5), 1500),
     (dict(height=20, width=20, num_snakes=4, snake_length=3, vision_range=5, frame_stack=4), 300),
